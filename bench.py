@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- mel-frames/sec through Text2Mel (AR, 210 steps) + SSRN on N B200s.
+
+Workload (BASELINE.json config 4 per-GPU shard; config.workload names it): every rank
+synthesises `--batch` (default 32) synthetic 100-character utterances: TextEnc once, 210
+autoregressive steps replayed from a CUDA graph, SSRN mel->linear; rank 0 then receives
+the finished spectrograms of all ranks in ONE NCCL gather.  A "step" is one such pass.
+`value` = N * batch * 210 * K / time, inputs resident in HBM; `e2e` = same metric through
+dctts_synthesize_host (host buffers, H2D + D2H inside the timed region).
+
+`--impl reference` times the oracle restatement of the reference's own schedule
+(synthesize.py:45-57: one full-graph pass per mel frame, then SSRN) on the host cores --
+the TF1 reference itself cannot run here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mel_frames_per_sec"
+UNIT = "mel-frames/s"
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm_gbs=p["hbm_gbs"], tf=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained"), src="measured")
+    except Exception:
+        return dict(hbm_gbs=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")   # B200_PROFILING.md
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# ------------------------------------------------------------------------------ reference arm
+def cpu_reference(passes, B=1, n_chars=100, threads=None):
+    """Oracle restatement of the reference schedule on the host cores: `passes` full-graph
+    Text2Mel passes (each yields ONE mel frame per utterance: synthesize.py:48-53) and one
+    SSRN pass, extrapolated to a 210-frame utterance."""
+    import numpy as np
+    import torch
+    from dc_tts_b200.hyperparams import Hyperparams as hp
+    from dc_tts_b200.params import init_params, synthetic_text
+    from oracle import ref_torch as rt
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    P = {k: torch.from_numpy(v) for k, v in init_params(0, "perturbed").items()}
+    L = synthetic_text(B, n_chars, seed=0)
+    Y = torch.zeros((B, hp.max_T, hp.n_mels))
+    pma = torch.zeros((B,), dtype=torch.int64)
+    with torch.no_grad():
+        rt.text2mel_forward(P, L, Y, pma)                      # warm-up
+        t0 = time.perf_counter()
+        for j in range(passes):
+            o = rt.text2mel_forward(P, L, Y, pma)
+            Y[:, j] = o["Y"][:, j]; pma = o["max_attentions"][:, j]
+        t_pass = (time.perf_counter() - t0) / passes
+        t0 = time.perf_counter()
+        rt.SSRN(P, Y)
+        t_ssrn = time.perf_counter() - t0
+    t_utt = hp.max_T * t_pass + t_ssrn
+    return dict(value=B * hp.max_T / t_utt, t_pass=t_pass, t_ssrn=t_ssrn, cores=threads,
+                sample="B=%d: %d of 210 full-graph Text2Mel passes (%.3f s each) + 1 SSRN pass (%.3f s), "
+                       "extrapolated to 210 passes" % (B, passes, t_pass, t_ssrn))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps_passes = 3                                           # full-graph passes per bench "step"
+    t0 = time.perf_counter()
+    r = cpu_reference(passes=max(1, (args.steps + args.warmup) * steps_passes))
+    wall = time.perf_counter() - t0
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * steps_passes * r["t_pass"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "TF1 reference cannot run (no TensorFlow; tf.contrib needs TF1/py<=3.7): timed the oracle "
+                    "restatement (torch-CPU fp32) of synthesize.py's own O(T^2) schedule; wall %.1f s" % wall}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE config 4 per-GPU shard: Text2Mel AR (210 steps, CUDA-graph loop) + SSRN, "
+                        "%d synthetic %d-char utterances per GPU, LJ hyper-parameters" % (args.batch, args.nchars),
+            "batch_per_gpu": args.batch, "global_batch": args.batch * world, "max_N": 180, "max_T": 210,
+            "parallelism": "utterance-shard x%d + one NCCL gather of Z to rank 0" % world,
+            "l2": "flushed between timed steps (256 MiB write, untimed); per-step working set "
+                  "(weights 210 MB + activations) also exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------ B200 arm
+def run_b200(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dc_tts_b200.engine import Engine
+    from dc_tts_b200.hyperparams import Hyperparams as hp
+    from dc_tts_b200.parallel import gather_spectrograms
+    from dc_tts_b200.params import init_params, synthetic_text
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    eng = Engine(local_rank)
+    eng.load_params(init_params(0, "perturbed"))
+    if args.tensor_path is not None:
+        eng.set_tensor_path(args.tensor_path)
+    B, T, F = args.batch, hp.max_T, 1 + hp.n_fft // 2
+    eng.reserve(B)
+    L_host = torch.from_numpy(synthetic_text(B, args.nchars, seed=0, first_index=rank * B)).pin_memory()
+    L_dev = L_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    total = B * world
+
+    def step():
+        Y, _, _, _ = eng.text2mel_generate(L_dev)
+        _, Z = eng.ssrn(Y, want_logits=False)
+        if world > 1:
+            Z = gather_spectrograms(Z, total, dst=0)
+        return Y, Z
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for k in range(args.steps):
+        flush.fill_(k & 0xff)                      # L2 flush, outside the per-step event pair
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = total * T * args.steps / (ms / 1e3)
+
+    # ---- e2e: public host-buffer API, H2D + D2H inside the timed region (per rank, max over ranks)
+    Yh = torch.empty((B, T, hp.n_mels)).pin_memory()
+    Zh = torch.empty((B, T * hp.r, F)).pin_memory()
+    eng.synthesize_host(L_host, Yh, Zh)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.synthesize_host(L_host, Yh, Zh)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total * T * e2e_steps / float(te.item())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        # ---- roofline of the dominant kernel: the SSRN HC_11 conv-GEMM (C=1024, k=3; 27 % of SSRN FLOPs)
+        rows = B * T * hp.r
+        kms = eng.bench_block("SSRN/HC_11", B, T * hp.r, iters=5, warmup=2)
+        flops = 2.0 * rows * 3 * 1024 * 2048
+        ach = flops / (kms[0] * 1e-3) / 1e12
+        roof = {"kernel": "SSRN/HC_11 conv-GEMM (M=%d, K=3x1024, N=2048)" % rows, "bound": "tensor",
+                "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
+                "traffic": None, "peak_source": peaks["src"] + " bf16 dense (burst)",
+                "kernel_ms": kms[0], "epilogue_ms": kms[1:],
+                "note": "algorithmic FLOPs 2*M*K*N / CUDA-event time of that launch"}
+        # ---- single-utterance latency (BASELINE config 2 + SSRN): RTF target >= 200x
+        L1 = L_dev[:1].contiguous()
+        for _ in range(2):
+            Y1, _, _, _ = eng.text2mel_generate(L1); eng.ssrn(Y1, want_logits=False)
+        torch.cuda.synchronize()
+        a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record(); Y1, _, _, _ = eng.text2mel_generate(L1); b.record(); eng.ssrn(Y1, want_logits=False); c.record()
+        torch.cuda.synchronize()
+        t2m_ms, ssrn_ms = a.elapsed_time(b), b.elapsed_time(c)
+        audio_s = T * hp.r * hp.hop_length / float(hp.sr)
+        single = {"text2mel_ms": t2m_ms, "ssrn_ms": ssrn_ms, "rtf_x_realtime": audio_s / ((t2m_ms + ssrn_ms) / 1e3)}
+        cpu = cpu_reference(passes=args.cpu_passes) if args.cpu_passes > 0 else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world),
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(L_host.numel() * 4),
+                        "d2h_bytes_per_step": int((Yh.numel() + Zh.numel()) * 4), "steps": e2e_steps,
+                        "api": "dctts_synthesize_host (pinned host buffers)"},
+                "roofline": roof, "single_utterance": single}
+        if cpu:
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
+                                    "sample": cpu["sample"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--nchars", type=int, default=100)
+    ap.add_argument("--cpu-passes", type=int, default=12, help="full-graph passes of the CPU baseline sample (0 = skip)")
+    ap.add_argument("--tensor-path", type=int, default=None, choices=[0, 1])
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 400)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,889 @@
+// dctts_api.cu -- handle, parameter packing, network chains, AR decode engine and the
+// C-ABI of include/dctts.h.
+//
+// Reference mapping (files under /root/reference):
+//   layer tables ............ networks.py:23-68 (TextEnc), :81-124 (AudioEnc),
+//                             :166-209 (AudioDec), :223-290 (SSRN)
+//   block semantics ......... modules.py:91-141 (conv1d), :143-197 (hc), :199-247 (conv1d_transpose)
+//   graph wiring / shift .... train.py:48-68, :74-77
+//   autoregressive loop ..... synthesize.py:45-57
+#include "../../include/dctts.h"
+#include "kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace dctts;
+
+#define CUDA_CHECK(expr)                                                                     \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            char _buf[512];                                                                  \
+            snprintf(_buf, sizeof(_buf), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                    \
+            throw std::runtime_error(_buf);                                                  \
+        }                                                                                    \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                   \
+    do {                                                     \
+        if (!(cond)) throw std::runtime_error(std::string(msg)); \
+    } while (0)
+
+namespace {
+
+std::string g_create_error;
+
+inline int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+enum Kind { K_C = 0, K_HC = 1, K_D = 2 };
+
+struct LayerDev {
+    std::string scope;   // full scope, e.g. "SSRN/HC_5"
+    int kind = K_C;
+    int cin = 0, cout = 0, size = 1, rate = 1;
+    bool causal = false;
+    int act = 0;
+    int nconv = 0, ldw = 0;
+    float* W = nullptr;      // [size][cin][ldw]
+    float* bias = nullptr;   // [ldw]
+    float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+};
+
+struct HostParam {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    void ensure(size_t n) {
+        if (n <= bytes) return;
+        if (p) CUDA_CHECK(cudaFree(p));
+        p = nullptr; bytes = 0;
+        CUDA_CHECK(cudaMalloc(&p, n));
+        bytes = n;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct dctts_handle_s {
+    dctts_hparams hp{};
+    int device = 0;
+    int F = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    std::map<std::string, HostParam> staged;
+    bool committed = false;
+    int64_t n_params = 0;
+
+    std::vector<LayerDev> textenc, audioenc, audiodec, ssrn;
+    std::map<std::string, LayerDev*> by_scope;
+    std::map<std::string, float*> dev_vec;    // every committed variable (flat copy) by TF name
+    std::vector<void*> param_allocs;
+    float* embed_table = nullptr;
+
+    // workspace (sized for ws_B utterances)
+    int ws_B = 0;
+    DevBuf scratch, act0, act1;
+    DevBuf kv;                    // (B, N, 2d) TextEnc output
+    DevBuf ybuf;                  // (B, T, n_mels) generated mels
+    DevBuf rbuf;                  // (B, T, 2d)
+    std::vector<DevBuf> ae_out;   // AudioEnc per-layer outputs (B, T, d)
+    std::vector<DevBuf> ad_out;   // AudioDec per-layer outputs (B, T, d | n_mels)
+    DevBuf ad_sig;                // scratch for sigmoid(logits) in full-graph mode
+    DevBuf ibuf;                  // ints: j, p_cur[B], p_next[B], p_prev[B], p_hist[B*T]
+    DevBuf lbuf;                  // (B, N) ids staging for the host entry point
+    DevBuf zbuf;                  // (B, 4T, F) staging for the host entry point
+
+    // AR decode graph
+    cudaGraphExec_t ar_exec = nullptr;
+    int ar_B = 0;
+    int64_t ar_nodes = 0;
+
+    int tensor_path = 0;
+    int64_t launches = 0;
+
+    ~dctts_handle_s() {
+        if (ar_exec) cudaGraphExecDestroy(ar_exec);
+        for (void* p : param_allocs) cudaFree(p);
+        scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
+        rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
+        for (auto& b : ae_out) b.release();
+        for (auto& b : ad_out) b.release();
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+using H = dctts_handle_s;
+
+// ---------------------------------------------------------------------------- layer tables
+void add_layer(std::vector<LayerDev>& v, const std::string& net, int kind, int idx, int cin, int cout,
+               int size, int rate, bool causal, int act) {
+    LayerDev l;
+    const char* pre = kind == K_C ? "C_" : (kind == K_HC ? "HC_" : "D_");
+    l.scope = net + "/" + pre + std::to_string(idx);
+    l.kind = kind; l.cin = cin; l.cout = cout; l.size = size; l.rate = rate;
+    l.causal = causal; l.act = act;
+    l.nconv = (kind == K_HC) ? 2 * cout : cout;
+    l.ldw = roundup(l.nconv, 4);
+    v.push_back(l);
+}
+
+void build_tables(H* h) {
+    const dctts_hparams& hp = h->hp;
+    const int d = hp.d, d2 = 2 * hp.d, c = hp.c, F = h->F;
+    int i;
+    // TextEnc, networks.py:23-68
+    {
+        auto& v = h->textenc; const std::string n = "Text2Mel/TextEnc"; i = 2;
+        add_layer(v, n, K_C, i++, hp.e, d2, 1, 1, false, 1);
+        add_layer(v, n, K_C, i++, d2, d2, 1, 1, false, 0);
+        for (int rep = 0; rep < 2; ++rep)
+            for (int j = 0, r = 1; j < 4; ++j, r *= 3) add_layer(v, n, K_HC, i++, d2, d2, 3, r, false, 0);
+        for (int rep = 0; rep < 2; ++rep) add_layer(v, n, K_HC, i++, d2, d2, 3, 1, false, 0);
+        for (int rep = 0; rep < 2; ++rep) add_layer(v, n, K_HC, i++, d2, d2, 1, 1, false, 0);
+    }
+    // AudioEnc, networks.py:81-124
+    {
+        auto& v = h->audioenc; const std::string n = "Text2Mel/AudioEnc"; i = 1;
+        add_layer(v, n, K_C, i++, hp.n_mels, d, 1, 1, true, 1);
+        add_layer(v, n, K_C, i++, d, d, 1, 1, true, 1);
+        add_layer(v, n, K_C, i++, d, d, 1, 1, true, 0);
+        for (int rep = 0; rep < 2; ++rep)
+            for (int j = 0, r = 1; j < 4; ++j, r *= 3) add_layer(v, n, K_HC, i++, d, d, 3, r, true, 0);
+        for (int rep = 0; rep < 2; ++rep) add_layer(v, n, K_HC, i++, d, d, 3, 3, true, 0);
+    }
+    // AudioDec, networks.py:166-209
+    {
+        auto& v = h->audiodec; const std::string n = "Text2Mel/AudioDec"; i = 1;
+        add_layer(v, n, K_C, i++, d2, d, 1, 1, true, 0);
+        for (int j = 0, r = 1; j < 4; ++j, r *= 3) add_layer(v, n, K_HC, i++, d, d, 3, r, true, 0);
+        for (int rep = 0; rep < 2; ++rep) add_layer(v, n, K_HC, i++, d, d, 3, 1, true, 0);
+        for (int rep = 0; rep < 3; ++rep) add_layer(v, n, K_C, i++, d, d, 1, 1, true, 1);
+        add_layer(v, n, K_C, i++, d, hp.n_mels, 1, 1, true, 0);
+    }
+    // SSRN, networks.py:223-290
+    {
+        auto& v = h->ssrn; const std::string n = "SSRN"; i = 1;
+        add_layer(v, n, K_C, i++, hp.n_mels, c, 1, 1, false, 0);
+        for (int j = 0, r = 1; j < 2; ++j, r *= 3) add_layer(v, n, K_HC, i++, c, c, 3, r, false, 0);
+        for (int rep = 0; rep < 2; ++rep) {
+            add_layer(v, n, K_D, i++, c, c, 3, 1, false, 0);
+            for (int j = 0, r = 1; j < 2; ++j, r *= 3) add_layer(v, n, K_HC, i++, c, c, 3, r, false, 0);
+        }
+        add_layer(v, n, K_C, i++, c, 2 * c, 1, 1, false, 0);
+        for (int rep = 0; rep < 2; ++rep) add_layer(v, n, K_HC, i++, 2 * c, 2 * c, 3, 1, false, 0);
+        add_layer(v, n, K_C, i++, 2 * c, F, 1, 1, false, 0);
+        for (int rep = 0; rep < 2; ++rep) add_layer(v, n, K_C, i++, F, F, 1, 1, false, 1);
+        add_layer(v, n, K_C, i, F, F, 1, 1, false, 0);     // networks.py:285-290 (counter not advanced)
+    }
+    for (auto* vec : {&h->textenc, &h->audioenc, &h->audiodec, &h->ssrn})
+        for (auto& l : *vec) h->by_scope[l.scope] = &l;
+}
+
+// ---------------------------------------------------------------------------- parameters
+const HostParam& need(H* h, const std::string& name, std::vector<int64_t> shape) {
+    auto it = h->staged.find(name);
+    if (it == h->staged.end()) throw std::runtime_error("missing variable: " + name);
+    if (it->second.shape != shape) throw std::runtime_error("bad shape for variable: " + name);
+    return it->second;
+}
+
+float* upload(H* h, const std::vector<float>& v) {
+    float* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, v.size() * sizeof(float)));
+    h->param_allocs.push_back(p);
+    CUDA_CHECK(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return p;
+}
+
+float* upload_vec(H* h, const std::string& name, int n, int padded) {
+    const HostParam& p = need(h, name, {n});
+    std::vector<float> v(padded, 0.f);
+    std::copy(p.data.begin(), p.data.end(), v.begin());
+    float* d = upload(h, v);
+    h->dev_vec[name] = d;
+    h->n_params += n;
+    return d;
+}
+
+void commit_layer(H* h, LayerDev& l) {
+    const int k = l.size, cin = l.cin, nconv = l.nconv, ldw = l.ldw;
+    std::vector<float> W((size_t)k * cin * ldw, 0.f);
+    if (l.kind == K_D) {
+        // TF kernel [1, k, Cout, Cin] (modules.py:232-239) -> [tap][Cin][ldw]
+        const HostParam& p = need(h, l.scope + "/conv2d_transpose/kernel", {1, k, l.cout, cin});
+        for (int j = 0; j < k; ++j)
+            for (int co = 0; co < l.cout; ++co)
+                for (int ci = 0; ci < cin; ++ci)
+                    W[((size_t)j * cin + ci) * ldw + co] = p.data[((size_t)j * l.cout + co) * cin + ci];
+        l.bias = upload_vec(h, l.scope + "/conv2d_transpose/bias", l.cout, ldw);
+        h->n_params += (int64_t)k * l.cout * cin;
+    } else {
+        // TF kernel [k, Cin, Nconv] (modules.py:134,187) -> same order, rows padded to ldw
+        const HostParam& p = need(h, l.scope + "/conv1d/kernel", {k, cin, nconv});
+        for (size_t row = 0; row < (size_t)k * cin; ++row)
+            std::copy(p.data.begin() + row * nconv, p.data.begin() + (row + 1) * nconv, W.begin() + row * ldw);
+        l.bias = upload_vec(h, l.scope + "/conv1d/bias", nconv, ldw);
+        h->n_params += (int64_t)k * cin * nconv;
+    }
+    l.W = upload(h, W);
+    if (l.kind == K_HC) {
+        l.g1 = upload_vec(h, l.scope + "/H1/gamma", l.cout, l.cout);
+        l.b1 = upload_vec(h, l.scope + "/H1/beta", l.cout, l.cout);
+        l.g2 = upload_vec(h, l.scope + "/H2/gamma", l.cout, l.cout);
+        l.b2 = upload_vec(h, l.scope + "/H2/beta", l.cout, l.cout);
+    } else {
+        l.g1 = upload_vec(h, l.scope + "/normalize/gamma", l.cout, l.cout);
+        l.b1 = upload_vec(h, l.scope + "/normalize/beta", l.cout, l.cout);
+    }
+}
+
+void commit_params(H* h) {
+    REQUIRE(!h->committed, "parameters already committed on this handle");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->n_params = 0;
+    {
+        const std::string name = "Text2Mel/TextEnc/embed_1/lookup_table";
+        const HostParam& p = need(h, name, {h->hp.vocab_size, h->hp.e});
+        h->embed_table = upload(h, p.data);
+        h->dev_vec[name] = h->embed_table;
+        h->n_params += (int64_t)h->hp.vocab_size * h->hp.e;
+    }
+    size_t expected = 1;
+    for (auto* vec : {&h->textenc, &h->audioenc, &h->audiodec, &h->ssrn})
+        for (auto& l : *vec) { commit_layer(h, l); expected += (l.kind == K_HC) ? 6 : 4; }
+    if (h->staged.size() != expected) {
+        for (auto& kvp : h->staged) {
+            const std::string& n = kvp.first;
+            bool known = h->dev_vec.count(n) || n.find("/kernel") != std::string::npos;
+            if (!known) throw std::runtime_error("unknown variable staged: " + n);
+        }
+        throw std::runtime_error("staged variable count does not match the path's variable set");
+    }
+    h->staged.clear();
+    h->committed = true;
+}
+
+// ---------------------------------------------------------------------------- workspace
+void ensure_ws(H* h, int B) {
+    if (B <= h->ws_B) return;
+    const dctts_hparams& hp = h->hp;
+    const int T = hp.max_T, N = hp.max_N, d = hp.d, F = h->F;
+    const size_t rows_ssrn = (size_t)B * T * hp.r;
+    // invalidate anything that baked pointers
+    if (h->ar_exec) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    const size_t ld_scr = (size_t)roundup(std::max(std::max(4 * hp.c, F), 4 * d), 4);
+    h->scratch.ensure(rows_ssrn * ld_scr * sizeof(float));
+    const size_t ld_act = (size_t)roundup(std::max(std::max(2 * hp.c, F), 2 * d), 4);
+    h->act0.ensure(rows_ssrn * ld_act * sizeof(float));
+    h->act1.ensure(rows_ssrn * ld_act * sizeof(float));
+    h->kv.ensure((size_t)B * N * 2 * d * sizeof(float));
+    h->ybuf.ensure((size_t)B * T * hp.n_mels * sizeof(float));
+    h->rbuf.ensure((size_t)B * T * 2 * d * sizeof(float));
+    h->ad_sig.ensure((size_t)B * T * hp.n_mels * sizeof(float));
+    h->ae_out.resize(h->audioenc.size());
+    for (size_t i = 0; i < h->audioenc.size(); ++i)
+        h->ae_out[i].ensure((size_t)B * T * h->audioenc[i].cout * sizeof(float));
+    h->ad_out.resize(h->audiodec.size());
+    for (size_t i = 0; i < h->audiodec.size(); ++i)
+        h->ad_out[i].ensure((size_t)B * T * h->audiodec[i].cout * sizeof(float));
+    h->ibuf.ensure((size_t)(4 + 3 * B + (size_t)B * T) * sizeof(int));
+    h->lbuf.ensure((size_t)B * N * sizeof(int));
+    h->ws_B = B;
+}
+
+struct IntBufs { int *j, *p_cur, *p_next, *p_prev, *p_hist; };
+IntBufs ints(H* h) {
+    int* base = h->ibuf.as<int>();
+    IntBufs r;
+    r.j = base; r.p_cur = base + 4; r.p_next = r.p_cur + h->ws_B; r.p_prev = r.p_next + h->ws_B;
+    r.p_hist = r.p_prev + h->ws_B;
+    return r;
+}
+
+// ---------------------------------------------------------------------------- block runners
+struct Launch {
+    H* h; cudaStream_t s;
+    std::vector<cudaEvent_t>* evs = nullptr;     // profile mode: one event after every kernel
+    void count(int n = 1) {
+        h->launches += n;
+        if (evs) {
+            cudaEvent_t e;
+            CUDA_CHECK(cudaEventCreate(&e));
+            CUDA_CHECK(cudaEventRecord(e, s));
+            evs->push_back(e);
+        }
+    }
+};
+
+// conv (+bias) into scratch, then the LN / highway epilogue.  `extra_shift` moves every tap
+// (AudioEnc's first block reads the mel buffer one frame back: train.py:51).
+void run_block(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
+               const float* X, int ldx, RowWin win, float* out, int ldo, float* out2, int ldo2,
+               int extra_shift = 0) {
+    H* h = lc.h;
+    REQUIRE(l.kind != K_D, "run_block: transposed conv must use run_deconv");
+    ConvArgs c{};
+    c.X = X; c.ldx = ldx; c.Y = h->scratch.as<float>(); c.ldy = l.ldw; c.bias = l.bias;
+    c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
+    c.ntaps = l.size;
+    const int tot = (l.size - 1) * rate;
+    const int left = causal ? tot : tot / 2;
+    for (int j = 0; j < l.size; ++j) {
+        c.taps[j].W = l.W + (size_t)j * l.cin * l.ldw;
+        c.taps[j].shift = j * rate - left + extra_shift;
+    }
+    c.win = win; c.Lout = win.L; c.ostride = 1; c.ooff = 0;
+    launch_conv_gemm(c, lc.s); lc.count();
+
+    LnArgs n{};
+    n.Y = c.Y; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2;
+    n.X = X; n.ldx = ldx; n.out = out; n.ldo = ldo; n.out2 = out2; n.ldo2 = ldo2;
+    n.C = l.cout; n.mode = (l.kind == K_HC) ? 1 : 0; n.act = act; n.win = win;
+    launch_ln_rows(n, lc.s); lc.count();
+}
+
+// stride-2 transposed conv (modules.py:232-239): out[2t] = W0 x[t] + W2 x[t-1], out[2t+1] = W1 x[t].
+void run_deconv(Launch& lc, const LayerDev& l, const float* X, int ldx, int B, int L, float* out, int ldo) {
+    H* h = lc.h;
+    ConvArgs c{};
+    c.X = X; c.ldx = ldx; c.Y = h->scratch.as<float>(); c.ldy = l.ldw; c.bias = l.bias;
+    c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
+    c.win = RowWin{B, L, L, nullptr}; c.Lout = 2 * L; c.ostride = 2;
+    const size_t tapsz = (size_t)l.cin * l.ldw;
+    c.ntaps = 2; c.taps[0] = ConvTap{l.W + 0 * tapsz, 0}; c.taps[1] = ConvTap{l.W + 2 * tapsz, -1}; c.ooff = 0;
+    launch_conv_gemm(c, lc.s); lc.count();
+    c.ntaps = 1; c.taps[0] = ConvTap{l.W + 1 * tapsz, 0}; c.ooff = 1;
+    launch_conv_gemm(c, lc.s); lc.count();
+    LnArgs n{};
+    n.Y = c.Y; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.out = out; n.ldo = ldo;
+    n.C = l.cout; n.mode = 0; n.act = 0; n.win = RowWin{B, 2 * L, 2 * L, nullptr};
+    launch_ln_rows(n, lc.s); lc.count();
+}
+
+// A whole chain over full sequences, ping-ponging act0/act1; the last block writes
+// `out` (dense, ld = its cout) and optionally sigmoid(out) into out_sig.
+void run_chain_full(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
+                    float* out, float* out_sig) {
+    H* h = lc.h;
+    const float* cur = X; int ld = ldx; int len = L;
+    float* bufs[2] = {h->act0.as<float>(), h->act1.as<float>()};
+    int which = 0;
+    for (size_t i = 0; i < net.size(); ++i) {
+        const LayerDev& l = net[i];
+        const bool last = (i + 1 == net.size());
+        float* dst = last ? out : bufs[which];
+        const int ldo = last ? l.cout : roundup(l.cout, 4);
+        if (last && !dst) { dst = bufs[which]; }            // logits not requested: park them
+        if (l.kind == K_D) {
+            run_deconv(lc, l, cur, ld, B, len, dst, ldo);
+            len *= 2;
+        } else {
+            run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, len, len, nullptr}, dst, ldo,
+                      last ? out_sig : nullptr, l.cout);
+        }
+        cur = dst; ld = ldo; which ^= 1;
+    }
+}
+
+void run_attention(Launch& lc, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
+                   RowWin win, int N, const int* pma, float* R, float* align, long long* maxatt,
+                   int* p_next, int* p_hist) {
+    H* h = lc.h;
+    REQUIRE(N <= 192, "attention: N exceeds the kernel's key capacity (192)");
+    REQUIRE(h->hp.d <= 256, "attention: d exceeds 256");
+    AttnArgs a{};
+    a.Q = Q; a.ldq = ldq; a.K = K; a.ldk = ldk; a.V = V; a.ldv = ldv;
+    a.Rout = R; a.ldr = 2 * h->hp.d; a.align = align; a.maxatt = maxatt; a.pma = pma;
+    a.p_next = p_next; a.p_hist = p_hist; a.N = N; a.d = h->hp.d; a.win_size = h->hp.attention_win_size;
+    a.win = win;
+    launch_attention(a, lc.s); lc.count();
+}
+
+void run_textenc(Launch& lc, const int* L, int B, float* kv_out /* (B,N,2d) */) {
+    H* h = lc.h;
+    const int N = h->hp.max_N;
+    float* emb = h->act1.as<float>();
+    // park the embedding at the far end of act1 so the ping-pong (which starts on act0) never
+    // overwrites it before the first block has consumed it
+    launch_embed(L, h->embed_table, emb, B * N, h->hp.e, lc.s); lc.count();
+    // first block reads act1 and writes act0, and so on
+    run_chain_full(lc, h->textenc, emb, h->hp.e, B, N, kv_out, nullptr);
+}
+
+// Receptive-field pyramid of AudioDec for ONE new frame: number of
+// trailing rows each block must (re)compute at every AR step.
+std::vector<int> audiodec_rows(const std::vector<LayerDev>& net, int T) {
+    std::vector<int> rows(net.size(), 1);
+    int need = 1;   // rows of this layer's OUTPUT needed
+    for (int i = (int)net.size() - 1; i >= 0; --i) {
+        rows[i] = std::min(need, T);
+        need += (net[i].size - 1) * net[i].rate;    // rows of its input needed
+    }
+    return rows;
+}
+
+// One AR step (synthesize.py:48-54 restated incrementally, exact w.r.t. the reference's
+// full recompute): AudioEnc row j, attention over the AudioDec receptive field under the
+// CURRENT window, AudioDec pyramid, Y[j] = sigmoid(logits[j]), p <- argmax of row j, j <- j+1.
+void run_ar_step(Launch& lc, int B) {
+    H* h = lc.h;
+    const dctts_hparams& hp = h->hp;
+    const int T = hp.max_T, N = hp.max_N, d = hp.d;
+    IntBufs ib = ints(h);
+    // AudioEnc: one new row per utterance; first block reads Y[j-1] (train.py:51)
+    const float* cur = h->ybuf.as<float>(); int ld = hp.n_mels;
+    for (size_t i = 0; i < h->audioenc.size(); ++i) {
+        const LayerDev& l = h->audioenc[i];
+        float* dst = h->ae_out[i].as<float>();
+        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, 1, ib.j}, dst, l.cout, nullptr, 0,
+                  i == 0 ? -1 : 0);
+        cur = dst; ld = l.cout;
+    }
+    const float* Q = cur;
+    std::vector<int> rows = audiodec_rows(h->audiodec, T);
+    const int att_rows = std::min(T, rows[0] + (h->audiodec[0].size - 1) * h->audiodec[0].rate);
+    const float* K = h->kv.as<float>();
+    run_attention(lc, Q, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, att_rows, ib.j}, N, ib.p_cur,
+                  h->rbuf.as<float>(), nullptr, nullptr, ib.p_next, ib.p_hist);
+    cur = h->rbuf.as<float>(); ld = 2 * d;
+    for (size_t i = 0; i < h->audiodec.size(); ++i) {
+        const LayerDev& l = h->audiodec[i];
+        const bool last = (i + 1 == h->audiodec.size());
+        float* dst = h->ad_out[i].as<float>();
+        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, rows[i], ib.j}, dst, l.cout,
+                  last ? h->ybuf.as<float>() : nullptr, hp.n_mels);
+        cur = dst; ld = l.cout;
+    }
+    launch_ar_advance(ib.p_cur, ib.p_next, ib.j, B, lc.s); lc.count();
+    // keep the window used by this step for the optional final alignment pass
+}
+
+void build_ar_graph(H* h, int B) {
+    if (h->ar_exec && h->ar_B == B) return;
+    if (h->ar_exec) { cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    cudaGraph_t graph = nullptr;
+    int64_t before = h->launches;
+    CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        Launch lc{h, h->stream};
+        run_ar_step(lc, B);
+    } catch (...) {
+        cudaStreamEndCapture(h->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        h->launches = before;
+        throw;
+    }
+    CUDA_CHECK(cudaStreamEndCapture(h->stream, &graph));
+    h->ar_nodes = h->launches - before;
+    h->launches = before;
+    cudaError_t e = cudaGraphInstantiate(&h->ar_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    CUDA_CHECK(e);
+    CUDA_CHECK(cudaGetLastError());
+    h->ar_B = B;
+}
+
+void text2mel_generate(H* h, const int* L, int B, int steps, float* Y, int* prev_hist,
+                       long long* maxatt, float* align, cudaStream_t s) {
+    const dctts_hparams& hp = h->hp;
+    const int T = hp.max_T, N = hp.max_N, d = hp.d;
+    if (steps <= 0 || steps > T) steps = T;
+    ensure_ws(h, B);
+    build_ar_graph(h, B);
+    IntBufs ib = ints(h);
+    Launch lc{h, s};
+    run_textenc(lc, L, B, h->kv.as<float>());
+    CUDA_CHECK(cudaMemsetAsync(h->ybuf.p, 0, (size_t)B * T * hp.n_mels * sizeof(float), s));
+    CUDA_CHECK(cudaMemsetAsync(h->ibuf.p, 0, (size_t)(4 + 3 * h->ws_B + (size_t)h->ws_B * T) * sizeof(int), s));
+    for (int j = 0; j < steps; ++j) {
+        CUDA_CHECK(cudaGraphLaunch(h->ar_exec, s));
+        h->launches += h->ar_nodes;
+    }
+    if (Y) CUDA_CHECK(cudaMemcpyAsync(Y, h->ybuf.p, (size_t)B * T * hp.n_mels * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, s));
+    if (prev_hist) CUDA_CHECK(cudaMemcpy2DAsync(prev_hist, (size_t)T * sizeof(int), ib.p_hist,
+                                                (size_t)T * sizeof(int), (size_t)T * sizeof(int), B,
+                                                cudaMemcpyDeviceToDevice, s));
+    if (maxatt || align) {
+        // what the LAST sess.run (j = steps-1) returns: every row under that step's window.
+        // p_hist[:, steps-1] is that window; gather it into p_prev.
+        CUDA_CHECK(cudaMemcpy2DAsync(ib.p_prev, sizeof(int), ib.p_hist + (steps - 1), (size_t)T * sizeof(int),
+                                     sizeof(int), B, cudaMemcpyDeviceToDevice, s));
+        const float* K = h->kv.as<float>();
+        run_attention(lc, h->ae_out.back().as<float>(), d, K, 2 * d, K + d, 2 * d, RowWin{B, T, T, nullptr}, N,
+                      ib.p_prev, h->rbuf.as<float>(), align, maxatt, nullptr, nullptr);
+    }
+}
+
+void text2mel_forward(H* h, const int* L, const float* mels, const int* pma, int B, float* Y,
+                      long long* maxatt, float* align, cudaStream_t s) {
+    const dctts_hparams& hp = h->hp;
+    const int T = hp.max_T, N = hp.max_N, d = hp.d;
+    ensure_ws(h, B);
+    Launch lc{h, s};
+    run_textenc(lc, L, B, h->kv.as<float>());
+    // AudioEnc over all rows, reading mels shifted by one frame (train.py:51)
+    const float* cur = mels; int ld = hp.n_mels;
+    for (size_t i = 0; i < h->audioenc.size(); ++i) {
+        const LayerDev& l = h->audioenc[i];
+        float* dst = h->ae_out[i].as<float>();
+        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, T, nullptr}, dst, l.cout, nullptr, 0,
+                  i == 0 ? -1 : 0);
+        cur = dst; ld = l.cout;
+    }
+    const float* K = h->kv.as<float>();
+    run_attention(lc, cur, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, T, nullptr}, N, pma, h->rbuf.as<float>(),
+                  align, maxatt, nullptr, nullptr);
+    cur = h->rbuf.as<float>(); ld = 2 * d;
+    for (size_t i = 0; i < h->audiodec.size(); ++i) {
+        const LayerDev& l = h->audiodec[i];
+        const bool last = (i + 1 == h->audiodec.size());
+        float* dst = h->ad_out[i].as<float>();
+        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, T, nullptr}, dst, l.cout,
+                  last ? Y : nullptr, hp.n_mels);
+        cur = dst; ld = l.cout;
+    }
+}
+
+LayerDev* find_layer(H* h, const char* scope, int kind) {
+    REQUIRE(h->committed, "parameters not committed");
+    auto it = h->by_scope.find(scope ? scope : "");
+    if (it == h->by_scope.end()) throw std::runtime_error(std::string("unknown scope: ") + (scope ? scope : "(null)"));
+    if (it->second->kind != kind) throw std::runtime_error(std::string("scope has a different block kind: ") + scope);
+    return it->second;
+}
+
+template <class Fn>
+int guarded(dctts_handle h, Fn&& fn) {
+    if (!h) { g_create_error = "null handle"; return 1; }
+    try {
+        CUDA_CHECK(cudaSetDevice(h->device));
+        fn();
+        CUDA_CHECK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& e) {
+        h->err = e.what();
+        cudaGetLastError();
+        return 2;
+    } catch (...) {
+        h->err = "unknown failure";
+        return 3;
+    }
+}
+
+// NULL means the legacy default stream (what torch's default stream is), so calls made from a
+// torch program are ordered with the surrounding torch work without extra synchronisation.
+inline cudaStream_t S(dctts_handle, void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Grow the pre-LN scratch for an op-level call; a reallocation invalidates the AR graph,
+// which has the old pointer baked in.
+void ensure_scratch(H* h, size_t bytes) {
+    if (bytes <= h->scratch.bytes) return;
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (h->ar_exec) { cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
+    h->scratch.ensure(bytes);
+}
+
+}  // namespace
+
+// ==================================================================================== C-ABI
+extern "C" {
+
+const char* dctts_version(void) { return "dc_tts_b200 0.1.0 (sm_100a)"; }
+
+const char* dctts_last_error(dctts_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int dctts_create(const dctts_hparams* hp, int device, dctts_handle* out) {
+    if (!hp || !out) { g_create_error = "dctts_create: null argument"; return 1; }
+    try {
+        int ndev = 0;
+        CUDA_CHECK(cudaGetDeviceCount(&ndev));
+        if (device < 0 || device >= ndev) throw std::runtime_error("dctts_create: no such CUDA device (no CPU fallback exists)");
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) throw std::runtime_error("dctts_create: this library is built for sm_100a (B200) only");
+        if (hp->d > 256 || hp->d % 8 || hp->e % 4 || hp->max_N > 192 || hp->r != 4)
+            throw std::runtime_error("dctts_create: unsupported hyper-parameters");
+        std::unique_ptr<dctts_handle_s> h(new dctts_handle_s());
+        h->hp = *hp; h->device = device; h->F = 1 + hp->n_fft / 2;
+        CUDA_CHECK(cudaSetDevice(device));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        build_tables(h.get());
+        *out = h.release();
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        cudaGetLastError();
+        return 2;
+    }
+}
+
+int dctts_destroy(dctts_handle h) {
+    if (!h) return 1;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    delete h;
+    return 0;
+}
+
+int dctts_set_param(dctts_handle h, const char* tf_name, const float* data, const int64_t* shape, int32_t rank) {
+    return guarded(h, [&] {
+        REQUIRE(!h->committed, "parameters already committed");
+        REQUIRE(tf_name && data && shape && rank >= 1 && rank <= 4, "dctts_set_param: bad arguments");
+        HostParam p;
+        size_t n = 1;
+        for (int i = 0; i < rank; ++i) { REQUIRE(shape[i] > 0, "dctts_set_param: bad shape"); p.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+        p.data.assign(data, data + n);
+        h->staged[tf_name] = std::move(p);
+    });
+}
+
+int dctts_commit_params(dctts_handle h) { return guarded(h, [&] { commit_params(h); }); }
+
+int64_t dctts_num_params(dctts_handle h) { return (h && h->committed) ? h->n_params : -1; }
+
+int dctts_embed(dctts_handle h, const char* scope, const int32_t* ids, int32_t B, int32_t N, float* out, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        auto it = h->dev_vec.find(std::string(scope ? scope : "") + "/lookup_table");
+        REQUIRE(it != h->dev_vec.end(), "dctts_embed: unknown scope");
+        launch_embed(ids, it->second, out, B * N, h->hp.e, S(h, stream)); h->launches++;
+    });
+}
+
+int dctts_normalize(dctts_handle h, const char* scope, const float* x, int64_t rows, int32_t C, float* out, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        auto g = h->dev_vec.find(std::string(scope ? scope : "") + "/gamma");
+        auto b = h->dev_vec.find(std::string(scope ? scope : "") + "/beta");
+        REQUIRE(g != h->dev_vec.end() && b != h->dev_vec.end(), "dctts_normalize: unknown scope");
+        REQUIRE(C >= 1 && C <= 1056 && rows < (1ll << 31), "dctts_normalize: unsupported width");
+        LnArgs n{};
+        n.Y = x; n.ldy = C; n.g1 = g->second; n.b1 = b->second; n.out = out; n.ldo = C; n.C = C;
+        n.mode = 0; n.act = 0; n.win = RowWin{1, (int)rows, (int)rows, nullptr};
+        launch_ln_rows(n, S(h, stream)); h->launches++;
+    });
+}
+
+int dctts_conv1d(dctts_handle h, const char* scope, const float* x, int32_t B, int32_t L, int32_t rate,
+                 int32_t causal, int32_t act, float* out, void* stream) {
+    return guarded(h, [&] {
+        LayerDev* l = find_layer(h, scope, K_C);
+        REQUIRE(B >= 1 && L >= 1 && rate >= 1, "dctts_conv1d: bad sizes");
+        ensure_scratch(h, (size_t)B * L * l->ldw * sizeof(float));
+        Launch lc{h, S(h, stream)};
+        run_block(lc, *l, rate, causal != 0, act, x, l->cin, RowWin{B, L, L, nullptr}, out, l->cout, nullptr, 0);
+    });
+}
+
+int dctts_hc(dctts_handle h, const char* scope, const float* x, int32_t B, int32_t L, int32_t rate,
+             int32_t causal, float* out, void* stream) {
+    return guarded(h, [&] {
+        LayerDev* l = find_layer(h, scope, K_HC);
+        REQUIRE(B >= 1 && L >= 1 && rate >= 1, "dctts_hc: bad sizes");
+        ensure_scratch(h, (size_t)B * L * l->ldw * sizeof(float));
+        Launch lc{h, S(h, stream)};
+        run_block(lc, *l, rate, causal != 0, 0, x, l->cin, RowWin{B, L, L, nullptr}, out, l->cout, nullptr, 0);
+    });
+}
+
+int dctts_conv1d_transpose(dctts_handle h, const char* scope, const float* x, int32_t B, int32_t L, float* out, void* stream) {
+    return guarded(h, [&] {
+        LayerDev* l = find_layer(h, scope, K_D);
+        REQUIRE(B >= 1 && L >= 1, "dctts_conv1d_transpose: bad sizes");
+        ensure_scratch(h, (size_t)B * 2 * L * l->ldw * sizeof(float));
+        Launch lc{h, S(h, stream)};
+        run_deconv(lc, *l, x, l->cin, B, L, out, l->cout);
+    });
+}
+
+int dctts_textenc(dctts_handle h, const int32_t* L, int32_t B, float* K, float* V, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && L && K && V, "dctts_textenc: bad arguments");
+        ensure_ws(h, B);
+        cudaStream_t s = S(h, stream);
+        Launch lc{h, s};
+        run_textenc(lc, L, B, h->kv.as<float>());
+        const int N = h->hp.max_N, d = h->hp.d;
+        const size_t w = (size_t)d * sizeof(float);
+        CUDA_CHECK(cudaMemcpy2DAsync(K, w, h->kv.as<float>(), 2 * w, w, (size_t)B * N, cudaMemcpyDeviceToDevice, s));
+        CUDA_CHECK(cudaMemcpy2DAsync(V, w, h->kv.as<float>() + d, 2 * w, w, (size_t)B * N, cudaMemcpyDeviceToDevice, s));
+    });
+}
+
+int dctts_audioenc(dctts_handle h, const float* Sin, int32_t B, int32_t T, float* Q, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && T >= 1 && T <= h->hp.max_T && Sin && Q, "dctts_audioenc: bad arguments (T must be <= max_T)");
+        ensure_ws(h, B);
+        Launch lc{h, S(h, stream)};
+        run_chain_full(lc, h->audioenc, Sin, h->hp.n_mels, B, T, Q, nullptr);
+    });
+}
+
+int dctts_attention(dctts_handle h, const float* Q, const float* K, const float* V, int32_t B, int32_t T, int32_t N,
+                    int32_t monotonic, const int32_t* pma, float* R, float* alignments, int64_t* max_attentions,
+                    void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(B >= 1 && T >= 1 && N >= 1 && Q && K && V && R, "dctts_attention: bad arguments");
+        REQUIRE(!monotonic || pma, "dctts_attention: monotonic attention needs prev_max_attentions");
+        Launch lc{h, S(h, stream)};
+        const int d = h->hp.d;
+        run_attention(lc, Q, d, K, d, V, d, RowWin{B, T, T, nullptr}, N, monotonic ? pma : nullptr, R, alignments,
+                      reinterpret_cast<long long*>(max_attentions), nullptr, nullptr);
+    });
+}
+
+int dctts_audiodec(dctts_handle h, const float* R, int32_t B, int32_t T, float* Y_logits, float* Y, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && T >= 1 && T <= h->hp.max_T && R && Y, "dctts_audiodec: bad arguments (T must be <= max_T)");
+        ensure_ws(h, B);
+        Launch lc{h, S(h, stream)};
+        run_chain_full(lc, h->audiodec, R, 2 * h->hp.d, B, T, Y_logits, Y);
+    });
+}
+
+int dctts_ssrn(dctts_handle h, const float* Y, int32_t B, int32_t T, float* Z_logits, float* Z, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && T >= 1 && T <= h->hp.max_T && Y && Z, "dctts_ssrn: bad arguments (T must be <= max_T)");
+        ensure_ws(h, B);
+        Launch lc{h, S(h, stream)};
+        run_chain_full(lc, h->ssrn, Y, h->hp.n_mels, B, T, Z_logits, Z);
+    });
+}
+
+int dctts_text2mel_forward(dctts_handle h, const int32_t* L, const float* mels, const int32_t* pma, int32_t B,
+                           float* Y, int64_t* max_attentions, float* alignments, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && L && mels && pma && Y, "dctts_text2mel_forward: bad arguments");
+        text2mel_forward(h, L, mels, pma, B, Y, reinterpret_cast<long long*>(max_attentions), alignments, S(h, stream));
+    });
+}
+
+int dctts_text2mel_generate(dctts_handle h, const int32_t* L, int32_t B, int32_t steps, float* Y, int32_t* prev_hist,
+                            int64_t* max_attentions, float* alignments, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && L, "dctts_text2mel_generate: bad arguments");
+        text2mel_generate(h, L, B, steps, Y, prev_hist, reinterpret_cast<long long*>(max_attentions), alignments,
+                          S(h, stream));
+    });
+}
+
+int dctts_synthesize_host(dctts_handle h, const int32_t* L_host, int32_t B, float* Y_host, float* Z_host) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(B >= 1 && L_host && Z_host, "dctts_synthesize_host: bad arguments");
+        const dctts_hparams& hp = h->hp;
+        const int T = hp.max_T, N = hp.max_N;
+        ensure_ws(h, B);
+        const size_t zbytes = (size_t)B * T * hp.r * h->F * sizeof(float);
+        h->zbuf.ensure(zbytes);
+        cudaStream_t s = h->stream;
+        CUDA_CHECK(cudaMemcpyAsync(h->lbuf.p, L_host, (size_t)B * N * sizeof(int), cudaMemcpyHostToDevice, s));
+        text2mel_generate(h, h->lbuf.as<int>(), B, T, nullptr, nullptr, nullptr, nullptr, s);
+        Launch lc{h, s};
+        run_chain_full(lc, h->ssrn, h->ybuf.as<float>(), hp.n_mels, B, T, nullptr, h->zbuf.as<float>());
+        if (Y_host) CUDA_CHECK(cudaMemcpyAsync(Y_host, h->ybuf.p, (size_t)B * T * hp.n_mels * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaMemcpyAsync(Z_host, h->zbuf.p, zbytes, cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+    });
+}
+
+int dctts_bench_block(dctts_handle h, const char* scope, int32_t B, int32_t L, int32_t iters, int32_t warmup,
+                      float* ms_per_kernel, int32_t* n_kernels, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(h->committed, "parameters not committed");
+        REQUIRE(scope && B >= 1 && L >= 1 && iters >= 1 && ms_per_kernel && n_kernels, "dctts_bench_block: bad arguments");
+        auto it = h->by_scope.find(scope);
+        REQUIRE(it != h->by_scope.end(), "dctts_bench_block: unknown scope");
+        const LayerDev& l = *it->second;
+        const int Lout = (l.kind == K_D) ? 2 * L : L;
+        ensure_scratch(h, (size_t)B * Lout * l.ldw * sizeof(float));
+        DevBuf x, y;
+        x.ensure((size_t)B * L * l.cin * sizeof(float));
+        y.ensure((size_t)B * Lout * l.cout * sizeof(float));
+        cudaStream_t s = S(h, stream);
+        CUDA_CHECK(cudaMemsetAsync(x.p, 0x3c, x.bytes, s));      // 0x3c3c3c3c = 0.0115 as float
+        std::vector<cudaEvent_t> evs;
+        std::vector<double> acc;
+        int nk = 0;
+        for (int i = 0; i < warmup + iters; ++i) {
+            Launch lc{h, s};
+            evs.clear();
+            if (i >= warmup) {
+                lc.evs = &evs;
+                cudaEvent_t e0; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventRecord(e0, s)); evs.push_back(e0);
+            }
+            if (l.kind == K_D) run_deconv(lc, l, x.as<float>(), l.cin, B, L, y.as<float>(), l.cout);
+            else run_block(lc, l, l.rate, l.causal, l.act, x.as<float>(), l.cin, RowWin{B, L, L, nullptr},
+                           y.as<float>(), l.cout, nullptr, 0);
+            if (i >= warmup) {
+                CUDA_CHECK(cudaStreamSynchronize(s));
+                nk = (int)evs.size() - 1;
+                if (acc.empty()) acc.assign(nk, 0.0);
+                for (int k = 0; k < nk; ++k) {
+                    float ms = 0.f;
+                    CUDA_CHECK(cudaEventElapsedTime(&ms, evs[k], evs[k + 1]));
+                    acc[k] += ms;
+                }
+                for (auto e : evs) cudaEventDestroy(e);
+            }
+        }
+        REQUIRE(nk <= 8, "dctts_bench_block: too many kernels");
+        for (int k = 0; k < nk; ++k) ms_per_kernel[k] = (float)(acc[k] / iters);
+        *n_kernels = nk;
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        x.release(); y.release();
+    });
+}
+
+int dctts_reserve(dctts_handle h, int32_t max_batch) {
+    return guarded(h, [&] { REQUIRE(max_batch >= 1, "dctts_reserve: bad batch"); ensure_ws(h, max_batch); });
+}
+
+int64_t dctts_launch_count(dctts_handle h) { return h ? h->launches : -1; }
+
+int dctts_set_tensor_path(dctts_handle h, int32_t mode) {
+    return guarded(h, [&] { REQUIRE(mode == 0 || mode == 1, "dctts_set_tensor_path: mode must be 0 or 1"); h->tensor_path = mode; });
+}
+
+int dctts_malloc(dctts_handle h, void** ptr, int64_t bytes) {
+    return guarded(h, [&] { REQUIRE(ptr && bytes > 0, "dctts_malloc: bad arguments"); CUDA_CHECK(cudaMalloc(ptr, (size_t)bytes)); });
+}
+int dctts_free(dctts_handle h, void* ptr) { return guarded(h, [&] { CUDA_CHECK(cudaFree(ptr)); }); }
+int dctts_memcpy_h2d(dctts_handle h, void* dst, const void* src, int64_t bytes, void* stream) {
+    return guarded(h, [&] { CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, S(h, stream))); });
+}
+int dctts_memcpy_d2h(dctts_handle h, void* dst, const void* src, int64_t bytes, void* stream) {
+    return guarded(h, [&] { CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, S(h, stream))); });
+}
+int dctts_malloc_host(dctts_handle h, void** ptr, int64_t bytes) {
+    return guarded(h, [&] { REQUIRE(ptr && bytes > 0, "dctts_malloc_host: bad arguments"); CUDA_CHECK(cudaMallocHost(ptr, (size_t)bytes)); });
+}
+int dctts_free_host(dctts_handle h, void* ptr) { return guarded(h, [&] { CUDA_CHECK(cudaFreeHost(ptr)); }); }
+int dctts_stream_sync(dctts_handle h, void* stream) { return guarded(h, [&] { CUDA_CHECK(cudaStreamSynchronize(S(h, stream))); }); }
+
+}  // extern "C"

@@ -1,0 +1,74 @@
+// kernels.cuh -- argument blocks and launchers shared by the kernel files and the C-ABI.
+//
+// Row addressing (all kernels): an activation tensor is (B, L, C) float32 channels-last
+// with leading dimension ld (floats).  A launch covers, for every batch element b, the
+// time rows t in [t_end-R+1, t_end] where t_end = *jptr (device int, the AR step) when
+// jptr != nullptr, else L-1.  Rows with t < 0 are skipped; a conv tap whose source row
+// falls outside [0, L) contributes zeros (TF zero padding, reference modules.py:121-125).
+// With R == L and jptr == nullptr this is the plain full-sequence case.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dctts {
+
+struct RowWin {
+    int B;            // batch
+    int L;            // time length of the tensors
+    int R;            // rows per batch element covered by this launch
+    const int* jptr;  // device step index (window end), or nullptr -> L-1
+};
+
+struct ConvTap {
+    const float* W;   // [K][ldw] row-major (output channel contiguous), zero padded to ldw
+    int shift;        // source row = t + shift
+};
+
+// Y[orow][n] = bias[n] + sum_taps sum_k X[b, t+shift, k] * W_tap[k][n]
+struct ConvArgs {
+    const float* X; int ldx;
+    float* Y; int ldy;             // pre-LN scratch, ldy == ldw (multiple of 4)
+    const float* bias;             // [ldw], zero padded
+    int K, N, ldw;
+    int ntaps; ConvTap taps[3];
+    RowWin win;
+    int Lout, ostride, ooff;       // output row = b*Lout + t*ostride + ooff
+};
+
+// Row-wise epilogue on the pre-LN scratch.
+//  mode 0 (conv1d):  o = act(LN(y[0:C]) * g1 + b1);            out = o; out2 = sigmoid(o) if out2
+//  mode 1 (hc):      H1 = sigmoid(LN(y[0:C])*g1+b1); H2 = LN(y[C:2C])*g2+b2;
+//                    out = H1*H2 + (1-H1)*x
+struct LnArgs {
+    const float* Y; int ldy;       // scratch rows indexed like the output rows
+    const float* g1; const float* b1; const float* g2; const float* b2;
+    const float* X; int ldx;       // highway residual (mode 1), same row index as out
+    float* out; int ldo;
+    float* out2; int ldo2;         // optional sigmoid copy (mode 0)
+    int C; int mode; int act;      // act: 0 none, 1 relu
+    RowWin win;                    // rows are output rows: L here is the OUTPUT length
+};
+
+struct AttnArgs {
+    const float* Q; int ldq;       // (B,T,d)
+    const float* K; int ldk;       // (B,N,d)
+    const float* V; int ldv;       // (B,N,d)
+    float* Rout; int ldr;          // (B,T,2d) = [A.V ; Q]
+    float* align;                  // (B,N,T) or nullptr
+    long long* maxatt;             // (B,T) or nullptr
+    const int* pma;                // (B) window start, nullptr -> dense softmax over all keys
+    int* p_next;                   // (B) or nullptr: argmax of row t_end
+    int* p_hist;                   // (B,T) or nullptr: p_hist[b][t_end] = pma[b]
+    int N, d, win_size;
+    RowWin win;                    // rows = query rows (L = T)
+};
+
+void launch_conv_gemm(const ConvArgs& a, cudaStream_t s);
+void launch_ln_rows(const LnArgs& a, cudaStream_t s);
+void launch_attention(const AttnArgs& a, cudaStream_t s);
+void launch_embed(const int* ids, const float* table, float* out, int rows, int e, cudaStream_t s);
+// p_cur = p_next; j += 1  (end of an AR step)
+void launch_ar_advance(int* p_cur, const int* p_next, int* j, int B, cudaStream_t s);
+void launch_fill_i32(int* p, int v, int n, cudaStream_t s);
+
+}  // namespace dctts

@@ -1,0 +1,243 @@
+"""Engine: one libdctts_b200 handle bound to one GPU, driven with torch device tensors.
+
+torch is used here for device memory and streams only; every computation goes through
+the C-ABI (include/dctts.h).  This object plays the role of the reference's
+`tf.Session` + restored variables (/root/reference/synthesize.py:28-41).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .hyperparams import Hyperparams as hp
+from .params import check_params
+
+
+class DcttsError(RuntimeError):
+    pass
+
+
+def _ptr(t):
+    return C.c_void_p(0) if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, device=0, hparams=hp):
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise DcttsError("dc_tts_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        self.hp = hparams
+        self.F = 1 + hparams.n_fft // 2
+        st = _lib.HParams(len(hparams.vocab), hparams.e, hparams.d, hparams.c, hparams.n_mels,
+                          hparams.n_fft, hparams.max_N, hparams.max_T, hparams.attention_win_size, hparams.r)
+        h = _lib.Handle()
+        torch.cuda.init()
+        with torch.cuda.device(self.device):
+            torch.zeros(1, device=self.device)          # make sure the primary context exists
+            rc = self._lib.dctts_create(C.byref(st), device, C.byref(h))
+        if rc != 0:
+            raise DcttsError("dctts_create: " + self._lib.dctts_last_error(None).decode())
+        self._h = h
+        self.params_loaded = False
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dctts_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise DcttsError("%s: %s" % (what, self._lib.dctts_last_error(self._h).decode()))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        return x.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _i32(self, x):
+        if isinstance(x, np.ndarray):
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32))
+        return torch.as_tensor(x).to(device=self.device, dtype=torch.int32).contiguous()
+
+    def _empty(self, *shape, dtype=torch.float32):
+        return torch.empty(shape, device=self.device, dtype=dtype)
+
+    # ------------------------------------------------------------------ parameters
+    def load_params(self, params):
+        """Stage every variable (TF names) and commit them to the device."""
+        check_params(params)
+        for name, arr in params.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            self._check(self._lib.dctts_set_param(self._h, name.encode(), a.ctypes.data_as(C.c_void_p),
+                                                   shape, a.ndim), "dctts_set_param(%s)" % name)
+        self._check(self._lib.dctts_commit_params(self._h), "dctts_commit_params")
+        self.params_loaded = True
+        return int(self._lib.dctts_num_params(self._h))
+
+    def set_tensor_path(self, mode):
+        self._check(self._lib.dctts_set_tensor_path(self._h, int(mode)), "dctts_set_tensor_path")
+
+    def reserve(self, batch):
+        self._check(self._lib.dctts_reserve(self._h, int(batch)), "dctts_reserve")
+
+    def bench_block(self, scope, B, L, iters=5, warmup=2):
+        """Mean device milliseconds of each kernel of one block (roofline leg of bench.py)."""
+        ms = (C.c_float * 8)()
+        n = C.c_int32(0)
+        self._check(self._lib.dctts_bench_block(self._h, scope.encode(), B, L, iters, warmup, ms, C.byref(n),
+                                                self._stream()), "dctts_bench_block")
+        return [float(ms[i]) for i in range(n.value)]
+
+    def launch_count(self):
+        return int(self._lib.dctts_launch_count(self._h))
+
+    # ------------------------------------------------------------------ building blocks
+    def embed(self, scope, ids):
+        ids = self._i32(ids)
+        B, N = ids.shape
+        out = self._empty(B, N, self.hp.e)
+        self._check(self._lib.dctts_embed(self._h, scope.encode(), _ptr(ids), B, N, _ptr(out), self._stream()), "dctts_embed")
+        return out
+
+    def normalize(self, scope, x):
+        x = self._f32(x)
+        Cc = x.shape[-1]
+        out = torch.empty_like(x)
+        self._check(self._lib.dctts_normalize(self._h, scope.encode(), _ptr(x), x.numel() // Cc, Cc, _ptr(out),
+                                              self._stream()), "dctts_normalize")
+        return out
+
+    def conv1d(self, scope, x, filters, rate=1, causal=False, act=0):
+        x = self._f32(x)
+        B, L, _ = x.shape
+        out = self._empty(B, L, filters)
+        self._check(self._lib.dctts_conv1d(self._h, scope.encode(), _ptr(x), B, L, rate, int(causal), act,
+                                           _ptr(out), self._stream()), "dctts_conv1d")
+        return out
+
+    def hc(self, scope, x, rate=1, causal=False):
+        x = self._f32(x)
+        B, L, _ = x.shape
+        out = torch.empty_like(x)
+        self._check(self._lib.dctts_hc(self._h, scope.encode(), _ptr(x), B, L, rate, int(causal), _ptr(out),
+                                       self._stream()), "dctts_hc")
+        return out
+
+    def conv1d_transpose(self, scope, x):
+        x = self._f32(x)
+        B, L, Cc = x.shape
+        out = self._empty(B, 2 * L, Cc)
+        self._check(self._lib.dctts_conv1d_transpose(self._h, scope.encode(), _ptr(x), B, L, _ptr(out),
+                                                     self._stream()), "dctts_conv1d_transpose")
+        return out
+
+    # ------------------------------------------------------------------ networks
+    def textenc(self, L):
+        L = self._i32(L)
+        B, N = L.shape
+        if N != self.hp.max_N:
+            raise DcttsError("TextEnc: text must be padded to max_N=%d (reference networks.py:145)" % self.hp.max_N)
+        K, V = self._empty(B, N, self.hp.d), self._empty(B, N, self.hp.d)
+        self._check(self._lib.dctts_textenc(self._h, _ptr(L), B, _ptr(K), _ptr(V), self._stream()), "dctts_textenc")
+        return K, V
+
+    def audioenc(self, S):
+        S = self._f32(S)
+        B, T, _ = S.shape
+        Q = self._empty(B, T, self.hp.d)
+        self._check(self._lib.dctts_audioenc(self._h, _ptr(S), B, T, _ptr(Q), self._stream()), "dctts_audioenc")
+        return Q
+
+    def attention(self, Q, K, V, monotonic=False, prev_max_attentions=None):
+        Q, K, V = self._f32(Q), self._f32(K), self._f32(V)
+        B, T, d = Q.shape
+        N = K.shape[1]
+        pma = self._i32(prev_max_attentions) if monotonic else None
+        R = self._empty(B, T, 2 * d)
+        A = self._empty(B, N, T)
+        M = self._empty(B, T, dtype=torch.int64)
+        self._check(self._lib.dctts_attention(self._h, _ptr(Q), _ptr(K), _ptr(V), B, T, N, int(bool(monotonic)),
+                                              _ptr(pma), _ptr(R), _ptr(A), _ptr(M), self._stream()), "dctts_attention")
+        return R, A, M
+
+    def audiodec(self, R):
+        R = self._f32(R)
+        B, T, _ = R.shape
+        logits, Y = self._empty(B, T, self.hp.n_mels), self._empty(B, T, self.hp.n_mels)
+        self._check(self._lib.dctts_audiodec(self._h, _ptr(R), B, T, _ptr(logits), _ptr(Y), self._stream()), "dctts_audiodec")
+        return logits, Y
+
+    def ssrn(self, Y, want_logits=True):
+        Y = self._f32(Y)
+        B, T, _ = Y.shape
+        Z = self._empty(B, T * self.hp.r, self.F)
+        logits = self._empty(B, T * self.hp.r, self.F) if want_logits else None
+        self._check(self._lib.dctts_ssrn(self._h, _ptr(Y), B, T, _ptr(logits), _ptr(Z), self._stream()), "dctts_ssrn")
+        return logits, Z
+
+    # ------------------------------------------------------------------ graph level
+    def text2mel_forward(self, L, mels, prev_max_attentions, want_alignments=True):
+        L, mels, pma = self._i32(L), self._f32(mels), self._i32(prev_max_attentions)
+        B = L.shape[0]
+        if L.shape[1] != self.hp.max_N or mels.shape[1] != self.hp.max_T:
+            raise DcttsError("synthesize graph needs N == max_N and T == max_T (reference networks.py:145)")
+        Y = self._empty(B, self.hp.max_T, self.hp.n_mels)
+        M = self._empty(B, self.hp.max_T, dtype=torch.int64)
+        A = self._empty(B, self.hp.max_N, self.hp.max_T) if want_alignments else None
+        self._check(self._lib.dctts_text2mel_forward(self._h, _ptr(L), _ptr(mels), _ptr(pma), B, _ptr(Y), _ptr(M),
+                                                     _ptr(A), self._stream()), "dctts_text2mel_forward")
+        return Y, M, A
+
+    def text2mel_generate(self, L, steps=0, want_final_attention=False):
+        L = self._i32(L)
+        B = L.shape[0]
+        Y = self._empty(B, self.hp.max_T, self.hp.n_mels)
+        P = self._empty(B, self.hp.max_T, dtype=torch.int32)
+        M = self._empty(B, self.hp.max_T, dtype=torch.int64) if want_final_attention else None
+        A = self._empty(B, self.hp.max_N, self.hp.max_T) if want_final_attention else None
+        self._check(self._lib.dctts_text2mel_generate(self._h, _ptr(L), B, int(steps), _ptr(Y), _ptr(P), _ptr(M),
+                                                      _ptr(A), self._stream()), "dctts_text2mel_generate")
+        return Y, P, M, A
+
+    def synthesize_host(self, L_host, Y_host=None, Z_host=None):
+        """synthesize.py:45-57 with host (ideally pinned) tensors in and out."""
+        L_host = torch.as_tensor(L_host, dtype=torch.int32).contiguous()
+        B = L_host.shape[0]
+        if Z_host is None:
+            Z_host = torch.empty((B, self.hp.max_T * self.hp.r, self.F), dtype=torch.float32).pin_memory()
+        if Y_host is None:
+            Y_host = torch.empty((B, self.hp.max_T, self.hp.n_mels), dtype=torch.float32).pin_memory()
+        self._check(self._lib.dctts_synthesize_host(self._h, _ptr(L_host), B, _ptr(Y_host), _ptr(Z_host)),
+                    "dctts_synthesize_host")
+        return Y_host, Z_host
+
+
+_default = None
+
+
+def get_engine():
+    """The process-wide default engine (used by modules.py / networks.py wrappers)."""
+    global _default
+    if _default is None:
+        import os
+        _default = Engine(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default
+
+
+def set_engine(e):
+    global _default
+    _default = e
+    return e

@@ -1,0 +1,63 @@
+"""Drop-in for the reference's synthesize.py (/root/reference/synthesize.py:21-64).
+
+Same flow: load text -> build Graph(mode="synthesize") -> restore parameters -> mel
+loop (:45-54) -> SSRN (:57) -> write one output per sentence.  Differences, all forced
+by what exists offline: parameters come from a name->array dict (no TF checkpoint
+reader yet; seeded initialiser weights when none are given), and the Griffin-Lim
+vocoder (utils.py:67-114, librosa) is a "next" row of SURVEY.md 8(f), so the linear
+magnitudes are saved as .npy instead of .wav.
+"""
+import os
+
+import numpy as np
+
+from .data_load import load_data
+from .engine import get_engine
+from .hyperparams import Hyperparams as hp
+from .params import init_params
+from .train import Graph, Session
+
+
+def synthesize(params=None, sentences=None, fast=True, write=True, seed=0):
+    # Load data
+    L = load_data("synthesize", sentences)
+
+    # Load graph
+    g = Graph(mode="synthesize")
+    print("Graph loaded")
+
+    with Session() as sess:
+        # Restore parameters (synthesize.py:31-41)
+        if not g.engine.params_loaded:
+            g.engine.load_params(params if params is not None else init_params(seed))
+        print("Text2Mel Restored!")
+        print("SSRN Restored!")
+
+        if fast:
+            # the whole loop on the device (CUDA-graph replay), identical results
+            Y, _ = g.generate(L)
+        else:
+            # the reference's loop, verbatim in structure (synthesize.py:45-54)
+            Y = np.zeros((len(L), hp.max_T, hp.n_mels), np.float32)
+            prev_max_attentions = np.zeros((len(L),), np.int32)
+            for j in range(hp.max_T):
+                _gs, _Y, _max_attentions, _alignments = \
+                    sess.run([g.global_step, g.Y, g.max_attentions, g.alignments],
+                             {g.L: L, g.mels: Y, g.prev_max_attentions: prev_max_attentions})
+                Y[:, j, :] = _Y[:, j, :]
+                prev_max_attentions = _max_attentions[:, j]
+
+        # Get magnitude (synthesize.py:57)
+        Z = sess.run(g.Z, {g.Y: Y})
+
+    if write:
+        if not os.path.exists(hp.sampledir):
+            os.makedirs(hp.sampledir)
+        for i, mag in enumerate(Z):
+            np.save(os.path.join(hp.sampledir, "{}.mag.npy".format(i + 1)), mag)
+    return (Y.cpu().numpy() if hasattr(Y, "cpu") else Y), Z
+
+
+if __name__ == '__main__':
+    synthesize()
+    print("Done")

@@ -1,0 +1,154 @@
+/*
+ * dctts.h -- C-ABI of the B200-native DC-TTS synthesis path (libdctts_b200.so).
+ *
+ * The reference (Kyubyong/dc_tts) has no FFI layer: its operator API is the set of
+ * Python signatures in modules.py / networks.py and the Graph attributes fetched by
+ * synthesize.py.  Each entry point below states the reference interface it replaces
+ * (file:line under /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every tensor is float32, channels-last (B, time, C), dense unless an explicit
+ *     leading dimension is passed; ids are int32, argmax outputs int64 (tf.argmax);
+ *   - `x`/`out` pointers are DEVICE pointers on the handle's device, except in the
+ *     `*_host` entry points, which take HOST pointers and do the copies themselves;
+ *   - the caller owns all tensors; the handle owns weights, workspace and CUDA graphs;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *   - every function returns 0 on success, non-zero on failure, never throws, and
+ *     never falls back to a CPU implementation; dctts_last_error() describes the
+ *     most recent failure on that handle (or the global one for create failures);
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef DCTTS_H_
+#define DCTTS_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dctts_handle_s* dctts_handle;
+
+/* Model hyper-parameters the kernels specialise on: reference hyperparams.py:19,27-32,38-40,14. */
+typedef struct dctts_hparams {
+    int32_t vocab_size;          /* len(hp.vocab) = 32 */
+    int32_t e;                   /* hp.e = 128  */
+    int32_t d;                   /* hp.d = 256  */
+    int32_t c;                   /* hp.c = 512  */
+    int32_t n_mels;              /* hp.n_mels = 80 */
+    int32_t n_fft;               /* hp.n_fft = 2048 -> F = 1 + n_fft/2 */
+    int32_t max_N;               /* hp.max_N = 180 */
+    int32_t max_T;               /* hp.max_T = 210 */
+    int32_t attention_win_size;  /* hp.attention_win_size = 3 */
+    int32_t r;                   /* hp.r = 4 (SSRN upsampling = two stride-2 deconvs) */
+} dctts_hparams;
+
+/* ---- lifetime ------------------------------------------------------------------ */
+/* Replaces Graph(mode="synthesize") construction + tf.Session() (train.py:22-80, synthesize.py:26-28). */
+int dctts_create(const dctts_hparams* hp, int device, dctts_handle* out);
+int dctts_destroy(dctts_handle h);
+const char* dctts_last_error(dctts_handle h);      /* h may be NULL: last create() error */
+const char* dctts_version(void);
+
+/* ---- parameters ---------------------------------------------------------------- */
+/* Replaces Saver.restore into TF variables (synthesize.py:31-41).  `tf_name` is the TF
+ * variable name, `data` a HOST float32 array of `shape[0..rank)`.
+ * dctts_commit_params() packs the staged variables into the kernels' layouts and
+ * uploads them; it fails if any variable of the path is missing or mis-shaped. */
+int dctts_set_param(dctts_handle h, const char* tf_name, const float* data,
+                    const int64_t* shape, int32_t rank);
+int dctts_commit_params(dctts_handle h);
+int64_t dctts_num_params(dctts_handle h);           /* committed scalar count, -1 on error */
+
+/* ---- building blocks (reference modules.py) ------------------------------------ */
+/* `scope` is the full variable scope, e.g. "Text2Mel/AudioEnc/HC_4". */
+
+/* embed (modules.py:13-42): ids (B,N) int32 -> out (B,N,e); row 0 of the table reads as zeros. */
+int dctts_embed(dctts_handle h, const char* scope, const int32_t* ids, int32_t B, int32_t N,
+                float* out, void* stream);
+/* normalize (modules.py:45-64): LN over the last axis with `scope`/{gamma,beta}, eps 1e-12. */
+int dctts_normalize(dctts_handle h, const char* scope, const float* x, int64_t rows, int32_t C,
+                    float* out, void* stream);
+/* conv1d (modules.py:91-141, training=False): conv(k, rate, SAME|CAUSAL) + bias -> LN -> act.
+ * k, Cin, Cout come from the committed kernel; act: 0 none, 1 relu.  x (B,L,Cin) -> out (B,L,Cout). */
+int dctts_conv1d(dctts_handle h, const char* scope, const float* x, int32_t B, int32_t L,
+                 int32_t rate, int32_t causal, int32_t act, float* out, void* stream);
+/* hc (modules.py:143-197): conv to 2C -> split -> LN(H1),LN(H2) -> sigmoid(H1) -> H1*H2+(1-H1)*x. */
+int dctts_hc(dctts_handle h, const char* scope, const float* x, int32_t B, int32_t L,
+             int32_t rate, int32_t causal, float* out, void* stream);
+/* conv1d_transpose (modules.py:199-247): stride-2, k=3, 'same' -> LN.  x (B,L,C) -> out (B,2L,C). */
+int dctts_conv1d_transpose(dctts_handle h, const char* scope, const float* x, int32_t B, int32_t L,
+                           float* out, void* stream);
+
+/* ---- networks (reference networks.py) ------------------------------------------ */
+/* TextEnc (networks.py:14-71): L (B,N) int32 -> K,V (B,N,d) each. */
+int dctts_textenc(dctts_handle h, const int32_t* L, int32_t B, float* K, float* V, void* stream);
+/* AudioEnc (networks.py:73-124): S (B,T,n_mels) -> Q (B,T,d). */
+int dctts_audioenc(dctts_handle h, const float* S, int32_t B, int32_t T, float* Q, void* stream);
+/* Attention (networks.py:126-155): Q (B,T,d), K,V (B,N,d) -> R (B,T,2d), alignments (B,N,T),
+ * max_attentions (B,T) int64.  prev_max_attentions (B) int32 selects the monotonic window
+ * [p, p+win) when `monotonic` != 0 (ignored otherwise, may be NULL).  alignments and
+ * max_attentions may be NULL. */
+int dctts_attention(dctts_handle h, const float* Q, const float* K, const float* V,
+                    int32_t B, int32_t T, int32_t N, int32_t monotonic,
+                    const int32_t* prev_max_attentions,
+                    float* R, float* alignments, int64_t* max_attentions, void* stream);
+/* AudioDec (networks.py:157-212): R (B,T,2d) -> Y_logits, Y (B,T,n_mels). Y_logits may be NULL. */
+int dctts_audiodec(dctts_handle h, const float* R, int32_t B, int32_t T,
+                   float* Y_logits, float* Y, void* stream);
+/* SSRN (networks.py:214-292): Y (B,T,n_mels) -> Z_logits, Z (B,4T,F). Z_logits may be NULL. */
+int dctts_ssrn(dctts_handle h, const float* Y, int32_t B, int32_t T,
+               float* Z_logits, float* Z, void* stream);
+
+/* ---- graph-level (reference train.py Graph, synthesize.py loop) ------------------ */
+/* One sess.run of the synthesize graph (train.py:48-68 fetched at synthesize.py:48-52):
+ * L (B,max_N), mels (B,max_T,n_mels), prev_max_attentions (B) ->
+ * Y (B,max_T,n_mels), max_attentions (B,max_T) int64, alignments (B,max_N,max_T).
+ * alignments may be NULL.  All rows are recomputed, as the reference does. */
+int dctts_text2mel_forward(dctts_handle h, const int32_t* L, const float* mels,
+                           const int32_t* prev_max_attentions, int32_t B,
+                           float* Y, int64_t* max_attentions, float* alignments, void* stream);
+/* The whole autoregressive loop of synthesize.py:45-54 on the device: TextEnc once, then
+ * `steps` (<= max_T; 0 means max_T) incremental steps replayed from a CUDA graph, each
+ * reproducing exactly what the reference's full-graph pass yields for row j (including
+ * the re-application of step j's attention window to the 85-row AudioDec history).
+ * Outputs: Y (B,max_T,n_mels); optional prev_hist (B,max_T) int32 = the
+ * prev_max_attentions value used at every step; optional final max_attentions /
+ * alignments as the last sess.run would return them. */
+int dctts_text2mel_generate(dctts_handle h, const int32_t* L, int32_t B, int32_t steps,
+                            float* Y, int32_t* prev_hist,
+                            int64_t* max_attentions, float* alignments, void* stream);
+/* synthesize.py:45-57 end to end with HOST buffers: copies L_host in, runs
+ * dctts_text2mel_generate + dctts_ssrn, copies Y_host (B,max_T,n_mels; may be NULL) and
+ * Z_host (B,4*max_T,F) out, and synchronises.  Host buffers should be pinned for speed. */
+int dctts_synthesize_host(dctts_handle h, const int32_t* L_host, int32_t B,
+                          float* Y_host, float* Z_host);
+
+/* ---- utilities ----------------------------------------------------------------- */
+/* Pre-size the workspace (otherwise grown lazily on first use) for batches up to B. */
+int dctts_reserve(dctts_handle h, int32_t max_batch);
+/* Number of kernels this library has launched on the handle since creation (graph
+ * replays count their kernel nodes). */
+int64_t dctts_launch_count(dctts_handle h);
+/* Selects the arithmetic path for the large-M fused blocks: 0 = fp32 SIMT kernels,
+ * 1 = tcgen05 split-fp16 (3-MMA, fp32-grade) tensor-core kernels where available. */
+int dctts_set_tensor_path(dctts_handle h, int32_t mode);
+/* Measurement aid for bench.py's roofline leg: runs the block `scope` on a synthetic
+ * (B,L,Cin) input `warmup`+`iters` times and returns the mean device time of each of its
+ * kernels (CUDA events on `stream` around every launch), ms_per_kernel[0..*n_kernels), <= 8. */
+int dctts_bench_block(dctts_handle h, const char* scope, int32_t B, int32_t L, int32_t iters,
+                      int32_t warmup, float* ms_per_kernel, int32_t* n_kernels, void* stream);
+/* Raw device memory helpers so that a host without torch can drive the library. */
+int dctts_malloc(dctts_handle h, void** ptr, int64_t bytes);
+int dctts_free(dctts_handle h, void* ptr);
+int dctts_memcpy_h2d(dctts_handle h, void* dst, const void* src, int64_t bytes, void* stream);
+int dctts_memcpy_d2h(dctts_handle h, void* dst, const void* src, int64_t bytes, void* stream);
+int dctts_malloc_host(dctts_handle h, void** ptr, int64_t bytes);   /* pinned */
+int dctts_free_host(dctts_handle h, void* ptr);
+int dctts_stream_sync(dctts_handle h, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* DCTTS_H_ */
