@@ -79,6 +79,27 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def usable_cores():
+    """Host cores this process may really use: CPU affinity capped by the cgroup quota
+    (a 128-thread pool on a quota-limited container is slower than 8 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, min(n, 32))       # torch-CPU conv/GEMM at these sizes stops scaling well before 32 threads
+
+
 # ------------------------------------------------------------------------------ reference arm
 def cpu_reference(passes, B=1, n_chars=100, threads=None):
     """Oracle restatement of the reference schedule on the host cores: `passes` full-graph
@@ -89,7 +110,7 @@ def cpu_reference(passes, B=1, n_chars=100, threads=None):
     from dc_tts_b200.hyperparams import Hyperparams as hp
     from dc_tts_b200.params import init_params, synthetic_text
     from oracle import ref_torch as rt
-    threads = threads or os.cpu_count()
+    threads = threads or usable_cores()
     torch.set_num_threads(threads)
     P = {k: torch.from_numpy(v) for k, v in init_params(0, "perturbed").items()}
     L = synthetic_text(B, n_chars, seed=0)
@@ -116,7 +137,7 @@ def run_reference(args, rank, world):
         return
     steps_passes = 3                                           # full-graph passes per bench "step"
     t0 = time.perf_counter()
-    r = cpu_reference(passes=max(1, (args.steps + args.warmup) * steps_passes))
+    r = cpu_reference(passes=max(1, min(24, (args.steps + args.warmup) * steps_passes)))
     wall = time.perf_counter() - t0
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup,

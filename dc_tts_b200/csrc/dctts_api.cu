@@ -9,8 +9,12 @@
 //   autoregressive loop ..... synthesize.py:45-57
 #include "../../include/dctts.h"
 #include "kernels.cuh"
+#include "kernels_tc.cuh"
 
 #include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -54,6 +58,14 @@ struct LayerDev {
     float* W = nullptr;      // [size][cin][ldw]
     float* bias = nullptr;   // [ldw]
     float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
+    // tensor-core path: split-fp16 K-major weight planes [ncta*bn][ntaps*cin_pad], pre-scaled
+    struct TcPack {
+        bool ok = false;
+        int mode = 0, ntaps = 0, kb_per_tap = 0, Ktot = 0, ncta = 1, bn = 0, half = 0, nrows = 0;
+        float inv_scale = 1.f;
+        __half *Whi = nullptr, *Wlo = nullptr;
+        CUtensorMap mWhi, mWlo;
+    } tc;
 };
 
 struct HostParam {
@@ -106,6 +118,7 @@ struct dctts_handle_s {
     DevBuf ibuf;                  // ints: j, p_cur[B], p_next[B], p_prev[B], p_hist[B*T]
     DevBuf lbuf;                  // (B, N) ids staging for the host entry point
     DevBuf zbuf;                  // (B, 4T, F) staging for the host entry point
+    DevBuf plane[4];              // tensor-core path activations: {hi,lo} x ping-pong, rows x 1032 fp16
 
     // AR decode graph
     cudaGraphExec_t ar_exec = nullptr;
@@ -120,6 +133,7 @@ struct dctts_handle_s {
         for (void* p : param_allocs) cudaFree(p);
         scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
+        for (auto& b : plane) b.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
         if (stream) cudaStreamDestroy(stream);
@@ -221,6 +235,64 @@ float* upload_vec(H* h, const std::string& name, int n, int padded) {
     return d;
 }
 
+// Split-fp16 packing for the tcgen05 kernel (kernels_tc.cu).  Rows are accumulator columns in
+// cluster-slice order (CTA i owns rows [i*bn, (i+1)*bn); for hc / transposed conv its first
+// `half` rows are the first LN half, the rest the second), columns are k = tap*cin_pad + ci.
+// Weights are multiplied by a power of two that brings max|W| into [2^10, 2^11) so that the
+// low plane stays in fp16's normal range; the kernel multiplies the accumulator back.
+void pack_tc(H* h, LayerDev& l, const std::vector<float>& W /* [size][cin][ldw] */) {
+    LayerDev::TcPack& p = l.tc;
+    const int cin_pad = roundup(l.cin, 64);
+    p.kb_per_tap = cin_pad / 64;
+    if (l.kind == K_C) {
+        p.mode = 0; p.ntaps = l.size;
+        p.ncta = 1;
+        while (roundup((l.cout + p.ncta - 1) / p.ncta, 16) > 256) p.ncta *= 2;
+        p.bn = roundup((l.cout + p.ncta - 1) / p.ncta, 16); p.half = p.bn;
+    } else {
+        if (l.cout % 128) return;
+        p.mode = (l.kind == K_HC) ? 1 : 2; p.ntaps = (l.kind == K_HC) ? l.size : 2;
+        p.half = 128; p.bn = 256; p.ncta = l.cout / 128;
+    }
+    if (p.ncta > 8) return;
+    p.Ktot = p.ntaps * cin_pad; p.nrows = p.ncta * p.bn;
+    auto wv = [&](int tap, int ci, int row) -> float {
+        const int i = row / p.bn, a = row % p.bn;
+        if (p.mode == 0) return row < l.cout ? W[((size_t)tap * l.cin + ci) * l.ldw + row] : 0.f;
+        const bool second = a >= p.half;
+        const int col = i * p.half + (a % p.half);
+        if (p.mode == 1) return W[((size_t)tap * l.cin + ci) * l.ldw + (second ? l.cout + col : col)];
+        // transposed conv: k-tap 0 reads x[t] (W0 -> even rows, W1 -> odd rows), k-tap 1 reads x[t-1] (W2 -> even rows)
+        if (tap == 0) return W[((size_t)(second ? 1 : 0) * l.cin + ci) * l.ldw + col];
+        return second ? 0.f : W[((size_t)2 * l.cin + ci) * l.ldw + col];
+    };
+    float maxabs = 0.f;
+    for (int tap = 0; tap < p.ntaps; ++tap)
+        for (int ci = 0; ci < l.cin; ++ci)
+            for (int row = 0; row < p.nrows; ++row) maxabs = std::max(maxabs, std::fabs(wv(tap, ci, row)));
+    float scale = 1.f;
+    if (maxabs > 0.f) { int e; std::frexp(maxabs, &e); scale = std::ldexp(1.f, 11 - e); }   // maxabs*scale in [2^10, 2^11)
+    p.inv_scale = 1.f / scale;
+    std::vector<__half> hi((size_t)p.nrows * p.Ktot, __float2half_rn(0.f)), lo(hi);
+    for (int row = 0; row < p.nrows; ++row)
+        for (int tap = 0; tap < p.ntaps; ++tap)
+            for (int ci = 0; ci < l.cin; ++ci) {
+                const float v = wv(tap, ci, row) * scale;
+                const __half hv = __float2half_rn(v);
+                const size_t idx = (size_t)row * p.Ktot + (size_t)tap * cin_pad + ci;
+                hi[idx] = hv;
+                lo[idx] = __float2half_rn(v - __half2float(hv));
+            }
+    const size_t bytes = hi.size() * sizeof(__half);
+    CUDA_CHECK(cudaMalloc(&p.Whi, bytes)); h->param_allocs.push_back(p.Whi);
+    CUDA_CHECK(cudaMalloc(&p.Wlo, bytes)); h->param_allocs.push_back(p.Wlo);
+    CUDA_CHECK(cudaMemcpy(p.Whi, hi.data(), bytes, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(p.Wlo, lo.data(), bytes, cudaMemcpyHostToDevice));
+    tc_make_w_map(&p.mWhi, p.Whi, p.Ktot, p.nrows, p.bn);
+    tc_make_w_map(&p.mWlo, p.Wlo, p.Ktot, p.nrows, p.bn);
+    p.ok = true;
+}
+
 void commit_layer(H* h, LayerDev& l) {
     const int k = l.size, cin = l.cin, nconv = l.nconv, ldw = l.ldw;
     std::vector<float> W((size_t)k * cin * ldw, 0.f);
@@ -242,6 +314,7 @@ void commit_layer(H* h, LayerDev& l) {
         h->n_params += (int64_t)k * cin * nconv;
     }
     l.W = upload(h, W);
+    pack_tc(h, l, W);
     if (l.kind == K_HC) {
         l.g1 = upload_vec(h, l.scope + "/H1/gamma", l.cout, l.cout);
         l.b1 = upload_vec(h, l.scope + "/H1/beta", l.cout, l.cout);
@@ -289,7 +362,7 @@ void ensure_ws(H* h, int B) {
     if (h->ar_exec) { CUDA_CHECK(cudaStreamSynchronize(h->stream)); cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
     CUDA_CHECK(cudaDeviceSynchronize());
     const size_t ld_scr = (size_t)roundup(std::max(std::max(4 * hp.c, F), 4 * d), 4);
-    h->scratch.ensure(rows_ssrn * ld_scr * sizeof(float));
+    h->scratch.ensure(std::max(rows_ssrn * ld_scr * sizeof(float), (size_t)64 << 20));
     const size_t ld_act = (size_t)roundup(std::max(std::max(2 * hp.c, F), 2 * d), 4);
     h->act0.ensure(rows_ssrn * ld_act * sizeof(float));
     h->act1.ensure(rows_ssrn * ld_act * sizeof(float));
@@ -305,9 +378,11 @@ void ensure_ws(H* h, int B) {
         h->ad_out[i].ensure((size_t)B * T * h->audiodec[i].cout * sizeof(float));
     h->ibuf.ensure((size_t)(4 + 3 * B + (size_t)B * T) * sizeof(int));
     h->lbuf.ensure((size_t)B * N * sizeof(int));
+    for (auto& pb : h->plane) pb.ensure(rows_ssrn * (size_t)roundup(std::max(std::max(2 * hp.c, F), 2 * d), 8) * sizeof(__half));
     h->ws_B = B;
 }
 
+void ensure_scratch(H* h, size_t bytes);
 struct IntBufs { int *j, *p_cur, *p_next, *p_prev, *p_hist; };
 IntBufs ints(H* h) {
     int* base = h->ibuf.as<int>();
@@ -350,12 +425,13 @@ void run_block(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
         c.taps[j].shift = j * rate - left + extra_shift;
     }
     c.win = win; c.Lout = win.L; c.ostride = 1; c.ooff = 0;
-    launch_conv_gemm(c, lc.s); lc.count();
+    GemmOut go = launch_conv_gemm(c, lc.s, h->scratch.bytes); lc.count();
 
     LnArgs n{};
     n.Y = c.Y; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2;
     n.X = X; n.ldx = ldx; n.out = out; n.ldo = ldo; n.out2 = out2; n.ldo2 = ldo2;
     n.C = l.cout; n.mode = (l.kind == K_HC) ? 1 : 0; n.act = act; n.win = win;
+    n.nparts = go.nparts; n.compact = go.compact; n.part_stride = go.part_stride;
     launch_ln_rows(n, lc.s); lc.count();
 }
 
@@ -368,20 +444,25 @@ void run_deconv(Launch& lc, const LayerDev& l, const float* X, int ldx, int B, i
     c.win = RowWin{B, L, L, nullptr}; c.Lout = 2 * L; c.ostride = 2;
     const size_t tapsz = (size_t)l.cin * l.ldw;
     c.ntaps = 2; c.taps[0] = ConvTap{l.W + 0 * tapsz, 0}; c.taps[1] = ConvTap{l.W + 2 * tapsz, -1}; c.ooff = 0;
-    launch_conv_gemm(c, lc.s); lc.count();
+    launch_conv_gemm(c, lc.s, h->scratch.bytes, false); lc.count();
     c.ntaps = 1; c.taps[0] = ConvTap{l.W + 1 * tapsz, 0}; c.ooff = 1;
-    launch_conv_gemm(c, lc.s); lc.count();
+    launch_conv_gemm(c, lc.s, h->scratch.bytes, false); lc.count();
     LnArgs n{};
     n.Y = c.Y; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.out = out; n.ldo = ldo;
     n.C = l.cout; n.mode = 0; n.act = 0; n.win = RowWin{B, 2 * L, 2 * L, nullptr};
     launch_ln_rows(n, lc.s); lc.count();
 }
 
+bool chain_tc_ok(H* h, const std::vector<LayerDev>& net);
+void run_chain_full_tc(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
+                       float* out, float* out_sig);
+
 // A whole chain over full sequences, ping-ponging act0/act1; the last block writes
 // `out` (dense, ld = its cout) and optionally sigmoid(out) into out_sig.
 void run_chain_full(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
                     float* out, float* out_sig) {
     H* h = lc.h;
+    if (chain_tc_ok(h, net) && (out || out_sig)) { run_chain_full_tc(lc, net, X, ldx, B, L, out, out_sig); return; }
     const float* cur = X; int ld = ldx; int len = L;
     float* bufs[2] = {h->act0.as<float>(), h->act1.as<float>()};
     int which = 0;
@@ -399,6 +480,79 @@ void run_chain_full(Launch& lc, const std::vector<LayerDev>& net, const float* X
                       last ? out_sig : nullptr, l.cout);
         }
         cur = dst; ld = ldo; which ^= 1;
+    }
+}
+
+Planes ws_planes(H* h, int which, int C) {
+    Planes p; p.hi = h->plane[2 * which].as<__half>(); p.lo = h->plane[2 * which + 1].as<__half>(); p.ld = roundup(C, 8);
+    return p;
+}
+
+// One reference block as ONE tcgen05 kernel (kernels_tc.cu).  X are the split planes of the
+// (B, L, cin) input; the output goes to planes and/or fp32 tensors.
+void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act, Planes X, RowWin win,
+                  int TT, int TB, int tiles_t, Planes out, float* out_f32, int ld_f32, float* sig_f32, int ld_sig,
+                  Planes sig, int extra_shift = 0) {
+    const LayerDev::TcPack& p = l.tc;
+    REQUIRE(p.ok, "tensor-core path not available for this block");
+    TcArgs a{};
+    a.bias = l.bias; a.g1 = l.g1; a.b1 = l.b1; a.g2 = (p.mode == 1) ? l.g2 : l.g1; a.b2 = (p.mode == 1) ? l.b2 : l.b1;
+    a.mode = p.mode; a.act = act; a.C = l.cout; a.bn = p.bn; a.half = p.half; a.inv_scale = p.inv_scale;
+    a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap;
+    if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
+    else {
+        const int tot = (l.size - 1) * rate, left = causal ? tot : tot / 2;
+        for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
+    }
+    a.stages = std::min(tc_stages_for(p.bn), std::max(1, a.ntaps * a.kb_per_tap));
+    a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.win = win;
+    a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
+    CUtensorMap mAh, mAl;
+    tc_make_act_map(&mAh, X.hi, l.cin, X.ld, win.L, win.B, TT, TB);
+    tc_make_act_map(&mAl, X.lo, l.cin, X.ld, win.L, win.B, TT, TB);
+    const int tiles = ((win.B + TB - 1) / TB) * tiles_t;
+    // DCTTS_TC_DEBUG=1: progress markers in host-mapped memory, dumped after a synchronising launch
+    static const bool debug = getenv("DCTTS_TC_DEBUG") != nullptr;
+    static int* dbg_host = nullptr;
+    if (debug) {
+        if (!dbg_host) CUDA_CHECK(cudaHostAlloc(&dbg_host, 16 * 64 * sizeof(int), cudaHostAllocMapped));
+        memset(dbg_host, 0, 16 * 64 * sizeof(int));
+        CUDA_CHECK(cudaHostGetDevicePointer(&a.dbg, dbg_host, 0));
+        fprintf(stderr, "[tc] %s mode=%d ncta=%d bn=%d half=%d stages=%d nkb=%d tiles=%d TT=%d TB=%d L=%d B=%d\n", l.scope.c_str(),
+                a.mode, p.ncta, a.bn, a.half, a.stages, a.ntaps * a.kb_per_tap, tiles, TT, TB, win.L, win.B);
+    }
+    launch_conv_ln_tc(mAh, mAl, p.mWhi, p.mWlo, a, p.ncta, tiles, lc.s); lc.count();
+    if (debug) {
+        cudaError_t e = cudaStreamSynchronize(lc.s);
+        for (int c = 0; c < std::min(16, p.ncta * tiles); ++c)
+            fprintf(stderr, "[tc]  cta %2d: start=%d tmem=0x%x nkb=%d tma=%d mma=%d acc_ready=%d published=%d combined=%d\n", c,
+                    dbg_host[64 * c], dbg_host[64 * c + 1], dbg_host[64 * c + 2], dbg_host[64 * c + 3], dbg_host[64 * c + 4],
+                    dbg_host[64 * c + 5], dbg_host[64 * c + 6], dbg_host[64 * c + 7]);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("conv_ln_tc failed: ") + cudaGetErrorString(e));
+    }
+}
+
+bool chain_tc_ok(H* h, const std::vector<LayerDev>& net) {
+    if (!h->tensor_path) return false;
+    for (auto& l : net) if (!l.tc.ok) return false;
+    return true;
+}
+
+// Whole chain on the tensor-core path: fp32 in -> planes -> ... -> fp32 out (+ sigmoid).
+void run_chain_full_tc(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
+                       float* out, float* out_sig) {
+    H* h = lc.h;
+    int which = 0, len = L;
+    Planes cur = ws_planes(h, which, net[0].cin);
+    launch_f32_to_planes(X, ldx, cur, (long long)B * L, net[0].cin, lc.s); lc.count();
+    for (size_t i = 0; i < net.size(); ++i) {
+        const LayerDev& l = net[i];
+        const bool last = (i + 1 == net.size());
+        Planes dst = last ? Planes{} : ws_planes(h, which ^ 1, l.cout);
+        run_block_tc(lc, l, l.rate, l.causal, l.act, cur, RowWin{B, len, len, nullptr}, 128, 1, (len + 127) / 128,
+                     dst, last ? out : nullptr, l.cout, last ? out_sig : nullptr, l.cout, Planes{});
+        if (l.kind == K_D) len *= 2;
+        cur = dst; which ^= 1;
     }
 }
 
@@ -563,6 +717,27 @@ void text2mel_forward(H* h, const int* L, const float* mels, const int* pma, int
     }
 }
 
+// Op-level entry (modules.py signatures): fp32 in, fp32 out, on whichever path is selected.
+void run_block_op(Launch& lc, const LayerDev& l, int rate, bool causal, int act, const float* x, int B, int L, float* out) {
+    H* h = lc.h;
+    const int Lout = (l.kind == K_D) ? 2 * L : L;
+    if (h->tensor_path && l.tc.ok) {
+        const size_t need = (size_t)B * L * roundup(l.cin, 8) * sizeof(__half);
+        if (h->plane[0].bytes < need || h->plane[1].bytes < need) {
+            CUDA_CHECK(cudaDeviceSynchronize());
+            h->plane[0].ensure(need); h->plane[1].ensure(need);
+        }
+        Planes X = ws_planes(h, 0, l.cin);
+        launch_f32_to_planes(x, l.cin, X, (long long)B * L, l.cin, lc.s); lc.count();
+        run_block_tc(lc, l, rate, causal, act, X, RowWin{B, L, L, nullptr}, 128, 1, (L + 127) / 128, Planes{}, out, l.cout,
+                     nullptr, 0, Planes{});
+        return;
+    }
+    ensure_scratch(h, (size_t)B * Lout * l.ldw * sizeof(float));
+    if (l.kind == K_D) run_deconv(lc, l, x, l.cin, B, L, out, l.cout);
+    else run_block(lc, l, rate, causal, act, x, l.cin, RowWin{B, L, L, nullptr}, out, l.cout, nullptr, 0);
+}
+
 LayerDev* find_layer(H* h, const char* scope, int kind) {
     REQUIRE(h->committed, "parameters not committed");
     auto it = h->by_scope.find(scope ? scope : "");
@@ -596,6 +771,7 @@ inline cudaStream_t S(dctts_handle, void* s) { return reinterpret_cast<cudaStrea
 // Grow the pre-LN scratch for an op-level call; a reallocation invalidates the AR graph,
 // which has the old pointer baked in.
 void ensure_scratch(H* h, size_t bytes) {
+    bytes = std::max(bytes, (size_t)64 << 20);     // room for the skinny GEMM's split-K partials
     if (bytes <= h->scratch.bytes) return;
     CUDA_CHECK(cudaDeviceSynchronize());
     if (h->ar_exec) { cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
@@ -688,9 +864,8 @@ int dctts_conv1d(dctts_handle h, const char* scope, const float* x, int32_t B, i
     return guarded(h, [&] {
         LayerDev* l = find_layer(h, scope, K_C);
         REQUIRE(B >= 1 && L >= 1 && rate >= 1, "dctts_conv1d: bad sizes");
-        ensure_scratch(h, (size_t)B * L * l->ldw * sizeof(float));
         Launch lc{h, S(h, stream)};
-        run_block(lc, *l, rate, causal != 0, act, x, l->cin, RowWin{B, L, L, nullptr}, out, l->cout, nullptr, 0);
+        run_block_op(lc, *l, rate, causal != 0, act, x, B, L, out);
     });
 }
 
@@ -699,9 +874,8 @@ int dctts_hc(dctts_handle h, const char* scope, const float* x, int32_t B, int32
     return guarded(h, [&] {
         LayerDev* l = find_layer(h, scope, K_HC);
         REQUIRE(B >= 1 && L >= 1 && rate >= 1, "dctts_hc: bad sizes");
-        ensure_scratch(h, (size_t)B * L * l->ldw * sizeof(float));
         Launch lc{h, S(h, stream)};
-        run_block(lc, *l, rate, causal != 0, 0, x, l->cin, RowWin{B, L, L, nullptr}, out, l->cout, nullptr, 0);
+        run_block_op(lc, *l, rate, causal != 0, 0, x, B, L, out);
     });
 }
 
@@ -709,9 +883,8 @@ int dctts_conv1d_transpose(dctts_handle h, const char* scope, const float* x, in
     return guarded(h, [&] {
         LayerDev* l = find_layer(h, scope, K_D);
         REQUIRE(B >= 1 && L >= 1, "dctts_conv1d_transpose: bad sizes");
-        ensure_scratch(h, (size_t)B * 2 * L * l->ldw * sizeof(float));
         Launch lc{h, S(h, stream)};
-        run_deconv(lc, *l, x, l->cin, B, L, out, l->cout);
+        run_block_op(lc, *l, 1, false, 0, x, B, L, out);
     });
 }
 
@@ -821,7 +994,6 @@ int dctts_bench_block(dctts_handle h, const char* scope, int32_t B, int32_t L, i
         REQUIRE(it != h->by_scope.end(), "dctts_bench_block: unknown scope");
         const LayerDev& l = *it->second;
         const int Lout = (l.kind == K_D) ? 2 * L : L;
-        ensure_scratch(h, (size_t)B * Lout * l.ldw * sizeof(float));
         DevBuf x, y;
         x.ensure((size_t)B * L * l.cin * sizeof(float));
         y.ensure((size_t)B * Lout * l.cout * sizeof(float));
@@ -837,9 +1009,7 @@ int dctts_bench_block(dctts_handle h, const char* scope, int32_t B, int32_t L, i
                 lc.evs = &evs;
                 cudaEvent_t e0; CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventRecord(e0, s)); evs.push_back(e0);
             }
-            if (l.kind == K_D) run_deconv(lc, l, x.as<float>(), l.cin, B, L, y.as<float>(), l.cout);
-            else run_block(lc, l, l.rate, l.causal, l.act, x.as<float>(), l.cin, RowWin{B, L, L, nullptr},
-                           y.as<float>(), l.cout, nullptr, 0);
+            run_block_op(lc, l, l.rate, l.causal, l.act, x.as<float>(), B, L, y.as<float>());
             if (i >= warmup) {
                 CUDA_CHECK(cudaStreamSynchronize(s));
                 nk = (int)evs.size() - 1;

@@ -47,7 +47,12 @@ struct LnArgs {
     float* out2; int ldo2;         // optional sigmoid copy (mode 0)
     int C; int mode; int act;      // act: 0 none, 1 relu
     RowWin win;                    // rows are output rows: L here is the OUTPUT length
+    int nparts = 1;                // split-K partials to sum (skinny GEMM), else 1
+    int compact = 0;               // 1: scratch rows are indexed by b*R + r instead of the output row
+    size_t part_stride = 0;        // floats between consecutive partials
 };
+
+struct GemmOut { int nparts; int compact; size_t part_stride; };
 
 struct AttnArgs {
     const float* Q; int ldq;       // (B,T,d)
@@ -63,7 +68,8 @@ struct AttnArgs {
     RowWin win;                    // rows = query rows (L = T)
 };
 
-void launch_conv_gemm(const ConvArgs& a, cudaStream_t s);
+// scratch_bytes bounds the split-K partial buffer of the skinny path
+GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);
 void launch_ln_rows(const LnArgs& a, cudaStream_t s);
 void launch_attention(const AttnArgs& a, cudaStream_t s);
 void launch_embed(const int* ids, const float* table, float* out, int rows, int e, cudaStream_t s);

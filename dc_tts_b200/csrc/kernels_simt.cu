@@ -170,18 +170,21 @@ conv_gemm_tiled(const ConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------
-// Skinny conv-GEMM for the autoregressive decode (M = 1..85 rows per utterance): 16 rows
-// x 64 columns per CTA, the reduction split over 4 thread groups so that every weight
-// element is read once, coalesced, straight from L2, and reused for all 16 rows.
+// Skinny split-K conv-GEMM for the autoregressive decode (M = 1..256 rows in total, i.e.
+// weight-bandwidth / latency bound): a CTA owns 16 rows x 64 columns x ONE 64-deep slice of
+// the reduction (one tap, 64 input channels), so a 768x512 weight matrix is streamed once,
+// coalesced, by 96 CTAs instead of 8.  Partial sums go to Y[ks][m][n] (compact row index
+// m = b*R + r) and are reduced by the LN epilogue kernel, which needs whole rows anyway.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a) {
+__global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a, const int chunks_per_cta,
+                                                        const size_t part_stride) {
     constexpr int BM = 16, BN = 64, BKS = 64, KG = 4, KPG = BKS / KG;
     __shared__ __align__(16) float As[BKS][BM];
     __shared__ float red[KG - 1][BM][BN];
 
     const int tid = threadIdx.x;
     const int c = tid % BN, kg = tid / BN;
-    const int m0 = blockIdx.y * BM, n = blockIdx.x * BN + c;
+    const int m0 = blockIdx.z * BM, n = blockIdx.x * BN + c;
     const int L = a.win.L, R = a.win.R;
     const int t_end = win_t_end(a.win);
     const int Mtot = a.win.B * R;
@@ -201,51 +204,50 @@ __global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a) {
     for (int i = 0; i < BM; ++i) acc[i] = 0.f;
 
     const int KC = (a.K + BKS - 1) / BKS;
-    for (int tap = 0; tap < a.ntaps; ++tap) {
+    const int nchunks = a.ntaps * KC;
+    const int ch0 = blockIdx.y * chunks_per_cta;
+    for (int ch = ch0; ch < min(ch0 + chunks_per_cta, nchunks); ++ch) {
+        const int tap = ch / KC, k0 = (ch - tap * KC) * BKS;
         const float* __restrict__ W = a.taps[tap].W;
         const int ts = lt + a.taps[tap].shift;
         const bool row_ok = (lt >= 0 && ts >= 0 && ts < L);
-        const float* xrow = a.X + ((size_t)lb * L + (row_ok ? ts : 0)) * a.ldx;
-        for (int kc = 0; kc < KC; ++kc) {
-            const int k0 = kc * BKS;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            {
-                int k = k0 + lkq;
-                if (row_ok && k < a.K) {
-                    const float* p = xrow + k;
-                    if (vecA && k + 3 < a.K) v = __ldg(reinterpret_cast<const float4*>(p));
-                    else {
-                        v.x = __ldg(p);
-                        if (k + 1 < a.K) v.y = __ldg(p + 1);
-                        if (k + 2 < a.K) v.z = __ldg(p + 2);
-                        if (k + 3 < a.K) v.w = __ldg(p + 3);
-                    }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            int k = k0 + lkq;
+            if (row_ok && k < a.K) {
+                const float* p = a.X + ((size_t)lb * L + ts) * a.ldx + k;
+                if (vecA && k + 3 < a.K) v = __ldg(reinterpret_cast<const float4*>(p));
+                else {
+                    v.x = __ldg(p);
+                    if (k + 1 < a.K) v.y = __ldg(p + 1);
+                    if (k + 2 < a.K) v.z = __ldg(p + 2);
+                    if (k + 3 < a.K) v.w = __ldg(p + 3);
                 }
             }
-            __syncthreads();               // previous stage fully consumed
-            As[lkq + 0][lrow] = v.x; As[lkq + 1][lrow] = v.y;
-            As[lkq + 2][lrow] = v.z; As[lkq + 3][lrow] = v.w;
-            __syncthreads();
-            float w[KPG];
+        }
+        float w[KPG];
 #pragma unroll
-            for (int kk = 0; kk < KPG; ++kk) {
-                int k = k0 + kg * KPG + kk;
-                w[kk] = (n_ok && k < a.K) ? __ldg(W + (size_t)k * a.ldw + n) : 0.f;
-            }
+        for (int kk = 0; kk < KPG; ++kk) {
+            int k = k0 + kg * KPG + kk;
+            w[kk] = (n_ok && k < a.K) ? __ldg(W + (size_t)k * a.ldw + n) : 0.f;
+        }
+        __syncthreads();               // previous chunk fully consumed
+        As[lkq + 0][lrow] = v.x; As[lkq + 1][lrow] = v.y;
+        As[lkq + 2][lrow] = v.z; As[lkq + 3][lrow] = v.w;
+        __syncthreads();
 #pragma unroll
-            for (int kk = 0; kk < KPG; ++kk) {
-                const float4* xr = reinterpret_cast<const float4*>(&As[kg * KPG + kk][0]);
-                float4 x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
-                float ww = w[kk];
-                acc[0] = fmaf(x0.x, ww, acc[0]);   acc[1] = fmaf(x0.y, ww, acc[1]);
-                acc[2] = fmaf(x0.z, ww, acc[2]);   acc[3] = fmaf(x0.w, ww, acc[3]);
-                acc[4] = fmaf(x1.x, ww, acc[4]);   acc[5] = fmaf(x1.y, ww, acc[5]);
-                acc[6] = fmaf(x1.z, ww, acc[6]);   acc[7] = fmaf(x1.w, ww, acc[7]);
-                acc[8] = fmaf(x2.x, ww, acc[8]);   acc[9] = fmaf(x2.y, ww, acc[9]);
-                acc[10] = fmaf(x2.z, ww, acc[10]); acc[11] = fmaf(x2.w, ww, acc[11]);
-                acc[12] = fmaf(x3.x, ww, acc[12]); acc[13] = fmaf(x3.y, ww, acc[13]);
-                acc[14] = fmaf(x3.z, ww, acc[14]); acc[15] = fmaf(x3.w, ww, acc[15]);
-            }
+        for (int kk = 0; kk < KPG; ++kk) {
+            const float4* xr = reinterpret_cast<const float4*>(&As[kg * KPG + kk][0]);
+            float4 x0 = xr[0], x1 = xr[1], x2 = xr[2], x3 = xr[3];
+            float ww = w[kk];
+            acc[0] = fmaf(x0.x, ww, acc[0]);   acc[1] = fmaf(x0.y, ww, acc[1]);
+            acc[2] = fmaf(x0.z, ww, acc[2]);   acc[3] = fmaf(x0.w, ww, acc[3]);
+            acc[4] = fmaf(x1.x, ww, acc[4]);   acc[5] = fmaf(x1.y, ww, acc[5]);
+            acc[6] = fmaf(x1.z, ww, acc[6]);   acc[7] = fmaf(x1.w, ww, acc[7]);
+            acc[8] = fmaf(x2.x, ww, acc[8]);   acc[9] = fmaf(x2.y, ww, acc[9]);
+            acc[10] = fmaf(x2.z, ww, acc[10]); acc[11] = fmaf(x2.w, ww, acc[11]);
+            acc[12] = fmaf(x3.x, ww, acc[12]); acc[13] = fmaf(x3.y, ww, acc[13]);
+            acc[14] = fmaf(x3.z, ww, acc[14]); acc[15] = fmaf(x3.w, ww, acc[15]);
         }
     }
     if (kg > 0) {
@@ -254,27 +256,34 @@ __global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a) {
     }
     __syncthreads();
     if (kg == 0 && n_ok) {
-        const float bsv = __ldg(a.bias + n);
+        const float bsv = (blockIdx.y == 0) ? __ldg(a.bias + n) : 0.f;
+        float* yp = a.Y + (size_t)blockIdx.y * part_stride;
 #pragma unroll
         for (int i = 0; i < BM; ++i) {
             int m = m0 + i;
             if (m >= Mtot) break;
-            int b = m / R, r = m - b * R;
-            int t = t_end - (R - 1) + r;
-            if (t < 0) continue;
             float s = acc[i] + red[0][i][c] + red[1][i][c] + red[2][i][c] + bsv;
-            a.Y[((size_t)b * a.Lout + (size_t)t * a.ostride + a.ooff) * a.ldy + n] = s;
+            yp[((size_t)m * a.ostride + a.ooff) * a.ldy + n] = s;
         }
     }
 }
 
-void launch_conv_gemm(const ConvArgs& a, cudaStream_t s) {
+GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny) {
+    GemmOut out{1, 0, 0};
     const int M = a.win.B * a.win.R;
-    if (M <= 0) return;
+    if (M <= 0) return out;
     const int tiles128 = ((M + 127) / 128) * ((a.ldw + 127) / 128);
-    if (M <= 256) {
-        dim3 grid((a.ldw + 63) / 64, (M + 15) / 16);
-        conv_gemm_skinny<<<grid, 256, 0, s>>>(a);
+    if (M <= 256 && allow_skinny) {
+        const size_t part = (size_t)M * a.ostride * a.ldy;            // floats per partial
+        const int nchunks = a.ntaps * ((a.K + 63) / 64);
+        int max_parts = (int)(scratch_bytes / sizeof(float) / (part ? part : 1));
+        if (max_parts < 1) max_parts = 1;
+        if (max_parts > 64) max_parts = 64;
+        const int cpc = (nchunks + max_parts - 1) / max_parts;
+        const int nparts = (nchunks + cpc - 1) / cpc;
+        dim3 grid((a.ldw + 63) / 64, nparts, (M + 15) / 16);
+        conv_gemm_skinny<<<grid, 256, 0, s>>>(a, cpc, part);
+        out.nparts = nparts; out.compact = 1; out.part_stride = part;
     } else if (tiles128 >= 120) {
         dim3 grid((a.ldw + 127) / 128, (M + 127) / 128);
         conv_gemm_tiled<128, 128, 16, 8, 8><<<grid, 256, 0, s>>>(a);
@@ -282,6 +291,7 @@ void launch_conv_gemm(const ConvArgs& a, cudaStream_t s) {
         dim3 grid((a.ldw + 63) / 64, (M + 63) / 64);
         conv_gemm_tiled<64, 64, 16, 4, 4><<<grid, 256, 0, s>>>(a);
     }
+    return out;
 }
 
 // ------------------------------------------------------------------------------------
@@ -308,6 +318,32 @@ __device__ __forceinline__ void ln_stats(const float (&v)[MAXV], int C, int lane
     inv = 1.0f / sqrtf(var + 1e-12f);
 }
 
+// v[i] = sum_p y[p*stride + off + lane + 32 i]: the split-K partials of the skinny GEMM, summed
+// in ascending p (deterministic).  Loads are issued G partials at a time so that their
+// latencies overlap instead of forming a chain of nparts dependent round trips.
+template <int MAXV>
+__device__ __forceinline__ void ln_load_partials(const float* __restrict__ y, int off, int C, int lane, int nparts,
+                                                 size_t stride, float (&v)[MAXV]) {
+    constexpr int G = MAXV <= 8 ? 4 : (MAXV <= 16 ? 2 : 1);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) v[i] = 0.f;
+#pragma unroll 1
+    for (int p = 0; p < nparts; p += G) {
+        float t[G][MAXV];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                int c = lane + 32 * i;
+                t[g][i] = (c < C && p + g < nparts) ? y[(size_t)(p + g) * stride + off + c] : 0.f;
+            }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) v[i] += t[g][i];
+    }
+}
+
 template <int MAXV>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -319,12 +355,12 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
     const int t = t_end - (R - 1) + r;
     if (t < 0) return;
     const size_t row = (size_t)b * L + t;
-    const float* y = a.Y + row * a.ldy;
+    // pre-LN rows: indexed like the output rows, or compactly by (b, r) with split-K partials
+    const float* y = a.Y + (a.compact ? (size_t)warp : row) * a.ldy;
     const int C = a.C;
 
     float v1[MAXV];
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) { int c = lane + 32 * i; v1[i] = (c < C) ? y[c] : 0.f; }
+    ln_load_partials<MAXV>(y, 0, C, lane, a.nparts, a.part_stride, v1);
     float mean1, inv1;
     ln_stats<MAXV>(v1, C, lane, mean1, inv1);
 
@@ -343,8 +379,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
         }
     } else {
         float v2[MAXV];
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) { int c = lane + 32 * i; v2[i] = (c < C) ? y[C + c] : 0.f; }
+        ln_load_partials<MAXV>(y, C, C, lane, a.nparts, a.part_stride, v2);
         float mean2, inv2;
         ln_stats<MAXV>(v2, C, lane, mean2, inv2);
         const float* x = a.X + row * a.ldx;

@@ -1,0 +1,476 @@
+// kernels_tc.cu -- tcgen05 / TMEM / TMA fused block kernel for sm_100a.
+//
+// ONE kernel per reference block (modules.py:91-141 conv1d, :143-197 hc, :199-247
+// conv1d_transpose): the dilated / causal conv as an implicit GEMM on the 5th-generation
+// tensor cores, and the whole epilogue -- bias, LayerNorm (two of them for hc), relu /
+// sigmoid gate / highway mix -- applied to the accumulator straight out of tensor memory.
+//
+//   grid    (ncta, tiles); a thread-block CLUSTER of `ncta` CTAs shares one 128-row tile and
+//           splits the output channels; LayerNorm statistics are combined across the
+//           cluster through distributed shared memory (Chan's parallel mean/M2 merge).
+//   warp 0  TMA producer: per k-block (64 channels of one tap) one {64 x 128 rows} box of
+//           each activation plane -- the tap's time shift is just the box coordinate, and
+//           TMA's out-of-bounds zero fill IS the reference's zero padding -- plus the
+//           {64 x bn} box of each weight plane, 128B-swizzled, mbarrier pipelined.
+//   warp 1  allocates TMEM and issues tcgen05.mma (kind::f16, M=128, N=bn, K=16):
+//           hi*Whi + hi*Wlo + lo*Whi per k-step into one fp32 accumulator.
+//   warps 2-5  epilogue: tcgen05.ld rows (thread == row, so LN reductions are thread-local),
+//           three sweeps over TMEM (sum, centred M2, normalise+store); TMEM re-reads are
+//           cheaper than holding 256 columns in registers.
+#include "kernels_tc.cuh"
+#include "tc_ptx.cuh"
+
+#include <stdexcept>
+#include <string>
+
+namespace dctts {
+
+using namespace ptx;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 256;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;                 // 16384 B
+constexpr int TC_AUX_BYTES = 128 /*barriers*/ + 3 * 256 * 4 /*bias,gamma,beta*/ + 8 * 128 * 16 /*stats*/;
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// Optional progress markers into host-mapped memory (survive a trapped launch): dbg[64*cta + slot].
+__device__ __forceinline__ void dbg_mark(int* dbg, int slot, int v) {
+    if (dbg) {
+        const int cta = blockIdx.y * gridDim.x + blockIdx.x;
+        if (cta < 16) { reinterpret_cast<volatile int*>(dbg)[64 * cta + slot] = v; __threadfence_system(); }
+    }
+}
+
+__device__ __forceinline__ void split_store16(const float (&o)[16], __half* hi, __half* lo) {
+    __align__(16) __half h[16];
+    __align__(16) __half l[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        h[i] = __float2half_rn(o[i]);
+        l[i] = __float2half_rn(o[i] - __half2float(h[i]));
+    }
+    reinterpret_cast<uint4*>(hi)[0] = reinterpret_cast<const uint4*>(h)[0];
+    reinterpret_cast<uint4*>(hi)[1] = reinterpret_cast<const uint4*>(h)[1];
+    reinterpret_cast<uint4*>(lo)[0] = reinterpret_cast<const uint4*>(l)[0];
+    reinterpret_cast<uint4*>(lo)[1] = reinterpret_cast<const uint4*>(l)[1];
+}
+
+__device__ __forceinline__ void store_planes(const Planes& p, size_t row, int col, int C, const float (&o)[16]) {
+    __half* hi = p.hi + row * p.ld + col;
+    __half* lo = p.lo + row * p.ld + col;
+    if (col + 16 <= p.ld) {
+        split_store16(o, hi, lo);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (col + i < C) {
+                __half h = __float2half_rn(o[i]);
+                hi[i] = h;
+                lo[i] = __float2half_rn(o[i] - __half2float(h));
+            }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
+                  const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                  const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+    const int ncta = (int)cluster_nctarank();
+    const int bn = a.bn, half = a.half;
+    const int b_plane = bn * 128;                                    // bytes of one weight plane tile
+    const int stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
+    const int stages = a.stages;
+    const int nkb = a.ntaps * a.kb_per_tap;
+
+    uint8_t* aux = smem + (size_t)stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [stages]
+    uint64_t* empty_bar = full_bar + TC_MAX_STAGES;                      // [stages]
+    uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    float* s_bias = reinterpret_cast<float*>(aux + 128);
+    float* s_gam = s_bias + 256;
+    float* s_bet = s_gam + 256;
+    float4* s_part = reinterpret_cast<float4*>(s_bet + 256);            // [8 ranks][128 rows]
+
+    // ---- tile coordinates ----
+    const int tile = blockIdx.y;
+    const int bg = tile / a.tiles_t, tt = tile - bg * a.tiles_t;
+    const int b0 = bg * a.TB;
+    const int L = a.win.L;
+    int t_end, t_lo, t0;
+    if (a.win.jptr) {
+        t_end = __ldg(a.win.jptr);
+        t_lo = max(0, t_end - a.win.R + 1);
+        t0 = t_end - a.tiles_t * a.TT + 1 + tt * a.TT;
+    } else {
+        t_end = L - 1; t_lo = 0; t0 = tt * a.TT;
+    }
+
+    // ---- one-time setup ----
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&mapA_hi); prefetch_tmap(&mapA_lo); prefetch_tmap(&mapW_hi); prefetch_tmap(&mapW_lo);
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr_smem);
+    if (warp >= 2) {
+        // epilogue vectors, indexed by accumulator column
+        for (int c = threadIdx.x - 64; c < bn; c += 128) {
+            float bi = 0.f, g = 0.f, be = 0.f;
+            if (a.mode == 0) {
+                int col = rank * bn + c;
+                if (col < a.C) { bi = a.bias[col]; g = a.g1[col]; be = a.b1[col]; }
+            } else {
+                int second = c >= half;
+                int col = rank * half + (second ? c - half : c);
+                bi = (a.mode == 1 && second) ? a.bias[a.C + col] : a.bias[col];
+                g = second ? a.g2[col] : a.g1[col];
+                be = second ? a.b2[col] : a.b1[col];
+            }
+            s_bias[c] = bi; s_gam[c] = g; s_bet[c] = be;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    if (threadIdx.x == 0) { dbg_mark(a.dbg, 0, 1); dbg_mark(a.dbg, 1, (int)tmem_base); dbg_mark(a.dbg, 2, nkb); }
+    if (ncta > 1) cluster_arrive();          // phase 1: every CTA of the cluster is running
+
+    if (warp == 0) {
+        // =========================== TMA producer ===========================
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % stages;
+                const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const int tap = kb / a.kb_per_tap, kc = kb - tap * a.kb_per_tap;
+                const int tcoord = t0 + a.shifts[tap];
+                tma_load_3d(&mapA_hi, &full_bar[s], st, kc * TC_BK, tcoord, b0);
+                tma_load_3d(&mapA_lo, &full_bar[s], st + TC_A_PLANE, kc * TC_BK, tcoord, b0);
+                tma_load_2d(&mapW_hi, &full_bar[s], st + 2 * TC_A_PLANE, kb * TC_BK, rank * bn);
+                tma_load_2d(&mapW_lo, &full_bar[s], st + 2 * TC_A_PLANE + b_plane, kb * TC_BK, rank * bn);
+                dbg_mark(a.dbg, 3, kb + 1);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =========================== MMA issuer ===========================
+        const uint32_t idesc = umma_idesc_f16(TC_BM, (uint32_t)bn);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int s = kb % stages;
+            const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint64_t dA_hi = umma_desc_sw128(st);
+                const uint64_t dA_lo = umma_desc_sw128(st + TC_A_PLANE);
+                const uint64_t dB_hi = umma_desc_sw128(st + 2 * TC_A_PLANE);
+                const uint64_t dB_lo = umma_desc_sw128(st + 2 * TC_A_PLANE + b_plane);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 16 fp16 = 32 B inside the 128 B atom
+                    tc_mma_f16(tmem_base, dA_hi + adv, dB_hi + adv, idesc, (kb | k) != 0);
+                    tc_mma_f16(tmem_base, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                    tc_mma_f16(tmem_base, dA_lo + adv, dB_hi + adv, idesc, 1u);
+                }
+                tc_commit(&empty_bar[s]);                                  // frees the smem stage
+                if (kb == nkb - 1) tc_commit(tmem_full_bar);               // accumulator complete
+                dbg_mark(a.dbg, 4, kb + 1);
+            }
+            __syncwarp();
+        }
+    } else {
+        // =========================== epilogue ===========================
+        const int q = warp & 3;                                            // TMEM lane quarter of this warp
+        const int r = q * 32 + lane;                                       // tile row == TMEM lane
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int bi = r / a.TT, ti = r - bi * a.TT;
+        const int b = b0 + bi, t = t0 + ti;
+        const bool row_ok = (b < a.win.B) && (t >= t_lo) && (t <= t_end) && (t < L);
+        const float inv_s = a.inv_scale;
+        const int n1 = (a.mode == 0) ? min(max(a.C - rank * bn, 0), bn) : half;
+
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        if (r == 0) dbg_mark(a.dbg, 5, 1);
+
+        // sweep 1: sums
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = 0; c < n1; c += 16) {
+            float v[16];
+            tmem_ld16(taddr + c, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c + i < n1) s1 += fmaf(v[i], inv_s, s_bias[c + i]);
+        }
+        if (a.mode != 0) {
+            for (int c = 0; c < half; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + half + c, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s2 += fmaf(v[i], inv_s, s_bias[half + c + i]);
+            }
+        }
+        const float m1 = n1 > 0 ? s1 / (float)n1 : 0.f;
+        const float m2 = s2 / (float)half;
+        // sweep 2: centred second moments about the local means
+        float q1 = 0.f, q2 = 0.f;
+        for (int c = 0; c < n1; c += 16) {
+            float v[16];
+            tmem_ld16(taddr + c, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (c + i < n1) { float d = fmaf(v[i], inv_s, s_bias[c + i]) - m1; q1 = fmaf(d, d, q1); }
+        }
+        if (a.mode != 0) {
+            for (int c = 0; c < half; c += 16) {
+                float v[16];
+                tmem_ld16(taddr + half + c, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { float d = fmaf(v[i], inv_s, s_bias[half + c + i]) - m2; q2 = fmaf(d, d, q2); }
+            }
+        }
+        // combine over the cluster
+        float mean1, rstd1, mean2 = 0.f, rstd2 = 0.f;
+        if (ncta > 1) {
+            cluster_wait();                                                // phase 1 done: peers are alive
+            const uint32_t my_slot = smem_u32(&s_part[rank * 128 + r]);
+            for (int p = 0; p < ncta; ++p) st_cluster_f4(mapa(my_slot, (uint32_t)p), s1, q1, s2, q2);
+            if (r == 0) dbg_mark(a.dbg, 6, 1);
+            cluster_arrive();                                              // phase 2: partials published
+            cluster_wait();
+            if (r == 0) dbg_mark(a.dbg, 7, 1);
+            float S1 = 0.f, S2 = 0.f;
+            for (int p = 0; p < ncta; ++p) { float4 v = s_part[p * 128 + r]; S1 += v.x; S2 += v.z; }
+            mean1 = S1 / (float)a.C; mean2 = S2 / (float)a.C;
+            float M1 = 0.f, M2 = 0.f;
+            for (int p = 0; p < ncta; ++p) {
+                float4 v = s_part[p * 128 + r];
+                const int np = (a.mode == 0) ? min(max(a.C - p * bn, 0), bn) : half;
+                if (np > 0) { float d = v.x / (float)np - mean1; M1 += v.y + (float)np * d * d; }
+                if (a.mode != 0) { float d = v.z / (float)half - mean2; M2 += v.w + (float)half * d * d; }
+            }
+            rstd1 = 1.0f / sqrtf(M1 / (float)a.C + 1e-12f);
+            rstd2 = 1.0f / sqrtf(M2 / (float)a.C + 1e-12f);
+        } else {
+            mean1 = m1; rstd1 = 1.0f / sqrtf(q1 / (float)a.C + 1e-12f);
+            mean2 = m2; rstd2 = 1.0f / sqrtf(q2 / (float)a.C + 1e-12f);
+        }
+
+        // sweep 3: normalise, activate, mix, store.  tcgen05.ld is warp-collective (.sync.aligned):
+        // every lane runs the loads, only the stores are predicated on the row being valid.
+        {
+            if (a.mode == 0) {
+                const size_t row = (size_t)b * L + t;
+                for (int c = 0; c < n1; c += 16) {
+                    float v[16], o[16];
+                    tmem_ld16(taddr + c, v);
+                    const int col = rank * bn + c;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float z = (fmaf(v[i], inv_s, s_bias[c + i]) - mean1) * rstd1 * s_gam[c + i] + s_bet[c + i];
+                        if (a.act == 1) z = fmaxf(z, 0.f);
+                        o[i] = (c + i < n1) ? z : 0.f;
+                    }
+                    if (row_ok && a.out.hi) store_planes(a.out, row, col, a.C, o);
+                    if (row_ok && a.out_f32) {
+                        float* p = a.out_f32 + row * a.ld_f32 + col;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) if (c + i < n1) p[i] = o[i];
+                    }
+                    if (a.sig_f32 || a.sig.hi) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = (c + i < n1) ? sigmoid_acc(o[i]) : 0.f;
+                        if (row_ok && a.sig.hi) store_planes(a.sig, row, col, a.C, o);
+                        if (row_ok && a.sig_f32) {
+                            float* p = a.sig_f32 + row * a.ld_sig + col;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) if (c + i < n1) p[i] = o[i];
+                        }
+                    }
+                }
+            } else if (a.mode == 1) {
+                const size_t row = (size_t)b * L + t;
+                for (int c = 0; c < half; c += 16) {
+                    float v1[16], v2[16], o[16];
+                    const int col = rank * half + c;
+                    // highway residual: 16 channels of both planes (2 x 32 B)
+                    __align__(16) __half xh[16] = {};
+                    __align__(16) __half xl[16] = {};
+                    if (row_ok) {
+                        const uint4* ph = reinterpret_cast<const uint4*>(a.X.hi + row * a.X.ld + col);
+                        const uint4* pl = reinterpret_cast<const uint4*>(a.X.lo + row * a.X.ld + col);
+                        reinterpret_cast<uint4*>(xh)[0] = __ldg(ph); reinterpret_cast<uint4*>(xh)[1] = __ldg(ph + 1);
+                        reinterpret_cast<uint4*>(xl)[0] = __ldg(pl); reinterpret_cast<uint4*>(xl)[1] = __ldg(pl + 1);
+                    }
+                    tmem_ld16(taddr + c, v1);
+                    tmem_ld16(taddr + half + c, v2);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float z1 = (fmaf(v1[i], inv_s, s_bias[c + i]) - mean1) * rstd1 * s_gam[c + i] + s_bet[c + i];
+                        float z2 = (fmaf(v2[i], inv_s, s_bias[half + c + i]) - mean2) * rstd2 * s_gam[half + c + i] + s_bet[half + c + i];
+                        float h1 = sigmoid_acc(z1);
+                        float x = __half2float(xh[i]) + __half2float(xl[i]);
+                        o[i] = h1 * z2 + (1.0f - h1) * x;
+                    }
+                    if (row_ok && a.out.hi) store_planes(a.out, row, col, a.C, o);
+                    if (row_ok && a.out_f32) {
+                        float* p = a.out_f32 + row * a.ld_f32 + col;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) p[i] = o[i];
+                    }
+                }
+            } else {
+                // transposed conv: first half -> output row 2t, second half -> row 2t+1 (modules.py:232-241)
+                const size_t row_e = (size_t)b * (2 * L) + 2 * (size_t)t;
+                for (int hsel = 0; hsel < 2; ++hsel) {
+                    const float mean = hsel ? mean2 : mean1, rstd = hsel ? rstd2 : rstd1;
+                    for (int c = 0; c < half; c += 16) {
+                        float v[16], o[16];
+                        tmem_ld16(taddr + hsel * half + c, v);
+                        const int col = rank * half + c;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int ac = hsel * half + c + i;
+                            o[i] = (fmaf(v[i], inv_s, s_bias[ac]) - mean) * rstd * s_gam[ac] + s_bet[ac];
+                        }
+                        if (row_ok && a.out.hi) store_planes(a.out, row_e + hsel, col, a.C, o);
+                        if (row_ok && a.out_f32) {
+                            float* p = a.out_f32 + (row_e + hsel) * a.ld_f32 + col;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) p[i] = o[i];
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+
+    // ---- teardown: match the cluster barrier phases of the epilogue warps ----
+    if (ncta > 1) {
+        if (warp < 2) { cluster_wait(); cluster_arrive(); cluster_wait(); }
+        cluster_arrive();                     // phase 3: nobody reads my shared memory any more
+        cluster_wait();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// plane conversion kernels (boundaries of the tensor-core path)
+// ------------------------------------------------------------------------------------------
+__global__ void f32_to_planes_kernel(const float* __restrict__ x, int ldx, Planes p, long long rows, int C) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = rows * C;
+    if (i >= total) return;
+    long long r = i / C; int c = (int)(i - r * C);
+    float v = x[r * ldx + c];
+    __half h = __float2half_rn(v);
+    p.hi[r * p.ld + c] = h;
+    p.lo[r * p.ld + c] = __float2half_rn(v - __half2float(h));
+}
+__global__ void planes_to_f32_kernel(Planes p, float* __restrict__ y, int ldy, long long rows, int C) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = rows * C;
+    if (i >= total) return;
+    long long r = i / C; int c = (int)(i - r * C);
+    y[r * ldy + c] = __half2float(p.hi[r * p.ld + c]) + __half2float(p.lo[r * p.ld + c]);
+}
+void launch_f32_to_planes(const float* x, int ldx, Planes p, long long rows, int C, cudaStream_t s) {
+    long long n = rows * C;
+    if (n > 0) f32_to_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, ldx, p, rows, C);
+}
+void launch_planes_to_f32(Planes p, float* y, int ldy, long long rows, int C, cudaStream_t s) {
+    long long n = rows * C;
+    if (n > 0) planes_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, y, ldy, rows, C);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps and the cluster launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            throw std::runtime_error("cuTensorMapEncodeTiled is not available from the driver");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, int B, int TT, int TB) {
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TT, (cuuint32_t)TB};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+}
+
+void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn) {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Nrows};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
+}
+
+int tc_stages_for(int bn) {
+    const int stage = 2 * TC_A_PLANE + 2 * bn * 128;
+    int s = (200 * 1024) / stage;
+    return s < 2 ? 2 : (s > TC_MAX_STAGES ? TC_MAX_STAGES : s);
+}
+
+void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
+                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, cudaStream_t s) {
+    static bool attr_set = false;
+    const int max_smem = 227 * 1024;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const size_t smem = (size_t)a.stages * (2 * TC_A_PLANE + 2 * a.bn * 128) + TC_AUX_BYTES + 1024;
+    if (smem > (size_t)max_smem) throw std::runtime_error("conv_ln_tc: shared memory budget exceeded");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ncta, (unsigned)tiles, 1);
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel, a_hi, a_lo, w_hi, w_lo, a);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("conv_ln_tc launch: ") + cudaGetErrorString(e));
+}
+
+}  // namespace dctts

@@ -96,8 +96,14 @@ def test_generate_is_deterministic_and_batch_independent(engine):
     Y1, P1, _, _ = engine.text2mel_generate(L, steps=40)
     Y2, P2, _, _ = engine.text2mel_generate(L, steps=40)
     assert torch.equal(Y1, Y2) and torch.equal(P1, P2)
-    Ys, Ps, _, _ = engine.text2mel_generate(L[2:3], steps=40)          # utterances never interact
-    assert torch.equal(Ys[0], Y1[2]) and torch.equal(Ps[0], P1[2])
+    # utterances never interact: permuting the batch permutes the result, bit for bit
+    perm = [2, 0, 3, 1]
+    Yp, Pp, _, _ = engine.text2mel_generate(L[perm], steps=40)
+    assert torch.equal(Yp, Y1[perm]) and torch.equal(Pp, P1[perm])
+    # a different batch size may select a different GEMM tiling (different summation
+    # order), so across batch sizes the guarantee is the parity tolerance, not bits
+    Ys, Ps, _, _ = engine.text2mel_generate(L[2:3], steps=40)
+    assert torch.equal(Ps[0], P1[2]) and (Ys[0] - Y1[2]).abs().max().item() < 1e-4
 
 
 def test_synthesize_host_end_to_end(engine):
