@@ -177,8 +177,7 @@ def run_b200(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     eng = Engine(local_rank)
     eng.load_params(init_params(0, "perturbed"))
-    if args.tensor_path is not None:
-        eng.set_tensor_path(args.tensor_path)
+    eng.set_tensor_path(args.tensor_path)
     B, T, F = args.batch, hp.max_T, 1 + hp.n_fft // 2
     eng.reserve(B)
     L_host = torch.from_numpy(synthetic_text(B, args.nchars, seed=0, first_index=rank * B)).pin_memory()
@@ -243,12 +242,17 @@ def run_b200(args, rank, local_rank, world):
         rows = B * T * hp.r
         kms = eng.bench_block("SSRN/HC_11", B, T * hp.r, iters=5, warmup=2)
         flops = 2.0 * rows * 3 * 1024 * 2048
-        ach = flops / (kms[0] * 1e-3) / 1e12
-        roof = {"kernel": "SSRN/HC_11 conv-GEMM (M=%d, K=3x1024, N=2048)" % rows, "bound": "tensor",
-                "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
-                "traffic": None, "peak_source": peaks["src"] + " bf16 dense (burst)",
-                "kernel_ms": kms[0], "epilogue_ms": kms[1:],
-                "note": "algorithmic FLOPs 2*M*K*N / CUDA-event time of that launch"}
+        tensor = args.tensor_path != 0
+        k_ms = kms[1] if tensor else kms[0]          # tensor path: [fp32->planes, fused block]; fp32 path: [GEMM, LN]
+        ach = flops / (k_ms * 1e-3) / 1e12
+        roof = {"kernel": ("conv_ln_tc_kernel: SSRN/HC_11 fused hc block on tcgen05 (M=%d, K=3x1024, N=2048, 3 fp16 MMA "
+                           "passes per k-step)" if tensor else "conv_gemm_tiled: SSRN/HC_11 conv-GEMM on fp32 cores (M=%d, K=3x1024, N=2048)") % rows,
+                "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
+                "traffic": None, "peak_source": peaks["src"] + " bf16/fp16 dense (burst)",
+                "kernel_ms": k_ms, "other_kernels_of_block_ms": [m for i, m in enumerate(kms) if m != k_ms],
+                "tensor_pipe_flops_executed_tflops": (3 * ach if tensor else 0.0),
+                "note": "achieved = ALGORITHMIC FLOPs 2*M*K*N / CUDA-event time of that launch; the split-fp16 "
+                        "scheme needed for the 1e-3 parity budget executes 3x that on the tensor pipe, so frac <= 1/3"}
         # ---- single-utterance latency (BASELINE config 2 + SSRN): RTF target >= 200x
         L1 = L_dev[:1].contiguous()
         for _ in range(2):
@@ -263,7 +267,7 @@ def run_b200(args, rank, local_rank, world):
         cpu = cpu_reference(passes=args.cpu_passes) if args.cpu_passes > 0 else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16x2 split operands on tcgen05, fp32 accumulate)" if args.tensor_path else "f32", "data": "synthetic",
                 "config": workload_config(args, world),
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(L_host.numel() * 4),
@@ -288,7 +292,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--nchars", type=int, default=100)
     ap.add_argument("--cpu-passes", type=int, default=12, help="full-graph passes of the CPU baseline sample (0 = skip)")
-    ap.add_argument("--tensor-path", type=int, default=None, choices=[0, 1])
+    ap.add_argument("--tensor-path", type=int, default=1, choices=[0, 1], help="1 = tcgen05 blocks (default), 0 = fp32 CUDA-core kernels only")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -119,13 +119,14 @@ struct dctts_handle_s {
     DevBuf lbuf;                  // (B, N) ids staging for the host entry point
     DevBuf zbuf;                  // (B, 4T, F) staging for the host entry point
     DevBuf plane[4];              // tensor-core path activations: {hi,lo} x ping-pong, rows x 1032 fp16
+    DevBuf arpl[10];              // AR decode planes: R (B,T,2d) and four AudioDec outputs (B,T,d), {hi,lo} each
 
     // AR decode graph
     cudaGraphExec_t ar_exec = nullptr;
     int ar_B = 0;
     int64_t ar_nodes = 0;
 
-    int tensor_path = 0;
+    int tensor_path = 1;          // tcgen05 blocks wherever they apply; 0 forces the fp32 CUDA-core kernels
     int64_t launches = 0;
 
     ~dctts_handle_s() {
@@ -134,6 +135,7 @@ struct dctts_handle_s {
         scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
         for (auto& b : plane) b.release();
+        for (auto& b : arpl) b.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
         if (stream) cudaStreamDestroy(stream);
@@ -379,6 +381,11 @@ void ensure_ws(H* h, int B) {
     h->ibuf.ensure((size_t)(4 + 3 * B + (size_t)B * T) * sizeof(int));
     h->lbuf.ensure((size_t)B * N * sizeof(int));
     for (auto& pb : h->plane) pb.ensure(rows_ssrn * (size_t)roundup(std::max(std::max(2 * hp.c, F), 2 * d), 8) * sizeof(__half));
+    for (int i = 0; i < 10; ++i) {
+        const size_t bytes = (size_t)B * T * (i < 2 ? 2 * d : d) * sizeof(__half);
+        h->arpl[i].ensure(bytes);
+        CUDA_CHECK(cudaMemset(h->arpl[i].p, 0, h->arpl[i].bytes));
+    }
     h->ws_B = B;
 }
 
@@ -558,12 +565,13 @@ void run_chain_full_tc(Launch& lc, const std::vector<LayerDev>& net, const float
 
 void run_attention(Launch& lc, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
                    RowWin win, int N, const int* pma, float* R, float* align, long long* maxatt,
-                   int* p_next, int* p_hist) {
+                   int* p_next, int* p_hist, Planes Rpl = Planes{}) {
     H* h = lc.h;
     REQUIRE(N <= 192, "attention: N exceeds the kernel's key capacity (192)");
     REQUIRE(h->hp.d <= 256, "attention: d exceeds 256");
     AttnArgs a{};
     a.Q = Q; a.ldq = ldq; a.K = K; a.ldk = ldk; a.V = V; a.ldv = ldv;
+    a.r_hi = Rpl.hi; a.r_lo = Rpl.lo; a.ldr_h = Rpl.ld;
     a.Rout = R; a.ldr = 2 * h->hp.d; a.align = align; a.maxatt = maxatt; a.pma = pma;
     a.p_next = p_next; a.p_hist = p_hist; a.N = N; a.d = h->hp.d; a.win_size = h->hp.attention_win_size;
     a.win = win;
@@ -614,15 +622,32 @@ void run_ar_step(Launch& lc, int B) {
     std::vector<int> rows = audiodec_rows(h->audiodec, T);
     const int att_rows = std::min(T, rows[0] + (h->audiodec[0].size - 1) * h->audiodec[0].rate);
     const float* K = h->kv.as<float>();
+    // Large batches run the wide part of the AudioDec pyramid (85..59 rows per utterance) on the
+    // tensor cores, one 128-row tile per utterance ending at row j; the narrow tail and the
+    // one-row AudioEnc stay on the latency-oriented fp32 kernels.
+    auto on_tc = [&](size_t i) { return h->tensor_path && B >= 8 && i < 4 && rows[i] >= 32 && h->audiodec[i].tc.ok; };
+    auto ar_planes = [&](int idx, int C) {
+        Planes p; p.hi = h->arpl[2 * idx].as<__half>(); p.lo = h->arpl[2 * idx + 1].as<__half>(); p.ld = C; return p;
+    };
+    Planes Rpl = on_tc(0) ? ar_planes(0, 2 * d) : Planes{};
     run_attention(lc, Q, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, att_rows, ib.j}, N, ib.p_cur,
-                  h->rbuf.as<float>(), nullptr, nullptr, ib.p_next, ib.p_hist);
+                  h->rbuf.as<float>(), nullptr, nullptr, ib.p_next, ib.p_hist, Rpl);
     cur = h->rbuf.as<float>(); ld = 2 * d;
+    Planes cur_pl = Rpl;
     for (size_t i = 0; i < h->audiodec.size(); ++i) {
         const LayerDev& l = h->audiodec[i];
         const bool last = (i + 1 == h->audiodec.size());
         float* dst = h->ad_out[i].as<float>();
-        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, rows[i], ib.j}, dst, l.cout,
-                  last ? h->ybuf.as<float>() : nullptr, hp.n_mels);
+        if (on_tc(i)) {
+            const bool next_tc = (i + 1 < h->audiodec.size()) && on_tc(i + 1);
+            Planes outp = next_tc ? ar_planes((int)i + 1, l.cout) : Planes{};
+            run_block_tc(lc, l, l.rate, l.causal, l.act, cur_pl, RowWin{B, T, rows[i], ib.j}, 128, 1, 1, outp,
+                         next_tc ? nullptr : dst, l.cout, nullptr, 0, Planes{});
+            cur_pl = outp;
+        } else {
+            run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, rows[i], ib.j}, dst, l.cout,
+                      last ? h->ybuf.as<float>() : nullptr, hp.n_mels);
+        }
         cur = dst; ld = l.cout;
     }
     launch_ar_advance(ib.p_cur, ib.p_next, ib.j, B, lc.s); lc.count();

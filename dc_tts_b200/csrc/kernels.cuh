@@ -7,6 +7,7 @@
 // falls outside [0, L) contributes zeros (TF zero padding, reference modules.py:121-125).
 // With R == L and jptr == nullptr this is the plain full-sequence case.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -59,6 +60,7 @@ struct AttnArgs {
     const float* K; int ldk;       // (B,N,d)
     const float* V; int ldv;       // (B,N,d)
     float* Rout; int ldr;          // (B,T,2d) = [A.V ; Q]
+    __half* r_hi; __half* r_lo; int ldr_h;   // optional split-plane copy of R for the tensor-core AudioDec
     float* align;                  // (B,N,T) or nullptr
     long long* maxatt;             // (B,T) or nullptr
     const int* pma;                // (B) window start, nullptr -> dense softmax over all keys

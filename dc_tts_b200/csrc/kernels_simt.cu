@@ -493,6 +493,18 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnArg
     float* ro = a.Rout + ((size_t)b * T + t) * a.ldr;
 #pragma unroll
     for (int i = 0; i < 8; ++i) if (lane * 8 + i < d) { ro[lane * 8 + i] = ctx[i]; ro[d + lane * 8 + i] = qv[i]; }
+    if (a.r_hi) {
+        __half* rh = a.r_hi + ((size_t)b * T + t) * a.ldr_h;
+        __half* rl = a.r_lo + ((size_t)b * T + t) * a.ldr_h;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (lane * 8 + i < d) {
+                __half h = __float2half_rn(ctx[i]);
+                rh[lane * 8 + i] = h; rl[lane * 8 + i] = __float2half_rn(ctx[i] - __half2float(h));
+                h = __float2half_rn(qv[i]);
+                rh[d + lane * 8 + i] = h; rl[d + lane * 8 + i] = __float2half_rn(qv[i] - __half2float(h));
+            }
+    }
     if (a.align) {
         for (int n = lane; n < a.N; n += 32) {
             float p_ = (n >= n_lo && n < n_hi) ? pr[n - n_lo] : 0.f;

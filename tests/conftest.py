@@ -35,3 +35,11 @@ def engine(params):
 
 def golden(name):
     return np.load(os.path.join(GOLDEN, name))
+
+
+@pytest.fixture(params=[0, 1], ids=["fp32path", "tensorpath"])
+def path(engine, request):
+    """Runs a GPU test once per arithmetic path: 0 = fp32 CUDA-core kernels, 1 = tcgen05."""
+    engine.set_tensor_path(request.param)
+    yield request.param
+    engine.set_tensor_path(1)

@@ -1,6 +1,8 @@
 """GPU parity tests, block and network level: CUDA path (through the C-ABI) vs the oracle
 on identical seeded inputs.  Tolerances are absolute, in float32: 2e-4 per block (pure
 re-association noise is ~1e-5), 1e-3 per network (the north-star tolerance)."""
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -10,7 +12,7 @@ from dc_tts_b200.hyperparams import Hyperparams as hp
 from dc_tts_b200.params import synthetic_text
 from oracle import ref_torch as rt
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("path")]
 BLOCK_TOL = 2e-4
 NET_TOL = 1e-3
 
@@ -59,7 +61,7 @@ CONV_CASES = [
 @pytest.mark.parametrize("net,scope,B,L", CONV_CASES)
 def test_conv1d_block(engine, params, net, scope, B, L):
     l = _layer(net, scope)
-    x = _rand((B, L, l.cin), hash(scope) % 1000)
+    x = _rand((B, L, l.cin), zlib.crc32(scope.encode()) % 1000)
     full = net + "/" + scope
     out = engine.conv1d(full, x, l.cout, l.rate, l.pad == "CAUSAL", 1 if l.act == "relu" else 0).cpu().numpy()
     ref = rt.conv1d(params, torch.from_numpy(x), full, l.rate, l.pad, l.act).numpy()
@@ -78,7 +80,7 @@ HC_CASES = [
 @pytest.mark.parametrize("net,scope,B,L", HC_CASES)
 def test_hc_block(engine, params, net, scope, B, L):
     l = _layer(net, scope)
-    x = _rand((B, L, l.cin), hash(scope) % 1000 + L)
+    x = _rand((B, L, l.cin), zlib.crc32(scope.encode()) % 1000 + L)
     full = net + "/" + scope
     out = engine.hc(full, x, l.rate, l.pad == "CAUSAL").cpu().numpy()
     ref = rt.hc(params, torch.from_numpy(x), full, l.rate, l.pad).numpy()

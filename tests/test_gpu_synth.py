@@ -12,7 +12,7 @@ from dc_tts_b200.hyperparams import Hyperparams as hp
 from dc_tts_b200.params import synthetic_text
 from oracle import ref_torch as rt
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("path")]
 TOL = 1e-3          # north star: max-abs 1e-3 on mel and linear magnitudes
 
 

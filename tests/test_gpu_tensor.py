@@ -109,3 +109,22 @@ def test_tensor_path_close_to_fp32_path(engine):
     finally:
         engine.set_tensor_path(0)
     assert (Z0 - Z1).abs().max().item() < 1e-4
+
+
+def test_generate_tensor_pyramid_vs_oracle(tc, params):
+    """B >= 8 moves the 85..59-row AudioDec pyramid of every AR step onto tcgen05 (windowed
+    128-row tiles ending at row j); free-running 40 steps against the oracle's literal schedule."""
+    L = np.concatenate([synthetic_text(1, 40 + 15 * i, seed=60 + i) for i in range(8)])
+    steps = 40
+    r = rt.synthesize(params, L, steps=steps, literal=False, record=True)
+    Y, P, _, _ = tc.text2mel_generate(L, steps=steps)
+    Yo, Po = r["Y"].numpy(), r["p_hist"].numpy()
+    ok = r["margin_hist"].numpy().min(1) > 1e-4
+    assert ok.sum() >= 6
+    assert np.array_equal(P.cpu().numpy()[ok, :steps], Po[ok])
+    assert np.abs(Y.cpu().numpy()[ok] - Yo[ok]).max() < NET_TOL
+    # and the same loop on the fp32 kernels
+    tc.set_tensor_path(0)
+    Y0, P0, _, _ = tc.text2mel_generate(L, steps=steps)
+    tc.set_tensor_path(1)
+    assert torch.equal(P0[ok], P[ok]) and (Y0[ok] - Y[ok]).abs().max().item() < 1e-4

@@ -12,7 +12,7 @@ from dc_tts_b200.params import init_params, synthetic_text  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--steps", type=int, default=100)
-ap.add_argument("--tensor-path", type=int, default=0)
+ap.add_argument("--tensor-path", type=int, default=1)
 ap.add_argument("--no-ssrn", action="store_true")
 a = ap.parse_args()
 e = Engine(0)
