@@ -248,13 +248,15 @@ void pack_tc(H* h, LayerDev& l, const std::vector<float>& W /* [size][cin][ldw] 
     p.kb_per_tap = cin_pad / 64;
     if (l.kind == K_C) {
         p.mode = 0; p.ntaps = l.size;
+        // small nets (<= 256 channels) are used on few rows (decode): prefer more, narrower CTAs
+        const int maxbn = (l.cout <= 256 && l.cout % 64 == 0) ? 64 : 256;
         p.ncta = 1;
-        while (roundup((l.cout + p.ncta - 1) / p.ncta, 16) > 256) p.ncta *= 2;
+        while (roundup((l.cout + p.ncta - 1) / p.ncta, 16) > maxbn) p.ncta *= 2;
         p.bn = roundup((l.cout + p.ncta - 1) / p.ncta, 16); p.half = p.bn;
     } else {
-        if (l.cout % 128) return;
         p.mode = (l.kind == K_HC) ? 1 : 2; p.ntaps = (l.kind == K_HC) ? l.size : 2;
-        p.half = 128; p.bn = 256; p.ncta = l.cout / 128;
+        p.half = (l.cout <= 256) ? 64 : 128; p.bn = 2 * p.half; p.ncta = l.cout / p.half;
+        if (l.cout % p.half) return;
     }
     if (p.ncta > 8) return;
     p.Ktot = p.ntaps * cin_pad; p.nrows = p.ncta * p.bn;
@@ -290,8 +292,8 @@ void pack_tc(H* h, LayerDev& l, const std::vector<float>& W /* [size][cin][ldw] 
     CUDA_CHECK(cudaMalloc(&p.Wlo, bytes)); h->param_allocs.push_back(p.Wlo);
     CUDA_CHECK(cudaMemcpy(p.Whi, hi.data(), bytes, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(p.Wlo, lo.data(), bytes, cudaMemcpyHostToDevice));
-    tc_make_w_map(&p.mWhi, p.Whi, p.Ktot, p.nrows, p.bn);
-    tc_make_w_map(&p.mWlo, p.Wlo, p.Ktot, p.nrows, p.bn);
+    tc_make_w_map(&p.mWhi, p.Whi, p.Ktot, p.nrows, p.bn, tc_bk());
+    tc_make_w_map(&p.mWlo, p.Wlo, p.Ktot, p.nrows, p.bn, tc_bk());
     p.ok = true;
 }
 
@@ -461,6 +463,8 @@ void run_deconv(Launch& lc, const LayerDev& l, const float* X, int ldx, int B, i
 }
 
 bool chain_tc_ok(H* h, const std::vector<LayerDev>& net);
+void run_chain_tc_planes(Launch& lc, const std::vector<LayerDev>& net, Planes cur, int which, int B, int L,
+                         float* out, float* out_sig, int first_extra_shift);
 void run_chain_full_tc(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
                        float* out, float* out_sig);
 
@@ -505,18 +509,24 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     TcArgs a{};
     a.bias = l.bias; a.g1 = l.g1; a.b1 = l.b1; a.g2 = (p.mode == 1) ? l.g2 : l.g1; a.b2 = (p.mode == 1) ? l.b2 : l.b1;
     a.mode = p.mode; a.act = act; a.C = l.cout; a.bn = p.bn; a.half = p.half; a.inv_scale = p.inv_scale;
-    a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap;
+    const int bk = tc_bk();
+    a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap * (64 / bk);
     if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
     else {
         const int tot = (l.size - 1) * rate, left = causal ? tot : tot / 2;
         for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
     }
-    a.stages = std::min(tc_stages_for(p.bn), std::max(1, a.ntaps * a.kb_per_tap));
+    a.stages = std::min(tc_stages_for(p.bn, bk), std::max(1, a.ntaps * a.kb_per_tap));
     a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.win = win;
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
+    // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the
+    // tile is 128 consecutive time rows, each CTA contributing 128/ncta of them
+    static const bool no_mcast = getenv("DCTTS_TC_NO_MCAST") != nullptr;
+    a.mcast = (!no_mcast && p.ncta > 1 && TT == 128 && TB == 1) ? 1 : 0;
+    const int box_rows = a.mcast ? TT / p.ncta : TT;
     CUtensorMap mAh, mAl;
-    tc_make_act_map(&mAh, X.hi, l.cin, X.ld, win.L, win.B, TT, TB);
-    tc_make_act_map(&mAl, X.lo, l.cin, X.ld, win.L, win.B, TT, TB);
+    tc_make_act_map(&mAh, X.hi, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
+    tc_make_act_map(&mAl, X.lo, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
     const int tiles = ((win.B + TB - 1) / TB) * tiles_t;
     // DCTTS_TC_DEBUG=1: progress markers in host-mapped memory, dumped after a synchronising launch
     static const bool debug = getenv("DCTTS_TC_DEBUG") != nullptr;
@@ -528,7 +538,7 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
         fprintf(stderr, "[tc] %s mode=%d ncta=%d bn=%d half=%d stages=%d nkb=%d tiles=%d TT=%d TB=%d L=%d B=%d\n", l.scope.c_str(),
                 a.mode, p.ncta, a.bn, a.half, a.stages, a.ntaps * a.kb_per_tap, tiles, TT, TB, win.L, win.B);
     }
-    launch_conv_ln_tc(mAh, mAl, p.mWhi, p.mWlo, a, p.ncta, tiles, lc.s); lc.count();
+    launch_conv_ln_tc(mAh, mAl, p.mWhi, p.mWlo, a, p.ncta, tiles, bk, lc.s); lc.count();
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(lc.s);
         for (int c = 0; c < std::min(16, p.ncta * tiles); ++c)
@@ -540,27 +550,37 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
 }
 
 bool chain_tc_ok(H* h, const std::vector<LayerDev>& net) {
-    if (!h->tensor_path) return false;
+    if (h->tensor_path != 1) return false;
     for (auto& l : net) if (!l.tc.ok) return false;
     return true;
 }
 
-// Whole chain on the tensor-core path: fp32 in -> planes -> ... -> fp32 out (+ sigmoid).
-void run_chain_full_tc(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
-                       float* out, float* out_sig) {
+// Whole chain on the tensor-core path, starting from split planes `cur` (buffer index `which`
+// of the ping-pong pair, or -1 for an external buffer): ... -> fp32 out (+ sigmoid).
+void run_chain_tc_planes(Launch& lc, const std::vector<LayerDev>& net, Planes cur, int which, int B, int L,
+                         float* out, float* out_sig, int first_extra_shift) {
     H* h = lc.h;
-    int which = 0, len = L;
-    Planes cur = ws_planes(h, which, net[0].cin);
-    launch_f32_to_planes(X, ldx, cur, (long long)B * L, net[0].cin, lc.s); lc.count();
+    int len = L;
+    int nxt = (which == 0) ? 1 : 0;
     for (size_t i = 0; i < net.size(); ++i) {
         const LayerDev& l = net[i];
         const bool last = (i + 1 == net.size());
-        Planes dst = last ? Planes{} : ws_planes(h, which ^ 1, l.cout);
+        Planes dst = last ? Planes{} : ws_planes(h, nxt, l.cout);
         run_block_tc(lc, l, l.rate, l.causal, l.act, cur, RowWin{B, len, len, nullptr}, 128, 1, (len + 127) / 128,
-                     dst, last ? out : nullptr, l.cout, last ? out_sig : nullptr, l.cout, Planes{});
+                     dst, last ? out : nullptr, l.cout, last ? out_sig : nullptr, l.cout, Planes{},
+                     i == 0 ? first_extra_shift : 0);
         if (l.kind == K_D) len *= 2;
-        cur = dst; which ^= 1;
+        cur = dst; nxt ^= 1;
     }
+}
+
+// fp32 in -> planes -> chain
+void run_chain_full_tc(Launch& lc, const std::vector<LayerDev>& net, const float* X, int ldx, int B, int L,
+                       float* out, float* out_sig) {
+    H* h = lc.h;
+    Planes cur = ws_planes(h, 0, net[0].cin);
+    launch_f32_to_planes(X, ldx, cur, (long long)B * L, net[0].cin, lc.s); lc.count();
+    run_chain_tc_planes(lc, net, cur, 0, B, L, out, out_sig, 0);
 }
 
 void run_attention(Launch& lc, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv,
@@ -601,6 +621,44 @@ std::vector<int> audiodec_rows(const std::vector<LayerDev>& net, int T) {
     return rows;
 }
 
+// Builds the argument block of the cluster-persistent chain kernel for layers [i0, i1) of `net`.
+// `in` is the input of layer i0, outs[i] the per-layer output buffers (ld = cout).
+bool chain_ok(const std::vector<LayerDev>& net, size_t i0, size_t i1) {
+    if (i1 - i0 > 13) return false;
+    for (size_t i = i0; i < i1; ++i) {
+        const LayerDev& l = net[i];
+        if (l.kind == K_D || (l.cin % 4)) return false;
+        if (l.kind == K_HC && (l.cout % 8 || l.cout / 8 > 32)) return false;
+        if (l.kind == K_C && (l.cout + 7) / 8 > 64) return false;
+    }
+    return true;
+}
+
+void run_chain_kernel(Launch& lc, const std::vector<LayerDev>& net, size_t i0, size_t i1, const std::vector<int>& rows,
+                      const float* in, int ld_in, int first_extra_shift, std::vector<DevBuf>& outs, float* last_sig,
+                      int ld_sig, int B, int T, const int* jptr) {
+    ChainArgs ca{};
+    ca.nlayers = (int)(i1 - i0); ca.B = B; ca.T = T; ca.jptr = jptr;
+    int rmax = 1;
+    for (size_t i = i0; i < i1; ++i) rmax = std::max(rmax, rows[i]);
+    REQUIRE(rmax <= 16, "chain kernel: more than 16 rows per utterance");
+    ca.G = (rmax == 1 && B > 8) ? 8 : 16 / rmax;       // one-row chains: 8 rows per cluster keeps the FMA work below the weight stream
+    const float* cur = in; int ld = ld_in;
+    for (size_t i = i0; i < i1; ++i) {
+        const LayerDev& l = net[i];
+        ChainLayer& c = ca.L[i - i0];
+        c.W = l.W; c.bias = l.bias; c.g1 = l.g1; c.b1 = l.b1; c.g2 = l.g2; c.b2 = l.b2;
+        c.X = cur; c.ldx = ld; c.out = outs[i].as<float>(); c.ldo = l.cout;
+        c.out2 = (i + 1 == i1) ? last_sig : nullptr; c.ldo2 = ld_sig;
+        c.ldw = l.ldw; c.kind = (l.kind == K_HC) ? 1 : 0; c.K = l.cin; c.C = l.cout; c.ntaps = l.size; c.act = l.act;
+        c.R = rows[i];
+        const int tot = (l.size - 1) * l.rate, left = l.causal ? tot : tot / 2;
+        for (int j = 0; j < l.size; ++j) c.shifts[j] = j * l.rate - left + (i == i0 ? first_extra_shift : 0);
+        cur = c.out; ld = l.cout;
+    }
+    launch_chain(ca, lc.s); lc.count();
+}
+
 // One AR step (synthesize.py:48-54 restated incrementally, exact w.r.t. the reference's
 // full recompute): AudioEnc row j, attention over the AudioDec receptive field under the
 // CURRENT window, AudioDec pyramid, Y[j] = sigmoid(logits[j]), p <- argmax of row j, j <- j+1.
@@ -611,12 +669,22 @@ void run_ar_step(Launch& lc, int B) {
     IntBufs ib = ints(h);
     // AudioEnc: one new row per utterance; first block reads Y[j-1] (train.py:51)
     const float* cur = h->ybuf.as<float>(); int ld = hp.n_mels;
-    for (size_t i = 0; i < h->audioenc.size(); ++i) {
-        const LayerDev& l = h->audioenc[i];
-        float* dst = h->ae_out[i].as<float>();
-        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, 1, ib.j}, dst, l.cout, nullptr, 0,
-                  i == 0 ? -1 : 0);
-        cur = dst; ld = l.cout;
+    // mode 2 only: measured SLOWER than the per-block kernels (one 8-CTA cluster walking 13 blocks
+    // serially cannot hide its own latencies: ncu IPC 0.25/SMSP, stalls = wait + instruction fetch)
+    const bool use_chain = h->tensor_path == 2;
+    if (use_chain && chain_ok(h->audioenc, 0, h->audioenc.size())) {
+        // all 13 blocks on the one new row per utterance: ONE cluster-persistent kernel
+        std::vector<int> ones(h->audioenc.size(), 1);
+        run_chain_kernel(lc, h->audioenc, 0, h->audioenc.size(), ones, cur, ld, -1, h->ae_out, nullptr, 0, B, T, ib.j);
+        cur = h->ae_out.back().as<float>(); ld = h->audioenc.back().cout;
+    } else {
+        for (size_t i = 0; i < h->audioenc.size(); ++i) {
+            const LayerDev& l = h->audioenc[i];
+            float* dst = h->ae_out[i].as<float>();
+            run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, 1, ib.j}, dst, l.cout, nullptr, 0,
+                      i == 0 ? -1 : 0);
+            cur = dst; ld = l.cout;
+        }
     }
     const float* Q = cur;
     std::vector<int> rows = audiodec_rows(h->audiodec, T);
@@ -625,7 +693,11 @@ void run_ar_step(Launch& lc, int B) {
     // Large batches run the wide part of the AudioDec pyramid (85..59 rows per utterance) on the
     // tensor cores, one 128-row tile per utterance ending at row j; the narrow tail and the
     // one-row AudioEnc stay on the latency-oriented fp32 kernels.
-    auto on_tc = [&](size_t i) { return h->tensor_path && B >= 8 && i < 4 && rows[i] >= 32 && h->audiodec[i].tc.ok; };
+    auto on_tc = [&](size_t i) { return h->tensor_path == 1 && B >= 8 && i < 4 && rows[i] >= 32 && h->audiodec[i].tc.ok; };
+    // first block of the narrow tail (<= 16 rows per utterance from there on)
+    size_t tail0 = h->audiodec.size();
+    for (size_t i = 0; i < h->audiodec.size(); ++i) if (rows[i] <= 5) { tail0 = i; break; }
+    const bool tail_chain = use_chain && tail0 < h->audiodec.size() && chain_ok(h->audiodec, tail0, h->audiodec.size());
     auto ar_planes = [&](int idx, int C) {
         Planes p; p.hi = h->arpl[2 * idx].as<__half>(); p.lo = h->arpl[2 * idx + 1].as<__half>(); p.ld = C; return p;
     };
@@ -638,6 +710,11 @@ void run_ar_step(Launch& lc, int B) {
         const LayerDev& l = h->audiodec[i];
         const bool last = (i + 1 == h->audiodec.size());
         float* dst = h->ad_out[i].as<float>();
+        if (tail_chain && i == tail0) {
+            run_chain_kernel(lc, h->audiodec, tail0, h->audiodec.size(), rows, cur, ld, 0, h->ad_out,
+                             h->ybuf.as<float>(), hp.n_mels, B, T, ib.j);
+            break;
+        }
         if (on_tc(i)) {
             const bool next_tc = (i + 1 < h->audiodec.size()) && on_tc(i + 1);
             Planes outp = next_tc ? ar_planes((int)i + 1, l.cout) : Planes{};
@@ -719,6 +796,19 @@ void text2mel_forward(H* h, const int* L, const float* mels, const int* pma, int
     ensure_ws(h, B);
     Launch lc{h, s};
     run_textenc(lc, L, B, h->kv.as<float>());
+    const float* K = h->kv.as<float>();
+    if (chain_tc_ok(h, h->audioenc) && chain_tc_ok(h, h->audiodec)) {
+        // tensor-core path: every block over all B*T rows as one tcgen05 kernel
+        Planes mp = ws_planes(h, 0, hp.n_mels);
+        launch_f32_to_planes(mels, hp.n_mels, mp, (long long)B * T, hp.n_mels, lc.s); lc.count();
+        float* Q = h->ae_out.back().as<float>();
+        run_chain_tc_planes(lc, h->audioenc, mp, 0, B, T, Q, nullptr, -1);          // shift: train.py:51
+        Planes Rpl; Rpl.hi = h->arpl[0].as<__half>(); Rpl.lo = h->arpl[1].as<__half>(); Rpl.ld = 2 * d;
+        run_attention(lc, Q, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, T, nullptr}, N, pma, h->rbuf.as<float>(),
+                      align, maxatt, nullptr, nullptr, Rpl);
+        run_chain_tc_planes(lc, h->audiodec, Rpl, -1, B, T, h->ad_out.back().as<float>(), Y, 0);
+        return;
+    }
     // AudioEnc over all rows, reading mels shifted by one frame (train.py:51)
     const float* cur = mels; int ld = hp.n_mels;
     for (size_t i = 0; i < h->audioenc.size(); ++i) {
@@ -728,7 +818,6 @@ void text2mel_forward(H* h, const int* L, const float* mels, const int* pma, int
                   i == 0 ? -1 : 0);
         cur = dst; ld = l.cout;
     }
-    const float* K = h->kv.as<float>();
     run_attention(lc, cur, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, T, nullptr}, N, pma, h->rbuf.as<float>(),
                   align, maxatt, nullptr, nullptr);
     cur = h->rbuf.as<float>(); ld = 2 * d;
@@ -746,7 +835,7 @@ void text2mel_forward(H* h, const int* L, const float* mels, const int* pma, int
 void run_block_op(Launch& lc, const LayerDev& l, int rate, bool causal, int act, const float* x, int B, int L, float* out) {
     H* h = lc.h;
     const int Lout = (l.kind == K_D) ? 2 * L : L;
-    if (h->tensor_path && l.tc.ok) {
+    if (h->tensor_path == 1 && l.tc.ok) {
         const size_t need = (size_t)B * L * roundup(l.cin, 8) * sizeof(__half);
         if (h->plane[0].bytes < need || h->plane[1].bytes < need) {
             CUDA_CHECK(cudaDeviceSynchronize());
@@ -823,6 +912,7 @@ int dctts_create(const dctts_hparams* hp, int device, dctts_handle* out) {
         if (prop.major != 10) throw std::runtime_error("dctts_create: this library is built for sm_100a (B200) only");
         if (hp->d > 256 || hp->d % 8 || hp->e % 4 || hp->max_N > 192 || hp->r != 4)
             throw std::runtime_error("dctts_create: unsupported hyper-parameters");
+        if (getenv("DCTTS_PDL")) pdl_enabled() = true;
         std::unique_ptr<dctts_handle_s> h(new dctts_handle_s());
         h->hp = *hp; h->device = device; h->F = 1 + hp->n_fft / 2;
         CUDA_CHECK(cudaSetDevice(device));
@@ -1062,7 +1152,14 @@ int dctts_reserve(dctts_handle h, int32_t max_batch) {
 int64_t dctts_launch_count(dctts_handle h) { return h ? h->launches : -1; }
 
 int dctts_set_tensor_path(dctts_handle h, int32_t mode) {
-    return guarded(h, [&] { REQUIRE(mode == 0 || mode == 1, "dctts_set_tensor_path: mode must be 0 or 1"); h->tensor_path = mode; });
+    return guarded(h, [&] {
+        REQUIRE(mode >= 0 && mode <= 2, "dctts_set_tensor_path: mode must be 0, 1 or 2");
+        if (mode != h->tensor_path && h->ar_exec) {      // the captured AR step depends on the mode
+            CUDA_CHECK(cudaDeviceSynchronize());
+            cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0;
+        }
+        h->tensor_path = mode;
+    });
 }
 
 int dctts_malloc(dctts_handle h, void** ptr, int64_t bytes) {

@@ -11,7 +11,31 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdexcept>
+#include <string>
+#include <utility>
+
 namespace dctts {
+
+// Programmatic dependent launch (PDL): every kernel of the decode step starts with
+// pdl_launch_dependents(); pdl_wait(); -- the next kernel's CTAs are scheduled while this one
+// runs and only its main body waits for this grid's completion and memory flush.  That hides
+// the kernel-to-kernel launch gap, which is what bounds the 50-kernel autoregressive step.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool& pdl_enabled();
+
+template <typename... Params, typename... Args>
+inline void launch_kernel(void (*kern)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
 
 struct RowWin {
     int B;            // batch
@@ -69,6 +93,25 @@ struct AttnArgs {
     int N, d, win_size;
     RowWin win;                    // rows = query rows (L = T)
 };
+
+// One block of a chain executed by the cluster-persistent chain kernel (kernels_chain.cu).
+struct ChainLayer {
+    const float* W; const float* bias;      // [ntaps][K][ldw], [ldw]
+    const float* g1; const float* b1; const float* g2; const float* b2;
+    const float* X;                         // input rows (B, T, K)
+    float* out; float* out2;                // output rows (B, T, C); optional sigmoid copy
+    int ldw, ldx, ldo, ldo2;
+    int kind;                               // 0 conv1d, 1 hc
+    int K, C, ntaps, act;
+    int R;                                  // trailing rows per utterance this block computes
+    int shifts[3];
+};
+struct ChainArgs {
+    int nlayers, B, T, G;                   // G utterances per cluster (G * max R <= 16)
+    const int* jptr;                        // device step index (window end)
+    ChainLayer L[13];
+};
+void launch_chain(const ChainArgs& a, cudaStream_t s);
 
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);

@@ -12,6 +12,8 @@
 
 namespace dctts {
 
+bool& pdl_enabled() { static bool on = false; return on; }   // opt-in (DCTTS_PDL=1): measured no gain inside CUDA graphs
+
 __device__ __forceinline__ int win_t_end(const RowWin& w) {
     return w.jptr ? __ldg(w.jptr) : (w.L - 1);
 }
@@ -23,6 +25,8 @@ __device__ __forceinline__ int win_t_end(const RowWin& w) {
 template <int BM, int BN, int BK, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_gemm_tiled(const ConvArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int NT = (BM / TM) * (BN / TN);
     constexpr int A_V = BM * BK / 4 / NT;      // float4 loads of A per thread per stage
     constexpr int B_V = BK * BN / 4 / NT;
@@ -178,6 +182,8 @@ conv_gemm_tiled(const ConvArgs a) {
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a, const int chunks_per_cta,
                                                         const size_t part_stride) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int BM = 16, BN = 64, BKS = 64, KG = 4, KPG = BKS / KG;
     __shared__ __align__(16) float As[BKS][BM];
     __shared__ float red[KG - 1][BM][BN];
@@ -282,14 +288,14 @@ GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes
         const int cpc = (nchunks + max_parts - 1) / max_parts;
         const int nparts = (nchunks + cpc - 1) / cpc;
         dim3 grid((a.ldw + 63) / 64, nparts, (M + 15) / 16);
-        conv_gemm_skinny<<<grid, 256, 0, s>>>(a, cpc, part);
+        launch_kernel(conv_gemm_skinny, grid, dim3(256), 0, s, a, cpc, part);
         out.nparts = nparts; out.compact = 1; out.part_stride = part;
     } else if (tiles128 >= 120) {
         dim3 grid((a.ldw + 127) / 128, (M + 127) / 128);
-        conv_gemm_tiled<128, 128, 16, 8, 8><<<grid, 256, 0, s>>>(a);
+        launch_kernel(conv_gemm_tiled<128, 128, 16, 8, 8>, grid, dim3(256), 0, s, a);
     } else {
         dim3 grid((a.ldw + 63) / 64, (M + 63) / 64);
-        conv_gemm_tiled<64, 64, 16, 4, 4><<<grid, 256, 0, s>>>(a);
+        launch_kernel(conv_gemm_tiled<64, 64, 16, 4, 4>, grid, dim3(256), 0, s, a);
     }
     return out;
 }
@@ -346,6 +352,8 @@ __device__ __forceinline__ void ln_load_partials(const float* __restrict__ y, in
 
 template <int MAXV>
 __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     const int R = a.win.R, L = a.win.L;
@@ -402,10 +410,10 @@ void launch_ln_rows(const LnArgs& a, cudaStream_t s) {
     const int warps_per_cta = rows >= 2048 ? 8 : 2;     // small launches: spread over SMs
     const int threads = warps_per_cta * 32;
     const int grid = (rows + warps_per_cta - 1) / warps_per_cta;
-    if (a.C <= 256)       ln_rows_kernel<8><<<grid, threads, 0, s>>>(a);
-    else if (a.C <= 512)  ln_rows_kernel<16><<<grid, threads, 0, s>>>(a);
-    else if (a.C <= 1024) ln_rows_kernel<32><<<grid, threads, 0, s>>>(a);
-    else                  ln_rows_kernel<33><<<grid, threads, 0, s>>>(a);   // F = 1025
+    if (a.C <= 256)       launch_kernel(ln_rows_kernel<8>, dim3(grid), dim3(threads), 0, s, a);
+    else if (a.C <= 512)  launch_kernel(ln_rows_kernel<16>, dim3(grid), dim3(threads), 0, s, a);
+    else if (a.C <= 1024) launch_kernel(ln_rows_kernel<32>, dim3(grid), dim3(threads), 0, s, a);
+    else                  launch_kernel(ln_rows_kernel<33>, dim3(grid), dim3(threads), 0, s, a);   // F = 1025
 }
 
 // ------------------------------------------------------------------------------------
@@ -417,6 +425,8 @@ constexpr int ATT_MAXN = 192;
 constexpr int ATT_WARPS = 4;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float probs[ATT_WARPS][ATT_MAXN];
     const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warp = blockIdx.x * ATT_WARPS + wib;
@@ -516,7 +526,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const AttnArg
 void launch_attention(const AttnArgs& a, cudaStream_t s) {
     const int rows = a.win.B * a.win.R;
     if (rows <= 0) return;
-    attention_kernel<<<(rows + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, s>>>(a);
+    launch_kernel(attention_kernel, dim3((rows + ATT_WARPS - 1) / ATT_WARPS), dim3(ATT_WARPS * 32), 0, s, a);
 }
 
 // ------------------------------------------------------------------------------------
@@ -540,12 +550,14 @@ void launch_embed(const int* ids, const float* table, float* out, int rows, int 
 }
 
 __global__ void ar_advance_kernel(int* p_cur, const int* p_next, int* j, int B) {
+    pdl_launch_dependents();
+    pdl_wait();
     int i = threadIdx.x + blockIdx.x * blockDim.x;
     if (i < B) p_cur[i] = p_next[i];
     if (i == 0) *j = *j + 1;
 }
 void launch_ar_advance(int* p_cur, const int* p_next, int* j, int B, cudaStream_t s) {
-    ar_advance_kernel<<<(B + 127) / 128, 128, 0, s>>>(p_cur, p_next, j, B);
+    launch_kernel(ar_advance_kernel, dim3((B + 127) / 128), dim3(128), 0, s, p_cur, p_next, j, B);
 }
 
 __global__ void fill_i32_kernel(int* p, int v, int n) {

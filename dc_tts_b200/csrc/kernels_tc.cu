@@ -20,6 +20,7 @@
 #include "kernels_tc.cuh"
 #include "tc_ptx.cuh"
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -28,12 +29,10 @@ namespace dctts {
 using namespace ptx;
 
 constexpr int TC_BM = 128;
-constexpr int TC_BK = 64;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;                 // 16384 B
-constexpr int TC_AUX_BYTES = 128 /*barriers*/ + 3 * 256 * 4 /*bias,gamma,beta*/ + 8 * 128 * 16 /*stats*/;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_AUX_BYTES = 256 /*barriers*/ + 3 * 256 * 4 /*bias,gamma,beta*/ + 8 * 128 * 16 /*stats*/;
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -75,18 +74,22 @@ __device__ __forceinline__ void store_planes(const Planes& p, size_t row, int co
     }
 }
 
+template <int TC_BK>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                   const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
                   const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    pdl_launch_dependents();          // PDL: let the next kernel's CTAs be scheduled behind this one
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int rank = (int)cluster_ctarank();
     const int ncta = (int)cluster_nctarank();
     const int bn = a.bn, half = a.half;
-    const int b_plane = bn * 128;                                    // bytes of one weight plane tile
+    constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;                    // bytes of one activation plane tile
+    constexpr int SW = TC_BK * 2;                                    // swizzle span = row bytes (128 or 64)
+    const int b_plane = bn * SW;                                     // bytes of one weight plane tile
     const int stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
     const int stages = a.stages;
     const int nkb = a.ntaps * a.kb_per_tap;
@@ -96,11 +99,12 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;                      // [stages]
     uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    float* s_bias = reinterpret_cast<float*>(aux + 128);
+    float* s_bias = reinterpret_cast<float*>(aux + 256);
     float* s_gam = s_bias + 256;
     float* s_bet = s_gam + 256;
     float4* s_part = reinterpret_cast<float4*>(s_bet + 256);            // [8 ranks][128 rows]
 
+    pdl_wait();                       // upstream grid complete, its writes visible
     // ---- tile coordinates ----
     const int tile = blockIdx.y;
     const int bg = tile / a.tiles_t, tt = tile - bg * a.tiles_t;
@@ -118,7 +122,9 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     // ---- one-time setup ----
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&mapA_hi); prefetch_tmap(&mapA_lo); prefetch_tmap(&mapW_hi); prefetch_tmap(&mapW_lo);
-        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        // with the multicast A tile a stage may only be refilled once EVERY CTA of the cluster has
+        // drained it: each MMA warp commits to all CTAs' empty barriers
+        for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], a.mcast ? (uint32_t)ncta : 1u); }
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
     }
@@ -145,7 +151,10 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     if (threadIdx.x == 0) { dbg_mark(a.dbg, 0, 1); dbg_mark(a.dbg, 1, (int)tmem_base); dbg_mark(a.dbg, 2, nkb); }
-    if (ncta > 1) cluster_arrive();          // phase 1: every CTA of the cluster is running
+    if (ncta > 1) { cluster_arrive(); cluster_wait(); }   // phase 1: every CTA is running, its barriers initialised
+    const bool mcast = a.mcast != 0 && ncta > 1;
+    const uint16_t cta_mask = (uint16_t)((1u << ncta) - 1u);
+    const int slice_rows = TC_BM / ncta;
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
@@ -158,8 +167,15 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 const int tap = kb / a.kb_per_tap, kc = kb - tap * a.kb_per_tap;
                 const int tcoord = t0 + a.shifts[tap];
-                tma_load_3d(&mapA_hi, &full_bar[s], st, kc * TC_BK, tcoord, b0);
-                tma_load_3d(&mapA_lo, &full_bar[s], st + TC_A_PLANE, kc * TC_BK, tcoord, b0);
+                if (mcast) {
+                    // this CTA fetches rows [rank*slice, +slice) of the tile for the whole cluster
+                    const int off = rank * slice_rows * SW;
+                    tma_load_3d_mc(&mapA_hi, &full_bar[s], st + off, kc * TC_BK, tcoord + rank * slice_rows, b0, cta_mask);
+                    tma_load_3d_mc(&mapA_lo, &full_bar[s], st + TC_A_PLANE + off, kc * TC_BK, tcoord + rank * slice_rows, b0, cta_mask);
+                } else {
+                    tma_load_3d(&mapA_hi, &full_bar[s], st, kc * TC_BK, tcoord, b0);
+                    tma_load_3d(&mapA_lo, &full_bar[s], st + TC_A_PLANE, kc * TC_BK, tcoord, b0);
+                }
                 tma_load_2d(&mapW_hi, &full_bar[s], st + 2 * TC_A_PLANE, kb * TC_BK, rank * bn);
                 tma_load_2d(&mapW_lo, &full_bar[s], st + 2 * TC_A_PLANE + b_plane, kb * TC_BK, rank * bn);
                 dbg_mark(a.dbg, 3, kb + 1);
@@ -176,18 +192,19 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t dA_hi = umma_desc_sw128(st);
-                const uint64_t dA_lo = umma_desc_sw128(st + TC_A_PLANE);
-                const uint64_t dB_hi = umma_desc_sw128(st + 2 * TC_A_PLANE);
-                const uint64_t dB_lo = umma_desc_sw128(st + 2 * TC_A_PLANE + b_plane);
+                const uint64_t dA_hi = umma_desc_kmajor<SW>(st);
+                const uint64_t dA_lo = umma_desc_kmajor<SW>(st + TC_A_PLANE);
+                const uint64_t dB_hi = umma_desc_kmajor<SW>(st + 2 * TC_A_PLANE);
+                const uint64_t dB_lo = umma_desc_kmajor<SW>(st + 2 * TC_A_PLANE + b_plane);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 16 fp16 = 32 B inside the 128 B atom
+                    const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 16 fp16 = 32 B inside the swizzle atom
                     tc_mma_f16(tmem_base, dA_hi + adv, dB_hi + adv, idesc, (kb | k) != 0);
                     tc_mma_f16(tmem_base, dA_hi + adv, dB_lo + adv, idesc, 1u);
                     tc_mma_f16(tmem_base, dA_lo + adv, dB_hi + adv, idesc, 1u);
                 }
-                tc_commit(&empty_bar[s]);                                  // frees the smem stage
+                if (mcast) tc_commit_mc(&empty_bar[s], cta_mask);          // frees the stage in every CTA's view
+                else tc_commit(&empty_bar[s]);                             // frees the smem stage
                 if (kb == nkb - 1) tc_commit(tmem_full_bar);               // accumulator complete
                 dbg_mark(a.dbg, 4, kb + 1);
             }
@@ -245,7 +262,6 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         // combine over the cluster
         float mean1, rstd1, mean2 = 0.f, rstd2 = 0.f;
         if (ncta > 1) {
-            cluster_wait();                                                // phase 1 done: peers are alive
             const uint32_t my_slot = smem_u32(&s_part[rank * 128 + r]);
             for (int p = 0; p < ncta; ++p) st_cluster_f4(mapa(my_slot, (uint32_t)p), s1, q1, s2, q2);
             if (r == 0) dbg_mark(a.dbg, 6, 1);
@@ -361,7 +377,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
 
     // ---- teardown: match the cluster barrier phases of the epilogue warps ----
     if (ncta > 1) {
-        if (warp < 2) { cluster_wait(); cluster_arrive(); cluster_wait(); }
+        if (warp < 2) { cluster_arrive(); cluster_wait(); }      // phase 2 (the epilogue warps did theirs)
         cluster_arrive();                     // phase 3: nobody reads my shared memory any more
         cluster_wait();
     }
@@ -421,55 +437,66 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, int B, int TT, int TB) {
+void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, int B, int TT, int TB, int bk) {
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)L, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)L * ld * 2};
-    cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TT, (cuuint32_t)TB};
+    cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)TT, (cuuint32_t)TB};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
 }
 
-void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn) {
+void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn, int bk) {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Nrows};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights) failed: " + std::to_string((int)r));
 }
 
-int tc_stages_for(int bn) {
-    const int stage = 2 * TC_A_PLANE + 2 * bn * 128;
+int tc_bk() {
+    // measured (SSRN/HC_11, B=32): BK=64 / 2 stages 1.24 ms, BK=32 / 4 stages 1.32 ms -- the kernel is bound by
+    // bytes delivered per SM, not by pipeline depth, so the wider slab (half as many TMA rows) wins
+    static const int bk = (getenv("DCTTS_TC_BK") && atoi(getenv("DCTTS_TC_BK")) == 32) ? 32 : 64;
+    return bk;
+}
+
+int tc_stages_for(int bn, int bk) {
+    const int stage = 2 * TC_BM * bk * 2 + 2 * bn * bk * 2;
     int s = (200 * 1024) / stage;
     return s < 2 ? 2 : (s > TC_MAX_STAGES ? TC_MAX_STAGES : s);
 }
 
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, cudaStream_t s) {
+                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, int bk, cudaStream_t s) {
     static bool attr_set = false;
     const int max_smem = 227 * 1024;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         attr_set = true;
     }
-    const size_t smem = (size_t)a.stages * (2 * TC_A_PLANE + 2 * a.bn * 128) + TC_AUX_BYTES + 1024;
+    const size_t smem = (size_t)a.stages * (2 * TC_BM * bk * 2 + 2 * a.bn * bk * 2) + TC_AUX_BYTES + 1024;
     if (smem > (size_t)max_smem) throw std::runtime_error("conv_ln_tc: shared memory budget exceeded");
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)ncta, (unsigned)tiles, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)ncta; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel, a_hi, a_lo, w_hi, w_lo, a);
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = (bk == 64) ? cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64>, a_hi, a_lo, w_hi, w_lo, a)
+                               : cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32>, a_hi, a_lo, w_hi, w_lo, a);
     if (e != cudaSuccess) throw std::runtime_error(std::string("conv_ln_tc launch: ") + cudaGetErrorString(e));
 }
 

@@ -32,7 +32,8 @@ struct TcArgs {
     int half;                      // columns per LN half per CTA (mode 0: == bn)
     float inv_scale;               // 1 / (power-of-two weight scale)
     // reduction schedule
-    int ntaps; int shifts[3]; int kb_per_tap; int stages;
+    int ntaps; int shifts[3]; int kb_per_tap; int stages;   // kb_per_tap in units of the kernel's BK (64 or 32)
+    int mcast;                     // 1: the A tile is fetched once per cluster (each CTA loads 128/ncta rows, TMA multicast)
     // tiling: 128 rows = TT time rows x TB batch rows
     int TT, TB, tiles_t;
     RowWin win;
@@ -45,16 +46,18 @@ struct TcArgs {
     int* dbg;                      // optional host-mapped progress markers (debugging), else null
 };
 
-// Encodes the rank-3 (C, L, B) activation map with a {64, TT, TB} box, 128-byte swizzle.
-void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, int B, int TT, int TB);
-// Encodes the rank-2 (Ktot, Nrows) K-major weight map with a {64, bn} box, 128-byte swizzle.
-void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn);
+// Encodes the rank-3 (C, L, B) activation map with a {bk, TT, TB} box; bk = 64 -> 128-byte swizzle, 32 -> 64-byte.
+void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, int B, int TT, int TB, int bk);
+// Encodes the rank-2 (Ktot, Nrows) K-major weight map with a {bk, bn} box, same swizzle rule.
+void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn, int bk);
 
 // pipeline depth that fits the shared-memory budget for `bn` accumulator columns per CTA
-int tc_stages_for(int bn);
+int tc_stages_for(int bn, int bk);
+// reduction slab per pipeline stage (fp16 elements): 64 (128B swizzle); DCTTS_TC_BK=32 selects 32 (64B swizzle, deeper pipeline)
+int tc_bk();
 // grid = (ncta, tiles); cluster (ncta,1,1)
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, cudaStream_t s);
+                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, int bk, cudaStream_t s);
 
 void launch_f32_to_planes(const float* x, int ldx, Planes p, long long rows, int C, cudaStream_t s);
 void launch_planes_to_f32(Planes p, float* y, int ldy, long long rows, int C, cudaStream_t s);

@@ -57,6 +57,14 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
                  : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask`, and
+// each destination CTA's barrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_3d_mc(const void* tmap, uint64_t* bar, void* dst, int c0, int c1, int c2, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+                 : "memory");
+}
+
 // ---- tcgen05 / TMEM -----------------------------------------------------------------------
 template <uint32_t COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_in_smem) {      // whole warp
@@ -72,6 +80,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // one thread: all previously issued tcgen05.mma of this thread arrive on `bar` when complete
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// multicast variant: arrives on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem desc] * B[smem desc]^T, fp16 inputs, fp32 accumulate
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -93,15 +106,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row atoms of 1024 B): the layout
-// TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.  sm_100 descriptor: start>>4 [0,14), LBO>>4 [16,30)
-// (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B, version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+// K-major swizzled operand tile, rows of SW bytes (SW = 128 or 64), 8-row atoms of 8*SW bytes: the
+// layout TMA writes with CU_TENSOR_MAP_SWIZZLE_{128B,64B}.  sm_100 descriptor: start>>4 [0,14),
+// LBO>>4 [16,30) (unused for swizzled K-major), SBO>>4 [32,46) = 8*SW, version=1 [46,48),
+// layout [61,64): SWIZZLE_128B = 2, SWIZZLE_64B = 4.
+template <int SW>
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) {
+    static_assert(SW == 128 || SW == 64, "swizzle span");
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>((8 * SW) >> 4) << 32;
     d |= 1ull << 46;
-    d |= 2ull << 61;
+    d |= static_cast<uint64_t>(SW == 128 ? 2 : 4) << 61;
     return d;
 }
 // kind::f16 instruction descriptor: D=f32 [4,6)=1, A/B=f16 [7,10)/[10,13)=0, both K-major, N>>3 [17,23), M>>4 [24,29)

@@ -37,9 +37,9 @@ def golden(name):
     return np.load(os.path.join(GOLDEN, name))
 
 
-@pytest.fixture(params=[0, 1], ids=["fp32path", "tensorpath"])
+@pytest.fixture(params=[0, 1, 2], ids=["fp32path", "tensorpath", "fp32chain"])
 def path(engine, request):
-    """Runs a GPU test once per arithmetic path: 0 = fp32 CUDA-core kernels, 1 = tcgen05."""
+    """Runs a GPU test once per kernel set (include/dctts.h: dctts_set_tensor_path)."""
     engine.set_tensor_path(request.param)
     yield request.param
     engine.set_tensor_path(1)
