@@ -119,6 +119,7 @@ struct dctts_handle_s {
     DevBuf lbuf;                  // (B, N) ids staging for the host entry point
     DevBuf zbuf;                  // (B, 4T, F) staging for the host entry point
     DevBuf plane[4];              // tensor-core path activations: {hi,lo} x ping-pong, rows x 1032 fp16
+    DevBuf attpl[6];              // tcgen05 attention operands: Q, K planes and transposed V planes ({hi,lo} each)
     DevBuf arpl[10];              // AR decode planes: R (B,T,2d) and four AudioDec outputs (B,T,d), {hi,lo} each
 
     // AR decode graph
@@ -136,6 +137,7 @@ struct dctts_handle_s {
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
         for (auto& b : plane) b.release();
         for (auto& b : arpl) b.release();
+        for (auto& b : attpl) b.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
         if (stream) cudaStreamDestroy(stream);
@@ -423,6 +425,22 @@ void run_block(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
                int extra_shift = 0) {
     H* h = lc.h;
     REQUIRE(l.kind != K_D, "run_block: transposed conv must use run_deconv");
+    const int Mrows = win.B * win.R;
+    if (h->tensor_path == 2 && Mrows <= 256 && rows_block_supported(l.kind == K_HC ? 1 : 0, l.cin, l.cout, l.size)) {
+        // mode 2 (experiment): the whole block in ONE 8-CTA cluster launch, no pre-LN round trip.  Measured
+        // slower than split-K GEMM + LN kernel (B=1: 336 vs 243 us per decode step): an SM pulls only
+        // ~50 GB/s from L2, so concentrating a block's 1.5 MB of weights on 8 SMs costs more than the
+        // second kernel boundary saves; the split-K form spreads them over ~100 SMs.
+        RowsBlockArgs r{};
+        r.W = l.W; r.bias = l.bias; r.g1 = l.g1; r.b1 = l.b1; r.g2 = l.g2; r.b2 = l.b2;
+        r.X = X; r.ldx = ldx; r.out = out; r.ldo = ldo; r.out2 = out2; r.ldo2 = ldo2; r.ldw = l.ldw;
+        r.kind = l.kind == K_HC ? 1 : 0; r.K = l.cin; r.C = l.cout; r.ntaps = l.size; r.act = act;
+        const int tot_ = (l.size - 1) * rate, left_ = causal ? tot_ : tot_ / 2;
+        for (int j = 0; j < l.size; ++j) r.shifts[j] = j * rate - left_ + extra_shift;
+        r.win = win;
+        launch_rows_block(r, lc.s); lc.count();
+        return;
+    }
     ConvArgs c{};
     c.X = X; c.ldx = ldx; c.Y = h->scratch.as<float>(); c.ldy = l.ldw; c.bias = l.bias;
     c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
@@ -509,15 +527,20 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     TcArgs a{};
     a.bias = l.bias; a.g1 = l.g1; a.b1 = l.b1; a.g2 = (p.mode == 1) ? l.g2 : l.g1; a.b2 = (p.mode == 1) ? l.b2 : l.b1;
     a.mode = p.mode; a.act = act; a.C = l.cout; a.bn = p.bn; a.half = p.half; a.inv_scale = p.inv_scale;
-    const int bk = tc_bk();
+    const int tiles = ((win.B + TB - 1) / TB) * tiles_t;
+    // big launches pair two 128-row tiles per CTA (one weight slab feeds both accumulators): the kernel is
+    // bound by the bytes an SM can pull from L2, and pairing cuts them by a third per MMA
+    static const bool no_pair = getenv("DCTTS_TC_NO_PAIR") != nullptr;
+    const int mt = (!no_pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
+    const int bk = (mt == 2) ? 32 : tc_bk();
     a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap * (64 / bk);
     if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
     else {
         const int tot = (l.size - 1) * rate, left = causal ? tot : tot / 2;
         for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
     }
-    a.stages = std::min(tc_stages_for(p.bn, bk), std::max(1, a.ntaps * a.kb_per_tap));
-    a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.win = win;
+    a.stages = std::min(tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));
+    a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.ntiles = tiles; a.win = win;
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
     // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the
     // tile is 128 consecutive time rows, each CTA contributing 128/ncta of them
@@ -527,7 +550,6 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     CUtensorMap mAh, mAl;
     tc_make_act_map(&mAh, X.hi, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
     tc_make_act_map(&mAl, X.lo, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
-    const int tiles = ((win.B + TB - 1) / TB) * tiles_t;
     // DCTTS_TC_DEBUG=1: progress markers in host-mapped memory, dumped after a synchronising launch
     static const bool debug = getenv("DCTTS_TC_DEBUG") != nullptr;
     static int* dbg_host = nullptr;
@@ -538,7 +560,9 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
         fprintf(stderr, "[tc] %s mode=%d ncta=%d bn=%d half=%d stages=%d nkb=%d tiles=%d TT=%d TB=%d L=%d B=%d\n", l.scope.c_str(),
                 a.mode, p.ncta, a.bn, a.half, a.stages, a.ntaps * a.kb_per_tap, tiles, TT, TB, win.L, win.B);
     }
-    launch_conv_ln_tc(mAh, mAl, p.mWhi, p.mWlo, a, p.ncta, tiles, bk, lc.s); lc.count();
+    CUtensorMap mWh = p.mWhi, mWl = p.mWlo;
+    if (bk != tc_bk()) { tc_make_w_map(&mWh, p.Whi, p.Ktot, p.nrows, p.bn, bk); tc_make_w_map(&mWl, p.Wlo, p.Ktot, p.nrows, p.bn, bk); }
+    launch_conv_ln_tc(mAh, mAl, mWh, mWl, a, p.ncta, (tiles + mt - 1) / mt, bk, mt, lc.s); lc.count();
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(lc.s);
         for (int c = 0; c < std::min(16, p.ncta * tiles); ++c)
@@ -598,6 +622,29 @@ void run_attention(Launch& lc, const float* Q, int ldq, const float* K, int ldk,
     launch_attention(a, lc.s); lc.count();
 }
 
+// Full-sequence attention on the tensor cores (kernels_attn_tc.cu): dense or with the monotonic
+// window.  Q, K, V are fp32 device tensors; their split planes are built here.
+bool attention_tc_ok(H* h, int N) { return h->tensor_path == 1 && h->hp.d == 256 && N <= attn_tc_padded_keys(); }
+
+void run_attention_tc(Launch& lc, const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, int B, int T,
+                      int N, const int* pma, float* R, float* align, long long* maxatt, Planes Rpl) {
+    H* h = lc.h;
+    const int d = h->hp.d, NP = attn_tc_padded_keys();
+    const size_t need[3] = {(size_t)B * T * d * sizeof(__half), (size_t)B * N * d * sizeof(__half), (size_t)B * d * NP * sizeof(__half)};
+    for (int i = 0; i < 6; ++i)
+        if (h->attpl[i].bytes < need[i / 2]) { CUDA_CHECK(cudaDeviceSynchronize()); h->attpl[i].ensure(need[i / 2]); }
+    Planes qp, kp, vp;
+    qp.hi = h->attpl[0].as<__half>(); qp.lo = h->attpl[1].as<__half>(); qp.ld = d;
+    kp.hi = h->attpl[2].as<__half>(); kp.lo = h->attpl[3].as<__half>(); kp.ld = d;
+    vp.hi = h->attpl[4].as<__half>(); vp.lo = h->attpl[5].as<__half>(); vp.ld = NP;
+    launch_f32_to_planes(Q, ldq, qp, (long long)B * T, d, lc.s); lc.count();
+    launch_attn_kv_planes(K, ldk, V, ldv, kp, vp, B, N, d, lc.s); lc.count();
+    AttnTcArgs a{};
+    a.Q = Q; a.ldq = ldq; a.R = R; a.ldr = 2 * d; a.Rpl = Rpl; a.align = align; a.maxatt = maxatt; a.pma = pma;
+    a.T = T; a.N = N; a.d = d; a.win_size = h->hp.attention_win_size; a.scale = 1.0f / std::sqrt((float)d);
+    launch_attention_tc(qp, kp, vp, a, B, lc.s); lc.count();
+}
+
 void run_textenc(Launch& lc, const int* L, int B, float* kv_out /* (B,N,2d) */) {
     H* h = lc.h;
     const int N = h->hp.max_N;
@@ -621,44 +668,6 @@ std::vector<int> audiodec_rows(const std::vector<LayerDev>& net, int T) {
     return rows;
 }
 
-// Builds the argument block of the cluster-persistent chain kernel for layers [i0, i1) of `net`.
-// `in` is the input of layer i0, outs[i] the per-layer output buffers (ld = cout).
-bool chain_ok(const std::vector<LayerDev>& net, size_t i0, size_t i1) {
-    if (i1 - i0 > 13) return false;
-    for (size_t i = i0; i < i1; ++i) {
-        const LayerDev& l = net[i];
-        if (l.kind == K_D || (l.cin % 4)) return false;
-        if (l.kind == K_HC && (l.cout % 8 || l.cout / 8 > 32)) return false;
-        if (l.kind == K_C && (l.cout + 7) / 8 > 64) return false;
-    }
-    return true;
-}
-
-void run_chain_kernel(Launch& lc, const std::vector<LayerDev>& net, size_t i0, size_t i1, const std::vector<int>& rows,
-                      const float* in, int ld_in, int first_extra_shift, std::vector<DevBuf>& outs, float* last_sig,
-                      int ld_sig, int B, int T, const int* jptr) {
-    ChainArgs ca{};
-    ca.nlayers = (int)(i1 - i0); ca.B = B; ca.T = T; ca.jptr = jptr;
-    int rmax = 1;
-    for (size_t i = i0; i < i1; ++i) rmax = std::max(rmax, rows[i]);
-    REQUIRE(rmax <= 16, "chain kernel: more than 16 rows per utterance");
-    ca.G = (rmax == 1 && B > 8) ? 8 : 16 / rmax;       // one-row chains: 8 rows per cluster keeps the FMA work below the weight stream
-    const float* cur = in; int ld = ld_in;
-    for (size_t i = i0; i < i1; ++i) {
-        const LayerDev& l = net[i];
-        ChainLayer& c = ca.L[i - i0];
-        c.W = l.W; c.bias = l.bias; c.g1 = l.g1; c.b1 = l.b1; c.g2 = l.g2; c.b2 = l.b2;
-        c.X = cur; c.ldx = ld; c.out = outs[i].as<float>(); c.ldo = l.cout;
-        c.out2 = (i + 1 == i1) ? last_sig : nullptr; c.ldo2 = ld_sig;
-        c.ldw = l.ldw; c.kind = (l.kind == K_HC) ? 1 : 0; c.K = l.cin; c.C = l.cout; c.ntaps = l.size; c.act = l.act;
-        c.R = rows[i];
-        const int tot = (l.size - 1) * l.rate, left = l.causal ? tot : tot / 2;
-        for (int j = 0; j < l.size; ++j) c.shifts[j] = j * l.rate - left + (i == i0 ? first_extra_shift : 0);
-        cur = c.out; ld = l.cout;
-    }
-    launch_chain(ca, lc.s); lc.count();
-}
-
 // One AR step (synthesize.py:48-54 restated incrementally, exact w.r.t. the reference's
 // full recompute): AudioEnc row j, attention over the AudioDec receptive field under the
 // CURRENT window, AudioDec pyramid, Y[j] = sigmoid(logits[j]), p <- argmax of row j, j <- j+1.
@@ -669,22 +678,12 @@ void run_ar_step(Launch& lc, int B) {
     IntBufs ib = ints(h);
     // AudioEnc: one new row per utterance; first block reads Y[j-1] (train.py:51)
     const float* cur = h->ybuf.as<float>(); int ld = hp.n_mels;
-    // mode 2 only: measured SLOWER than the per-block kernels (one 8-CTA cluster walking 13 blocks
-    // serially cannot hide its own latencies: ncu IPC 0.25/SMSP, stalls = wait + instruction fetch)
-    const bool use_chain = h->tensor_path == 2;
-    if (use_chain && chain_ok(h->audioenc, 0, h->audioenc.size())) {
-        // all 13 blocks on the one new row per utterance: ONE cluster-persistent kernel
-        std::vector<int> ones(h->audioenc.size(), 1);
-        run_chain_kernel(lc, h->audioenc, 0, h->audioenc.size(), ones, cur, ld, -1, h->ae_out, nullptr, 0, B, T, ib.j);
-        cur = h->ae_out.back().as<float>(); ld = h->audioenc.back().cout;
-    } else {
-        for (size_t i = 0; i < h->audioenc.size(); ++i) {
-            const LayerDev& l = h->audioenc[i];
-            float* dst = h->ae_out[i].as<float>();
-            run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, 1, ib.j}, dst, l.cout, nullptr, 0,
-                      i == 0 ? -1 : 0);
-            cur = dst; ld = l.cout;
-        }
+    for (size_t i = 0; i < h->audioenc.size(); ++i) {
+        const LayerDev& l = h->audioenc[i];
+        float* dst = h->ae_out[i].as<float>();
+        run_block(lc, l, l.rate, l.causal, l.act, cur, ld, RowWin{B, T, 1, ib.j}, dst, l.cout, nullptr, 0,
+                  i == 0 ? -1 : 0);
+        cur = dst; ld = l.cout;
     }
     const float* Q = cur;
     std::vector<int> rows = audiodec_rows(h->audiodec, T);
@@ -694,10 +693,6 @@ void run_ar_step(Launch& lc, int B) {
     // tensor cores, one 128-row tile per utterance ending at row j; the narrow tail and the
     // one-row AudioEnc stay on the latency-oriented fp32 kernels.
     auto on_tc = [&](size_t i) { return h->tensor_path == 1 && B >= 8 && i < 4 && rows[i] >= 32 && h->audiodec[i].tc.ok; };
-    // first block of the narrow tail (<= 16 rows per utterance from there on)
-    size_t tail0 = h->audiodec.size();
-    for (size_t i = 0; i < h->audiodec.size(); ++i) if (rows[i] <= 5) { tail0 = i; break; }
-    const bool tail_chain = use_chain && tail0 < h->audiodec.size() && chain_ok(h->audiodec, tail0, h->audiodec.size());
     auto ar_planes = [&](int idx, int C) {
         Planes p; p.hi = h->arpl[2 * idx].as<__half>(); p.lo = h->arpl[2 * idx + 1].as<__half>(); p.ld = C; return p;
     };
@@ -710,11 +705,6 @@ void run_ar_step(Launch& lc, int B) {
         const LayerDev& l = h->audiodec[i];
         const bool last = (i + 1 == h->audiodec.size());
         float* dst = h->ad_out[i].as<float>();
-        if (tail_chain && i == tail0) {
-            run_chain_kernel(lc, h->audiodec, tail0, h->audiodec.size(), rows, cur, ld, 0, h->ad_out,
-                             h->ybuf.as<float>(), hp.n_mels, B, T, ib.j);
-            break;
-        }
         if (on_tc(i)) {
             const bool next_tc = (i + 1 < h->audiodec.size()) && on_tc(i + 1);
             Planes outp = next_tc ? ar_planes((int)i + 1, l.cout) : Planes{};
@@ -804,8 +794,11 @@ void text2mel_forward(H* h, const int* L, const float* mels, const int* pma, int
         float* Q = h->ae_out.back().as<float>();
         run_chain_tc_planes(lc, h->audioenc, mp, 0, B, T, Q, nullptr, -1);          // shift: train.py:51
         Planes Rpl; Rpl.hi = h->arpl[0].as<__half>(); Rpl.lo = h->arpl[1].as<__half>(); Rpl.ld = 2 * d;
-        run_attention(lc, Q, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, T, nullptr}, N, pma, h->rbuf.as<float>(),
-                      align, maxatt, nullptr, nullptr, Rpl);
+        if (attention_tc_ok(h, N))
+            run_attention_tc(lc, Q, d, K, 2 * d, K + d, 2 * d, B, T, N, pma, h->rbuf.as<float>(), align, maxatt, Rpl);
+        else
+            run_attention(lc, Q, d, K, 2 * d, K + d, 2 * d, RowWin{B, T, T, nullptr}, N, pma, h->rbuf.as<float>(),
+                          align, maxatt, nullptr, nullptr, Rpl);
         run_chain_tc_planes(lc, h->audiodec, Rpl, -1, B, T, h->ad_out.back().as<float>(), Y, 0);
         return;
     }
@@ -1036,8 +1029,12 @@ int dctts_attention(dctts_handle h, const float* Q, const float* K, const float*
         REQUIRE(!monotonic || pma, "dctts_attention: monotonic attention needs prev_max_attentions");
         Launch lc{h, S(h, stream)};
         const int d = h->hp.d;
-        run_attention(lc, Q, d, K, d, V, d, RowWin{B, T, T, nullptr}, N, monotonic ? pma : nullptr, R, alignments,
-                      reinterpret_cast<long long*>(max_attentions), nullptr, nullptr);
+        if (attention_tc_ok(h, N))
+            run_attention_tc(lc, Q, d, K, d, V, d, B, T, N, monotonic ? pma : nullptr, R, alignments,
+                             reinterpret_cast<long long*>(max_attentions), Planes{});
+        else
+            run_attention(lc, Q, d, K, d, V, d, RowWin{B, T, T, nullptr}, N, monotonic ? pma : nullptr, R, alignments,
+                          reinterpret_cast<long long*>(max_attentions), nullptr, nullptr);
     });
 }
 

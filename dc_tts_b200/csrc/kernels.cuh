@@ -94,24 +94,20 @@ struct AttnArgs {
     RowWin win;                    // rows = query rows (L = T)
 };
 
-// One block of a chain executed by the cluster-persistent chain kernel (kernels_chain.cu).
-struct ChainLayer {
+// One block on a few rows in one launch (kernels_rows.cu): 8-CTA cluster, GEMM + LN fused.
+struct RowsBlockArgs {
     const float* W; const float* bias;      // [ntaps][K][ldw], [ldw]
     const float* g1; const float* b1; const float* g2; const float* b2;
-    const float* X;                         // input rows (B, T, K)
-    float* out; float* out2;                // output rows (B, T, C); optional sigmoid copy
+    const float* X;                         // input rows (B, L, K); also the highway residual
+    float* out; float* out2;                // output rows (B, L, C); optional sigmoid copy
     int ldw, ldx, ldo, ldo2;
     int kind;                               // 0 conv1d, 1 hc
     int K, C, ntaps, act;
-    int R;                                  // trailing rows per utterance this block computes
     int shifts[3];
+    RowWin win;
 };
-struct ChainArgs {
-    int nlayers, B, T, G;                   // G utterances per cluster (G * max R <= 16)
-    const int* jptr;                        // device step index (window end)
-    ChainLayer L[13];
-};
-void launch_chain(const ChainArgs& a, cudaStream_t s);
+bool rows_block_supported(int kind, int K, int C, int ntaps);
+void launch_rows_block(const RowsBlockArgs& a, cudaStream_t s);
 
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);

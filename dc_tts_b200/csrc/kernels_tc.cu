@@ -74,7 +74,9 @@ __device__ __forceinline__ void store_planes(const Planes& p, size_t row, int co
     }
 }
 
-template <int TC_BK>
+// MT = 128-row tiles per CTA (1 or 2).  With MT = 2 one weight slab feeds two accumulators, i.e. a
+// third fewer bytes per MMA through the SM's ~50 GB/s L2 port -- the measured limiter of this kernel.
+template <int TC_BK, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                   const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
@@ -90,7 +92,8 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;                    // bytes of one activation plane tile
     constexpr int SW = TC_BK * 2;                                    // swizzle span = row bytes (128 or 64)
     const int b_plane = bn * SW;                                     // bytes of one weight plane tile
-    const int stage_bytes = 2 * TC_A_PLANE + 2 * b_plane;
+    constexpr int A_BYTES = MT * 2 * TC_A_PLANE;                     // hi+lo planes of MT tiles
+    const int stage_bytes = A_BYTES + 2 * b_plane;
     const int stages = a.stages;
     const int nkb = a.ntaps * a.kb_per_tap;
 
@@ -105,18 +108,18 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     float4* s_part = reinterpret_cast<float4*>(s_bet + 256);            // [8 ranks][128 rows]
 
     pdl_wait();                       // upstream grid complete, its writes visible
-    // ---- tile coordinates ----
-    const int tile = blockIdx.y;
-    const int bg = tile / a.tiles_t, tt = tile - bg * a.tiles_t;
-    const int b0 = bg * a.TB;
+    // ---- tile coordinates (MT tiles per CTA; a tile index past the end loads zeros and stores nothing) ----
     const int L = a.win.L;
-    int t_end, t_lo, t0;
-    if (a.win.jptr) {
-        t_end = __ldg(a.win.jptr);
-        t_lo = max(0, t_end - a.win.R + 1);
-        t0 = t_end - a.tiles_t * a.TT + 1 + tt * a.TT;
-    } else {
-        t_end = L - 1; t_lo = 0; t0 = tt * a.TT;
+    int t_end, t_lo;
+    if (a.win.jptr) { t_end = __ldg(a.win.jptr); t_lo = max(0, t_end - a.win.R + 1); }
+    else { t_end = L - 1; t_lo = 0; }
+    int b0s[MT], t0s[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        const int tile = blockIdx.y * MT + m;
+        const int bg = tile / a.tiles_t, tt = tile - bg * a.tiles_t;
+        b0s[m] = (tile < a.ntiles) ? bg * a.TB : a.win.B;               // batch coordinate out of range -> TMA zero fill
+        t0s[m] = a.win.jptr ? (t_end - a.tiles_t * a.TT + 1 + tt * a.TT) : tt * a.TT;
     }
 
     // ---- one-time setup ----
@@ -128,7 +131,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         mbar_init(tmem_full_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<TC_TMEM_COLS>(tmem_ptr_smem);
+    if (warp == 1) tmem_alloc<MT * TC_TMEM_COLS>(tmem_ptr_smem);
     if (warp >= 2) {
         // epilogue vectors, indexed by accumulator column
         for (int c = threadIdx.x - 64; c < bn; c += 128) {
@@ -166,18 +169,22 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 const int tap = kb / a.kb_per_tap, kc = kb - tap * a.kb_per_tap;
-                const int tcoord = t0 + a.shifts[tap];
-                if (mcast) {
-                    // this CTA fetches rows [rank*slice, +slice) of the tile for the whole cluster
-                    const int off = rank * slice_rows * SW;
-                    tma_load_3d_mc(&mapA_hi, &full_bar[s], st + off, kc * TC_BK, tcoord + rank * slice_rows, b0, cta_mask);
-                    tma_load_3d_mc(&mapA_lo, &full_bar[s], st + TC_A_PLANE + off, kc * TC_BK, tcoord + rank * slice_rows, b0, cta_mask);
-                } else {
-                    tma_load_3d(&mapA_hi, &full_bar[s], st, kc * TC_BK, tcoord, b0);
-                    tma_load_3d(&mapA_lo, &full_bar[s], st + TC_A_PLANE, kc * TC_BK, tcoord, b0);
+#pragma unroll
+                for (int m = 0; m < MT; ++m) {
+                    uint8_t* sa = st + m * 2 * TC_A_PLANE;
+                    const int tcoord = t0s[m] + a.shifts[tap];
+                    if (mcast) {
+                        // this CTA fetches rows [rank*slice, +slice) of the tile for the whole cluster
+                        const int off = rank * slice_rows * SW;
+                        tma_load_3d_mc(&mapA_hi, &full_bar[s], sa + off, kc * TC_BK, tcoord + rank * slice_rows, b0s[m], cta_mask);
+                        tma_load_3d_mc(&mapA_lo, &full_bar[s], sa + TC_A_PLANE + off, kc * TC_BK, tcoord + rank * slice_rows, b0s[m], cta_mask);
+                    } else {
+                        tma_load_3d(&mapA_hi, &full_bar[s], sa, kc * TC_BK, tcoord, b0s[m]);
+                        tma_load_3d(&mapA_lo, &full_bar[s], sa + TC_A_PLANE, kc * TC_BK, tcoord, b0s[m]);
+                    }
                 }
-                tma_load_2d(&mapW_hi, &full_bar[s], st + 2 * TC_A_PLANE, kb * TC_BK, rank * bn);
-                tma_load_2d(&mapW_lo, &full_bar[s], st + 2 * TC_A_PLANE + b_plane, kb * TC_BK, rank * bn);
+                tma_load_2d(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, rank * bn);
+                tma_load_2d(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, rank * bn);
                 dbg_mark(a.dbg, 3, kb + 1);
             }
         }
@@ -192,16 +199,20 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint64_t dA_hi = umma_desc_kmajor<SW>(st);
-                const uint64_t dA_lo = umma_desc_kmajor<SW>(st + TC_A_PLANE);
-                const uint64_t dB_hi = umma_desc_kmajor<SW>(st + 2 * TC_A_PLANE);
-                const uint64_t dB_lo = umma_desc_kmajor<SW>(st + 2 * TC_A_PLANE + b_plane);
+                const uint64_t dB_hi = umma_desc_kmajor<SW>(st + A_BYTES);
+                const uint64_t dB_lo = umma_desc_kmajor<SW>(st + A_BYTES + b_plane);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    const uint64_t adv = (uint64_t)(k * 32 >> 4);          // 16 fp16 = 32 B inside the swizzle atom
-                    tc_mma_f16(tmem_base, dA_hi + adv, dB_hi + adv, idesc, (kb | k) != 0);
-                    tc_mma_f16(tmem_base, dA_hi + adv, dB_lo + adv, idesc, 1u);
-                    tc_mma_f16(tmem_base, dA_lo + adv, dB_hi + adv, idesc, 1u);
+                for (int m = 0; m < MT; ++m) {
+                    const uint64_t dA_hi = umma_desc_kmajor<SW>(st + m * 2 * TC_A_PLANE);
+                    const uint64_t dA_lo = umma_desc_kmajor<SW>(st + m * 2 * TC_A_PLANE + TC_A_PLANE);
+                    const uint32_t acc = tmem_base + m * TC_TMEM_COLS;
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 16; ++k) {
+                        const uint64_t adv = (uint64_t)(k * 32 >> 4);      // 16 fp16 = 32 B inside the swizzle atom
+                        tc_mma_f16(acc, dA_hi + adv, dB_hi + adv, idesc, (kb | k) != 0);
+                        tc_mma_f16(acc, dA_hi + adv, dB_lo + adv, idesc, 1u);
+                        tc_mma_f16(acc, dA_lo + adv, dB_hi + adv, idesc, 1u);
+                    }
                 }
                 if (mcast) tc_commit_mc(&empty_bar[s], cta_mask);          // frees the stage in every CTA's view
                 else tc_commit(&empty_bar[s]);                             // frees the smem stage
@@ -214,16 +225,18 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         // =========================== epilogue ===========================
         const int q = warp & 3;                                            // TMEM lane quarter of this warp
         const int r = q * 32 + lane;                                       // tile row == TMEM lane
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         const int bi = r / a.TT, ti = r - bi * a.TT;
-        const int b = b0 + bi, t = t0 + ti;
-        const bool row_ok = (b < a.win.B) && (t >= t_lo) && (t <= t_end) && (t < L);
         const float inv_s = a.inv_scale;
         const int n1 = (a.mode == 0) ? min(max(a.C - rank * bn, 0), bn) : half;
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         if (r == 0) dbg_mark(a.dbg, 5, 1);
+
+      for (int m = 0; m < MT; ++m) {                 // the MT accumulators, one after the other
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + m * TC_TMEM_COLS;
+        const int b = b0s[m] + bi, t = t0s[m] + ti;
+        const bool row_ok = (b < a.win.B) && (t >= t_lo) && (t <= t_end) && (t < L);
 
         // sweep 1: sums
         float s1 = 0.f, s2 = 0.f;
@@ -372,19 +385,25 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 }
             }
         }
+        // the statistics slots are reused by the next tile: wait until every CTA has read them
+        if (ncta > 1 && m + 1 < MT) { cluster_arrive(); cluster_wait(); }
+      }
         tc_fence_before();
     }
 
-    // ---- teardown: match the cluster barrier phases of the epilogue warps ----
+    // ---- teardown: match the cluster barrier phases of the epilogue warps (2*MT-1 of them) ----
     if (ncta > 1) {
-        if (warp < 2) { cluster_arrive(); cluster_wait(); }      // phase 2 (the epilogue warps did theirs)
-        cluster_arrive();                     // phase 3: nobody reads my shared memory any more
+        if (warp < 2) {
+#pragma unroll
+            for (int i = 0; i < 2 * MT - 1; ++i) { cluster_arrive(); cluster_wait(); }
+        }
+        cluster_arrive();                     // last phase: nobody reads my shared memory any more
         cluster_wait();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<TC_TMEM_COLS>(tmem_base);
+        tmem_dealloc<MT * TC_TMEM_COLS>(tmem_base);
     }
 }
 
@@ -466,26 +485,28 @@ int tc_bk() {
     return bk;
 }
 
-int tc_stages_for(int bn, int bk) {
-    const int stage = 2 * TC_BM * bk * 2 + 2 * bn * bk * 2;
+int tc_stages_for(int bn, int bk, int mt) {
+    const int stage = mt * 2 * TC_BM * bk * 2 + 2 * bn * bk * 2;
     int s = (200 * 1024) / stage;
     return s < 2 ? 2 : (s > TC_MAX_STAGES ? TC_MAX_STAGES : s);
 }
 
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, int bk, cudaStream_t s) {
+                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, cudaStream_t s) {
     static bool attr_set = false;
     const int max_smem = 227 * 1024;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         attr_set = true;
     }
-    const size_t smem = (size_t)a.stages * (2 * TC_BM * bk * 2 + 2 * a.bn * bk * 2) + TC_AUX_BYTES + 1024;
+    if (mt == 2 && bk != 32) throw std::runtime_error("conv_ln_tc: paired tiles need the 32-wide slab");
+    const size_t smem = (size_t)a.stages * (mt * 2 * TC_BM * bk * 2 + 2 * a.bn * bk * 2) + TC_AUX_BYTES + 1024;
     if (smem > (size_t)max_smem) throw std::runtime_error("conv_ln_tc: shared memory budget exceeded");
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)ncta, (unsigned)tiles, 1);
+    cfg.gridDim = dim3((unsigned)ncta, (unsigned)ctas_y, 1);
     cfg.blockDim = dim3(TC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = s;
@@ -495,8 +516,10 @@ void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    cudaError_t e = (bk == 64) ? cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64>, a_hi, a_lo, w_hi, w_lo, a)
-                               : cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32>, a_hi, a_lo, w_hi, w_lo, a);
+    cudaError_t e;
+    if (mt == 2)       e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 2>, a_hi, a_lo, w_hi, w_lo, a);
+    else if (bk == 64) e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1>, a_hi, a_lo, w_hi, w_lo, a);
+    else               e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 1>, a_hi, a_lo, w_hi, w_lo, a);
     if (e != cudaSuccess) throw std::runtime_error(std::string("conv_ln_tc launch: ") + cudaGetErrorString(e));
 }
 

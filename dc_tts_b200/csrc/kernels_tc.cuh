@@ -35,7 +35,7 @@ struct TcArgs {
     int ntaps; int shifts[3]; int kb_per_tap; int stages;   // kb_per_tap in units of the kernel's BK (64 or 32)
     int mcast;                     // 1: the A tile is fetched once per cluster (each CTA loads 128/ncta rows, TMA multicast)
     // tiling: 128 rows = TT time rows x TB batch rows
-    int TT, TB, tiles_t;
+    int TT, TB, tiles_t, ntiles;   // ntiles = batch groups x tiles_t (a CTA takes MT consecutive tiles)
     RowWin win;
     // residual (mode 1) and outputs
     Planes X;                      // highway residual, same row index as the output
@@ -52,12 +52,29 @@ void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, i
 void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn, int bk);
 
 // pipeline depth that fits the shared-memory budget for `bn` accumulator columns per CTA
-int tc_stages_for(int bn, int bk);
+int tc_stages_for(int bn, int bk, int mt);
 // reduction slab per pipeline stage (fp16 elements): 64 (128B swizzle); DCTTS_TC_BK=32 selects 32 (64B swizzle, deeper pipeline)
 int tc_bk();
 // grid = (ncta, tiles); cluster (ncta,1,1)
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int tiles, int bk, cudaStream_t s);
+                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, cudaStream_t s);
+
+// ---- tcgen05 attention (kernels_attn_tc.cu) ----
+struct AttnTcArgs {
+    const float* Q; int ldq;       // fp32 queries (copied verbatim into R[:, d:2d])
+    float* R; int ldr;             // (B,T,2d) = [A.V ; Q]
+    Planes Rpl;                    // optional split-plane copy of R
+    float* align;                  // (B,N,T) or nullptr
+    long long* maxatt;             // (B,T) or nullptr
+    const int* pma;                // (B) monotonic window start, nullptr -> dense softmax
+    int T, N, d, win_size;
+    float scale;                   // 1/sqrt(d)
+};
+int attn_tc_padded_keys();
+// K, V fp32 -> K planes (B,N,d) and transposed V planes (B,d,192), keys >= N zero
+void launch_attn_kv_planes(const float* K, int ldk, const float* V, int ldv, Planes kp, Planes vtp, int B, int N, int d,
+                           cudaStream_t s);
+void launch_attention_tc(const Planes& Q, const Planes& K, const Planes& Vt, const AttnTcArgs& a, int B, cudaStream_t s);
 
 void launch_f32_to_planes(const float* x, int ldx, Planes p, long long rows, int C, cudaStream_t s);
 void launch_planes_to_f32(Planes p, float* y, int ldy, long long rows, int C, cudaStream_t s);

@@ -133,9 +133,9 @@ int dctts_reserve(dctts_handle h, int32_t max_batch);
 int64_t dctts_launch_count(dctts_handle h);
 /* Selects the kernel set: 0 = one fp32 CUDA-core GEMM + one LN kernel per block (baseline),
  * 1 = default: tcgen05 split-fp16 (3-MMA, fp32-grade) fused blocks where they apply (whole
- * networks, and the wide AudioDec rows of the decode step when B >= 8), fp32 kernels for the
- * one-row decode blocks, 2 = experimental: fp32 blocks plus the cluster-persistent chain
- * kernels (kernels_chain.cu) for the one-row decode blocks -- correct, measured slower. */
+ * networks, full-sequence attention, and the wide AudioDec rows of the decode step when B >= 8),
+ * split-K fp32 kernels for the few-row decode blocks, 2 = experiment: fp32 CUDA-core blocks with
+ * the fused few-row block kernel (8-CTA cluster, GEMM + LN in one launch; measured slower). */
 int dctts_set_tensor_path(dctts_handle h, int32_t mode);
 /* Measurement aid for bench.py's roofline leg: runs the block `scope` on a synthetic
  * (B,L,Cin) input `warmup`+`iters` times and returns the mean device time of each of its
