@@ -528,10 +528,11 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     a.bias = l.bias; a.g1 = l.g1; a.b1 = l.b1; a.g2 = (p.mode == 1) ? l.g2 : l.g1; a.b2 = (p.mode == 1) ? l.b2 : l.b1;
     a.mode = p.mode; a.act = act; a.C = l.cout; a.bn = p.bn; a.half = p.half; a.inv_scale = p.inv_scale;
     const int tiles = ((win.B + TB - 1) / TB) * tiles_t;
-    // big launches pair two 128-row tiles per CTA (one weight slab feeds both accumulators): the kernel is
-    // bound by the bytes an SM can pull from L2, and pairing cuts them by a third per MMA
-    static const bool no_pair = getenv("DCTTS_TC_NO_PAIR") != nullptr;
-    const int mt = (!no_pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
+    // DCTTS_TC_PAIR=1: two 128-row tiles per CTA sharing one weight slab (a third fewer bytes per MMA).
+    // Measured no gain (SSRN/HC_11: 1.27 vs 1.26 ms), like TMA multicast and a deeper pipeline: the kernel sits
+    // at the ~50 % tensor-pipe ceiling of single-CTA (cta_group::1) MMAs with both operands in shared memory.
+    static const bool pair = getenv("DCTTS_TC_PAIR") != nullptr;
+    const int mt = (pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
     const int bk = (mt == 2) ? 32 : tc_bk();
     a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap * (64 / bk);
     if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
