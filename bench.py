@@ -248,7 +248,11 @@ def run_b200(args, rank, local_rank, world):
         roof = {"kernel": ("conv_ln_tc_kernel: SSRN/HC_11 fused hc block on tcgen05 (M=%d, K=3x1024, N=2048, 3 fp16 MMA "
                            "passes per k-step)" if tensor else "conv_gemm_tiled: SSRN/HC_11 conv-GEMM on fp32 cores (M=%d, K=3x1024, N=2048)") % rows,
                 "bound": "tensor", "achieved": ach, "peak": peaks["tf"], "unit": "TFLOP/s", "frac": ach / peaks["tf"],
-                "traffic": None, "peak_source": peaks["src"] + " bf16/fp16 dense (burst)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of this very launch shape (B=32), one ncu --set full
+                # capture: profiles/r01_conv_ln_tc_ssrn_hc11_b32.ncu-rep (algorithmic bytes: 245 MB)
+                "traffic": (218786816 if (tensor and B == 32) else None),
+                "algorithmic_bytes": int(rows * 1024 * 4 * 2 + 2 * 3 * 1024 * 2048 * 2),
+                "peak_source": peaks["src"] + " bf16/fp16 dense (burst)",
                 "kernel_ms": k_ms, "other_kernels_of_block_ms": [m for i, m in enumerate(kms) if m != k_ms],
                 "tensor_pipe_flops_executed_tflops": (3 * ach if tensor else 0.0),
                 "note": "achieved = ALGORITHMIC FLOPs 2*M*K*N / CUDA-event time of that launch; the split-fp16 "
