@@ -268,7 +268,7 @@ def run_b200(args, rank, local_rank, world):
         t2m_ms, ssrn_ms = a.elapsed_time(b), b.elapsed_time(c)
         audio_s = T * hp.r * hp.hop_length / float(hp.sr)
         single = {"text2mel_ms": t2m_ms, "ssrn_ms": ssrn_ms, "rtf_x_realtime": audio_s / ((t2m_ms + ssrn_ms) / 1e3)}
-        cpu = cpu_reference(passes=args.cpu_passes) if args.cpu_passes > 0 else None
+        cpu = cpu_reference(passes=args.cpu_passes) if (args.cpu_passes > 0 and world == 1) else None   # rank 0, N = 1 only
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16x2 split operands on tcgen05, fp32 accumulate)" if args.tensor_path else "f32", "data": "synthetic",
@@ -295,7 +295,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
     ap.add_argument("--nchars", type=int, default=100)
-    ap.add_argument("--cpu-passes", type=int, default=12, help="full-graph passes of the CPU baseline sample (0 = skip)")
+    ap.add_argument("--cpu-passes", type=int, default=60, help="full-graph passes of the CPU baseline sample (0 = skip)")
     ap.add_argument("--tensor-path", type=int, default=1, choices=[0, 1], help="1 = tcgen05 blocks (default), 0 = fp32 CUDA-core kernels only")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

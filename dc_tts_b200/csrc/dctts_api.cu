@@ -528,25 +528,32 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     a.bias = l.bias; a.g1 = l.g1; a.b1 = l.b1; a.g2 = (p.mode == 1) ? l.g2 : l.g1; a.b2 = (p.mode == 1) ? l.b2 : l.b1;
     a.mode = p.mode; a.act = act; a.C = l.cout; a.bn = p.bn; a.half = p.half; a.inv_scale = p.inv_scale;
     const int tiles = ((win.B + TB - 1) / TB) * tiles_t;
+    // CTA pairs (tcgen05 cta_group::2): hc / transposed-conv blocks packed with 128-channel halves, on full
+    // sequences.  Ranks (2s, 2s+1) of the cluster share channel slice s (256 channels), take consecutive tiles,
+    // each stages half of the slice's weight slab; the accumulator is 512 columns (256 gate + 256 info).
+    static const bool no_cg2 = getenv("DCTTS_TC_NO_CG2") != nullptr;
+    // Only when the paired grid still fills the machine: pairs halve the CTA count (B=1 SSRN: 1.09 vs 0.74 ms).
+    const int cg = (!no_cg2 && p.mode != 0 && p.half == 128 && p.bn == 256 && (p.ncta % 2) == 0 && !win.jptr && TT == 128 &&
+                    TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
+    if (cg == 2) { a.bn = 512; a.half = 256; }
     // DCTTS_TC_PAIR=1: two 128-row tiles per CTA sharing one weight slab (a third fewer bytes per MMA).
-    // Measured no gain (SSRN/HC_11: 1.27 vs 1.26 ms), like TMA multicast and a deeper pipeline: the kernel sits
-    // at the ~50 % tensor-pipe ceiling of single-CTA (cta_group::1) MMAs with both operands in shared memory.
+    // Measured no gain (SSRN/HC_11: 1.27 vs 1.26 ms), like TMA multicast and a deeper pipeline.
     static const bool pair = getenv("DCTTS_TC_PAIR") != nullptr;
-    const int mt = (pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
-    const int bk = (mt == 2) ? 32 : tc_bk();
+    const int mt = (cg == 1 && pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
+    const int bk = (mt == 2) ? 32 : (cg == 2 ? 64 : tc_bk());
     a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap * (64 / bk);
     if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
     else {
         const int tot = (l.size - 1) * rate, left = causal ? tot : tot / 2;
         for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
     }
-    a.stages = std::min(tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));
+    a.stages = std::min(tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
     a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.ntiles = tiles; a.win = win;
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
     // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the
     // tile is 128 consecutive time rows, each CTA contributing 128/ncta of them
     static const bool no_mcast = getenv("DCTTS_TC_NO_MCAST") != nullptr;
-    a.mcast = (!no_mcast && p.ncta > 1 && TT == 128 && TB == 1) ? 1 : 0;
+    a.mcast = (!no_mcast && cg == 1 && p.ncta > 1 && TT == 128 && TB == 1) ? 1 : 0;
     const int box_rows = a.mcast ? TT / p.ncta : TT;
     CUtensorMap mAh, mAl;
     tc_make_act_map(&mAh, X.hi, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
@@ -563,13 +570,33 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     }
     CUtensorMap mWh = p.mWhi, mWl = p.mWlo;
     if (bk != tc_bk()) { tc_make_w_map(&mWh, p.Whi, p.Ktot, p.nrows, p.bn, bk); tc_make_w_map(&mWl, p.Wlo, p.Ktot, p.nrows, p.bn, bk); }
-    launch_conv_ln_tc(mAh, mAl, mWh, mWl, a, p.ncta, (tiles + mt - 1) / mt, bk, mt, lc.s); lc.count();
+    // hc on full sequences: the residual tile comes in by TMA and the output planes leave by TMA (staged in the
+    // same drained pipeline stage), instead of row-scattered 32-byte loads / stores from the epilogue threads
+    static const bool no_rtma = getenv("DCTTS_TC_NO_RESID_TMA") != nullptr;
+    CUtensorMap io[4];
+    a.resid_tma = 0;
+    if (!no_rtma && p.mode == 1 && cg == 1 && mt == 1 && !win.jptr && TT == 128 && TB == 1 && out.hi &&
+        2 * a.half * 128 * 2 <= 2 * 128 * bk * 2 + 2 * a.bn * bk * 2) {
+        a.resid_tma = 1;
+        tc_make_act_map(&io[0], X.hi, l.cin, X.ld, win.L, win.B, 128, 1, 64);
+        tc_make_act_map(&io[1], X.lo, l.cin, X.ld, win.L, win.B, 128, 1, 64);
+        tc_make_act_map(&io[2], out.hi, l.cout, out.ld, win.L, win.B, 128, 1, 64);
+        tc_make_act_map(&io[3], out.lo, l.cout, out.ld, win.L, win.B, 128, 1, 64);
+    }
+    launch_conv_ln_tc(mAh, mAl, mWh, mWl, a.resid_tma ? io : nullptr, a, p.ncta, (tiles + mt * cg - 1) / (mt * cg), bk, mt, cg,
+                      lc.s); lc.count();
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(lc.s);
         for (int c = 0; c < std::min(16, p.ncta * tiles); ++c)
             fprintf(stderr, "[tc]  cta %2d: start=%d tmem=0x%x nkb=%d tma=%d mma=%d acc_ready=%d published=%d combined=%d\n", c,
                     dbg_host[64 * c], dbg_host[64 * c + 1], dbg_host[64 * c + 2], dbg_host[64 * c + 3], dbg_host[64 * c + 4],
                     dbg_host[64 * c + 5], dbg_host[64 * c + 6], dbg_host[64 * c + 7]);
+        {
+            const int* d0 = dbg_host;      // SM-clock deltas of CTA 0
+            auto dt = [&](int a_, int b_) { return (d0[b_] - d0[a_]) & 0x7fffffff; };
+            fprintf(stderr, "[tc]  cta 0 cycles: setup %d | main loop %d | sweeps1+2 %d | cluster barrier %d | sweep3+stores %d | teardown %d | total %d\n",
+                    dt(8, 9), dt(9, 10), dt(10, 11), dt(11, 12), dt(12, 13), dt(13, 14), dt(8, 14));
+        }
         if (e != cudaSuccess) throw std::runtime_error(std::string("conv_ln_tc failed: ") + cudaGetErrorString(e));
     }
 }

@@ -32,7 +32,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_AUX_BYTES = 256 /*barriers*/ + 3 * 256 * 4 /*bias,gamma,beta*/ + 8 * 128 * 16 /*stats*/;
+constexpr int TC_AUX_BYTES = 256 /*barriers*/ + 3 * 512 * 4 /*bias,gamma,beta*/ + 8 * 128 * 16 /*stats*/;
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -42,6 +42,10 @@ __device__ __forceinline__ void dbg_mark(int* dbg, int slot, int v) {
         const int cta = blockIdx.y * gridDim.x + blockIdx.x;
         if (cta < 16) { reinterpret_cast<volatile int*>(dbg)[64 * cta + slot] = v; __threadfence_system(); }
     }
+}
+
+__device__ __forceinline__ void dbg_time(int* dbg, int slot) {
+    if (dbg) dbg_mark(dbg, slot, (int)(clock64() & 0x7fffffff));
 }
 
 __device__ __forceinline__ void split_store16(const float (&o)[16], __half* hi, __half* lo) {
@@ -76,22 +80,33 @@ __device__ __forceinline__ void store_planes(const Planes& p, size_t row, int co
 
 // MT = 128-row tiles per CTA (1 or 2).  With MT = 2 one weight slab feeds two accumulators, i.e. a
 // third fewer bytes per MMA through the SM's ~50 GB/s L2 port -- the measured limiter of this kernel.
-template <int TC_BK, int MT>
+// CG = CTAs per MMA (tcgen05 cta_group): 1, or 2 = CTA pairs -- ranks (2s, 2s+1) of the cluster share channel slice s,
+// take two consecutive 128-row tiles, each loads HALF of the slice's weight slab, and the even CTA issues M = 256 MMAs
+// that fill both CTAs' tensor memory (512 columns each: the slice's gate half then its info half).
+template <int TC_BK, int MT, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
                   const __grid_constant__ CUtensorMap mapW_hi, const __grid_constant__ CUtensorMap mapW_lo,
+                  const __grid_constant__ CUtensorMap mapX_hi, const __grid_constant__ CUtensorMap mapX_lo,
+                  const __grid_constant__ CUtensorMap mapO_hi, const __grid_constant__ CUtensorMap mapO_lo,
                   const TcArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     pdl_launch_dependents();          // PDL: let the next kernel's CTAs be scheduled behind this one
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rank = (int)cluster_ctarank();
+    if (threadIdx.x == 0) dbg_time(a.dbg, 8);                        // t0: kernel entry
+    static_assert(CG == 1 || (CG == 2 && MT == 1), "CTA pairs take one tile each");
+    const int crank = (int)cluster_ctarank();
     const int ncta = (int)cluster_nctarank();
-    const int bn = a.bn, half = a.half;
+    const int rank = crank / CG;                                     // channel slice of this CTA
+    const int peer = crank % CG;                                     // position inside the CTA pair (0 = leader)
+    const int nslices = ncta / CG;
+    const int bn = a.bn, half = a.half;                              // accumulator columns per CTA / per LN half
     constexpr int TC_A_PLANE = TC_BM * TC_BK * 2;                    // bytes of one activation plane tile
     constexpr int SW = TC_BK * 2;                                    // swizzle span = row bytes (128 or 64)
-    const int b_plane = bn * SW;                                     // bytes of one weight plane tile
+    const int bn_load = bn / CG;                                     // weight rows this CTA stages (a pair splits the slab)
+    const int b_plane = bn_load * SW;                                // bytes of one weight plane tile
     constexpr int A_BYTES = MT * 2 * TC_A_PLANE;                     // hi+lo planes of MT tiles
     const int stage_bytes = A_BYTES + 2 * b_plane;
     const int stages = a.stages;
@@ -101,11 +116,12 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);              // [stages]
     uint64_t* empty_bar = full_bar + TC_MAX_STAGES;                      // [stages]
     uint64_t* tmem_full_bar = empty_bar + TC_MAX_STAGES;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* resid_bar = tmem_full_bar + 1;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(resid_bar + 1);
     float* s_bias = reinterpret_cast<float*>(aux + 256);
-    float* s_gam = s_bias + 256;
-    float* s_bet = s_gam + 256;
-    float4* s_part = reinterpret_cast<float4*>(s_bet + 256);            // [8 ranks][128 rows]
+    float* s_gam = s_bias + 512;
+    float* s_bet = s_gam + 512;
+    float4* s_part = reinterpret_cast<float4*>(s_bet + 512);            // [8 slices][128 rows]
 
     pdl_wait();                       // upstream grid complete, its writes visible
     // ---- tile coordinates (MT tiles per CTA; a tile index past the end loads zeros and stores nothing) ----
@@ -116,7 +132,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     int b0s[MT], t0s[MT];
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-        const int tile = blockIdx.y * MT + m;
+        const int tile = (blockIdx.y * MT + m) * CG + peer;
         const int bg = tile / a.tiles_t, tt = tile - bg * a.tiles_t;
         b0s[m] = (tile < a.ntiles) ? bg * a.TB : a.win.B;               // batch coordinate out of range -> TMA zero fill
         t0s[m] = a.win.jptr ? (t_end - a.tiles_t * a.TT + 1 + tt * a.TT) : tt * a.TT;
@@ -128,10 +144,11 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         // with the multicast A tile a stage may only be refilled once EVERY CTA of the cluster has
         // drained it: each MMA warp commits to all CTAs' empty barriers
         for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], a.mcast ? (uint32_t)ncta : 1u); }
-        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_full_bar, 1); mbar_init(resid_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc<MT * TC_TMEM_COLS>(tmem_ptr_smem);
+    if (CG == 2) { cluster_arrive(); cluster_wait(); }      // the pair allocator needs both CTAs up
+    if (warp == 1) { if (CG == 2) tmem_alloc_pair<512>(tmem_ptr_smem); else tmem_alloc<MT * TC_TMEM_COLS>(tmem_ptr_smem); }
     if (warp >= 2) {
         // epilogue vectors, indexed by accumulator column
         for (int c = threadIdx.x - 64; c < bn; c += 128) {
@@ -153,7 +170,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    if (threadIdx.x == 0) { dbg_mark(a.dbg, 0, 1); dbg_mark(a.dbg, 1, (int)tmem_base); dbg_mark(a.dbg, 2, nkb); }
+    if (threadIdx.x == 0) { dbg_mark(a.dbg, 0, 1); dbg_mark(a.dbg, 1, (int)tmem_base); dbg_mark(a.dbg, 2, nkb); dbg_time(a.dbg, 9); }   // t1: setup done
     if (ncta > 1) { cluster_arrive(); cluster_wait(); }   // phase 1: every CTA is running, its barriers initialised
     const bool mcast = a.mcast != 0 && ncta > 1;
     const uint16_t cta_mask = (uint16_t)((1u << ncta) - 1u);
@@ -166,7 +183,8 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 const int s = kb % stages;
                 const uint32_t ph = (uint32_t)(kb / stages) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);
-                mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                if (CG == 1) mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+                else if (peer == 0) mbar_expect_tx(&full_bar[s], 2u * (uint32_t)stage_bytes);   // both CTAs' bytes land on the leader's barrier
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 const int tap = kb / a.kb_per_tap, kc = kb - tap * a.kb_per_tap;
 #pragma unroll
@@ -178,20 +196,42 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         const int off = rank * slice_rows * SW;
                         tma_load_3d_mc(&mapA_hi, &full_bar[s], sa + off, kc * TC_BK, tcoord + rank * slice_rows, b0s[m], cta_mask);
                         tma_load_3d_mc(&mapA_lo, &full_bar[s], sa + TC_A_PLANE + off, kc * TC_BK, tcoord + rank * slice_rows, b0s[m], cta_mask);
+                    } else if (CG == 2) {
+                        tma_load_3d_pair(&mapA_hi, &full_bar[s], sa, kc * TC_BK, tcoord, b0s[m]);
+                        tma_load_3d_pair(&mapA_lo, &full_bar[s], sa + TC_A_PLANE, kc * TC_BK, tcoord, b0s[m]);
                     } else {
                         tma_load_3d(&mapA_hi, &full_bar[s], sa, kc * TC_BK, tcoord, b0s[m]);
                         tma_load_3d(&mapA_lo, &full_bar[s], sa + TC_A_PLANE, kc * TC_BK, tcoord, b0s[m]);
                     }
                 }
-                tma_load_2d(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, rank * bn);
-                tma_load_2d(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, rank * bn);
-                dbg_mark(a.dbg, 3, kb + 1);
+                if (CG == 2) {
+                    tma_load_2d_pair(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, crank * bn_load);
+                    tma_load_2d_pair(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, crank * bn_load);
+                } else {
+                    tma_load_2d(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, rank * bn);
+                    tma_load_2d(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, rank * bn);
+                }
+            }
+            dbg_mark(a.dbg, 3, nkb);
+            if (a.resid_tma) {
+                // highway residual = this CTA's 'half' channels of the same rows: fetched into the next ring stage
+                // as soon as it has drained, i.e. while the last k-blocks are still being multiplied
+                const int s = nkb % stages;
+                mbar_wait(&empty_bar[s], ((uint32_t)(nkb / stages) & 1u) ^ 1u);
+                uint8_t* st = smem + (size_t)s * stage_bytes;
+                const int nbox = half / 64;
+                mbar_expect_tx(resid_bar, (uint32_t)(2 * nbox * 16384));
+                for (int i = 0; i < nbox; ++i) {
+                    tma_load_3d(&mapX_hi, resid_bar, st + i * 16384, rank * half + i * 64, t0s[0], b0s[0]);
+                    tma_load_3d(&mapX_lo, resid_bar, st + (nbox + i) * 16384, rank * half + i * 64, t0s[0], b0s[0]);
+                }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        // =========================== MMA issuer ===========================
-        const uint32_t idesc = umma_idesc_f16(TC_BM, (uint32_t)bn);
+    } else if (warp == 1 && peer == 0) {
+        // =========================== MMA issuer (the pair's leader only) ===========================
+        const uint32_t idesc = (CG == 2) ? umma_idesc_f16(256, 256) : umma_idesc_f16(TC_BM, (uint32_t)bn);
+        const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1));
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % stages;
             const uint32_t ph = (uint32_t)(kb / stages) & 1u;
@@ -201,6 +241,24 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t dB_hi = umma_desc_kmajor<SW>(st + A_BYTES);
                 const uint64_t dB_lo = umma_desc_kmajor<SW>(st + A_BYTES + b_plane);
+                if (CG == 2) {
+                    // two N = 256 chunks: rows [0,128) / [128,256) of each CTA's weight tile -> TMEM columns [0,256) / [256,512)
+                    const uint64_t dA_hi = umma_desc_kmajor<SW>(st), dA_lo = umma_desc_kmajor<SW>(st + TC_A_PLANE);
+#pragma unroll
+                    for (int ck = 0; ck < 2; ++ck) {
+                        const uint64_t cb = (uint64_t)((ck * 128 * SW) >> 4);
+                        const uint32_t acc = tmem_base + ck * 256;
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k) {
+                            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                            tc_mma_f16_pair(acc, dA_hi + adv, dB_hi + cb + adv, idesc, (kb | k) != 0);
+                            tc_mma_f16_pair(acc, dA_hi + adv, dB_lo + cb + adv, idesc, 1u);
+                            tc_mma_f16_pair(acc, dA_lo + adv, dB_hi + cb + adv, idesc, 1u);
+                        }
+                    }
+                    tc_commit_pair(&empty_bar[s], pair_mask);                  // frees the stage in both CTAs
+                    if (kb == nkb - 1) tc_commit_pair(tmem_full_bar, pair_mask);
+                } else {
 #pragma unroll
                 for (int m = 0; m < MT; ++m) {
                     const uint64_t dA_hi = umma_desc_kmajor<SW>(st + m * 2 * TC_A_PLANE);
@@ -217,11 +275,12 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 if (mcast) tc_commit_mc(&empty_bar[s], cta_mask);          // frees the stage in every CTA's view
                 else tc_commit(&empty_bar[s]);                             // frees the smem stage
                 if (kb == nkb - 1) tc_commit(tmem_full_bar);               // accumulator complete
-                dbg_mark(a.dbg, 4, kb + 1);
+                }
             }
             __syncwarp();
         }
-    } else {
+        if (lane == 0) dbg_mark(a.dbg, 4, nkb);
+    } else if (warp >= 2) {
         // =========================== epilogue ===========================
         const int q = warp & 3;                                            // TMEM lane quarter of this warp
         const int r = q * 32 + lane;                                       // tile row == TMEM lane
@@ -231,61 +290,66 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
 
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        if (r == 0) dbg_mark(a.dbg, 5, 1);
+        if (r == 0) { dbg_mark(a.dbg, 5, 1); dbg_time(a.dbg, 10); }       // t2: accumulator complete (main loop over)
 
       for (int m = 0; m < MT; ++m) {                 // the MT accumulators, one after the other
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + m * TC_TMEM_COLS;
         const int b = b0s[m] + bi, t = t0s[m] + ti;
         const bool row_ok = (b < a.win.B) && (t >= t_lo) && (t <= t_end) && (t < L);
 
-        // sweep 1: sums
-        float s1 = 0.f, s2 = 0.f;
-        for (int c = 0; c < n1; c += 16) {
-            float v[16];
-            tmem_ld16(taddr + c, v);
+        // ONE statistics sweep (was two): shifted sums about a pivot taken from the row itself, so that
+        // M2 = Q - S^2/n does not cancel; 64 columns per tcgen05.wait (two x32 loads in flight).
+        float s1, s2 = 0.f, q1, q2 = 0.f, m1, m2 = 0.f;
+        {
+            float piv = 0.f, S = 0.f, Q = 0.f;
+            for (int c = 0; c < n1; c += 64) {
+                float v[2][32];
+                tmem_ld32_nowait(taddr + c, v[0]);
+                if (c + 32 < n1) tmem_ld32_nowait(taddr + c + 32, v[1]);
+                tmem_ld_wait();
+                if (c == 0) piv = fmaf(v[0][0], inv_s, s_bias[0]);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) if (c + i < n1) s1 += fmaf(v[i], inv_s, s_bias[c + i]);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int cc = c + h * 32 + i;
+                        if (cc < n1) { const float d = fmaf(v[h][i], inv_s, s_bias[cc]) - piv; S += d; Q = fmaf(d, d, Q); }
+                    }
+            }
+            const float n = (float)max(n1, 1);
+            s1 = piv * (float)n1 + S; m1 = n1 > 0 ? s1 / n : 0.f; q1 = fmaxf(Q - S * S / n, 0.f);
         }
         if (a.mode != 0) {
-            for (int c = 0; c < half; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + half + c, v);
+            float piv = 0.f, S = 0.f, Q = 0.f;
+            for (int c = 0; c < half; c += 64) {
+                float v[2][32];
+                tmem_ld32_nowait(taddr + half + c, v[0]);
+                tmem_ld32_nowait(taddr + half + c + 32, v[1]);
+                tmem_ld_wait();
+                if (c == 0) piv = fmaf(v[0][0], inv_s, s_bias[half]);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) s2 += fmaf(v[i], inv_s, s_bias[half + c + i]);
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float d = fmaf(v[h][i], inv_s, s_bias[half + c + h * 32 + i]) - piv; S += d; Q = fmaf(d, d, Q);
+                    }
             }
-        }
-        const float m1 = n1 > 0 ? s1 / (float)n1 : 0.f;
-        const float m2 = s2 / (float)half;
-        // sweep 2: centred second moments about the local means
-        float q1 = 0.f, q2 = 0.f;
-        for (int c = 0; c < n1; c += 16) {
-            float v[16];
-            tmem_ld16(taddr + c, v);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) if (c + i < n1) { float d = fmaf(v[i], inv_s, s_bias[c + i]) - m1; q1 = fmaf(d, d, q1); }
-        }
-        if (a.mode != 0) {
-            for (int c = 0; c < half; c += 16) {
-                float v[16];
-                tmem_ld16(taddr + half + c, v);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { float d = fmaf(v[i], inv_s, s_bias[half + c + i]) - m2; q2 = fmaf(d, d, q2); }
-            }
+            s2 = piv * (float)half + S; m2 = s2 / (float)half; q2 = fmaxf(Q - S * S / (float)half, 0.f);
         }
         // combine over the cluster
         float mean1, rstd1, mean2 = 0.f, rstd2 = 0.f;
         if (ncta > 1) {
             const uint32_t my_slot = smem_u32(&s_part[rank * 128 + r]);
-            for (int p = 0; p < ncta; ++p) st_cluster_f4(mapa(my_slot, (uint32_t)p), s1, q1, s2, q2);
-            if (r == 0) dbg_mark(a.dbg, 6, 1);
+            for (int p = 0; p < nslices; ++p) st_cluster_f4(mapa(my_slot, (uint32_t)(p * CG + peer)), s1, q1, s2, q2);
+            if (r == 0) { dbg_mark(a.dbg, 6, 1); dbg_time(a.dbg, 11); }   // t3: sweeps 1+2 done, partials published
             cluster_arrive();                                              // phase 2: partials published
             cluster_wait();
-            if (r == 0) dbg_mark(a.dbg, 7, 1);
+            if (r == 0) { dbg_mark(a.dbg, 7, 1); dbg_time(a.dbg, 12); }   // t4: cluster barrier passed
             float S1 = 0.f, S2 = 0.f;
-            for (int p = 0; p < ncta; ++p) { float4 v = s_part[p * 128 + r]; S1 += v.x; S2 += v.z; }
+            for (int p = 0; p < nslices; ++p) { float4 v = s_part[p * 128 + r]; S1 += v.x; S2 += v.z; }
             mean1 = S1 / (float)a.C; mean2 = S2 / (float)a.C;
             float M1 = 0.f, M2 = 0.f;
-            for (int p = 0; p < ncta; ++p) {
+            for (int p = 0; p < nslices; ++p) {
                 float4 v = s_part[p * 128 + r];
                 const int np = (a.mode == 0) ? min(max(a.C - p * bn, 0), bn) : half;
                 if (np > 0) { float d = v.x / (float)np - mean1; M1 += v.y + (float)np * d * d; }
@@ -332,13 +396,25 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 }
             } else if (a.mode == 1) {
                 const size_t row = (size_t)b * L + t;
+                // residual / output staging tile in the drained ring stage: [plane][box of 64 ch][128 rows][128 B], 128B swizzle
+                uint8_t* rs = smem + (size_t)(nkb % stages) * stage_bytes;
+                const int nbox = half / 64;
+                if (a.resid_tma) mbar_wait(resid_bar, 0);
                 for (int c = 0; c < half; c += 16) {
                     float v1[16], v2[16], o[16];
                     const int col = rank * half + c;
                     // highway residual: 16 channels of both planes (2 x 32 B)
                     __align__(16) __half xh[16] = {};
                     __align__(16) __half xl[16] = {};
-                    if (row_ok) {
+                    uint8_t* sh = rs + (c >> 6) * 16384 + r * 128;              // this row inside box c/64 (hi plane)
+                    uint8_t* sl = sh + nbox * 16384;
+                    const int k0 = (((c & 63) >> 3) ^ (r & 7)) << 4, k1 = ((((c & 63) >> 3) + 1) ^ (r & 7)) << 4;
+                    if (a.resid_tma) {
+                        reinterpret_cast<uint4*>(xh)[0] = *reinterpret_cast<const uint4*>(sh + k0);
+                        reinterpret_cast<uint4*>(xh)[1] = *reinterpret_cast<const uint4*>(sh + k1);
+                        reinterpret_cast<uint4*>(xl)[0] = *reinterpret_cast<const uint4*>(sl + k0);
+                        reinterpret_cast<uint4*>(xl)[1] = *reinterpret_cast<const uint4*>(sl + k1);
+                    } else if (row_ok) {
                         const uint4* ph = reinterpret_cast<const uint4*>(a.X.hi + row * a.X.ld + col);
                         const uint4* pl = reinterpret_cast<const uint4*>(a.X.lo + row * a.X.ld + col);
                         reinterpret_cast<uint4*>(xh)[0] = __ldg(ph); reinterpret_cast<uint4*>(xh)[1] = __ldg(ph + 1);
@@ -354,11 +430,35 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         float x = __half2float(xh[i]) + __half2float(xl[i]);
                         o[i] = h1 * z2 + (1.0f - h1) * x;
                     }
-                    if (row_ok && a.out.hi) store_planes(a.out, row, col, a.C, o);
+                    if (a.resid_tma && a.out.hi) {
+                        // stage the output planes in place of the residual just consumed (same swizzled slots)
+                        __align__(16) __half oh[16];
+                        __align__(16) __half ol[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { oh[i] = __float2half_rn(o[i]); ol[i] = __float2half_rn(o[i] - __half2float(oh[i])); }
+                        *reinterpret_cast<uint4*>(sh + k0) = reinterpret_cast<const uint4*>(oh)[0];
+                        *reinterpret_cast<uint4*>(sh + k1) = reinterpret_cast<const uint4*>(oh)[1];
+                        *reinterpret_cast<uint4*>(sl + k0) = reinterpret_cast<const uint4*>(ol)[0];
+                        *reinterpret_cast<uint4*>(sl + k1) = reinterpret_cast<const uint4*>(ol)[1];
+                    } else if (row_ok && a.out.hi) {
+                        store_planes(a.out, row, col, a.C, o);
+                    }
                     if (row_ok && a.out_f32) {
                         float* p = a.out_f32 + row * a.ld_f32 + col;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) p[i] = o[i];
+                    }
+                }
+                if (a.resid_tma && a.out.hi) {
+                    // whole tile staged: one thread hands it to the TMA engine (rows past the end are clipped)
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps only
+                    if (warp == 2 && lane == 0) {
+                        for (int i = 0; i < nbox; ++i) {
+                            tma_store_3d(&mapO_hi, rs + i * 16384, rank * half + i * 64, t0s[m], b0s[m]);
+                            tma_store_3d(&mapO_lo, rs + (nbox + i) * 16384, rank * half + i * 64, t0s[m], b0s[m]);
+                        }
+                        tma_store_commit_and_wait();
                     }
                 }
             } else {
@@ -389,6 +489,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         if (ncta > 1 && m + 1 < MT) { cluster_arrive(); cluster_wait(); }
       }
         tc_fence_before();
+        if (r == 0) dbg_time(a.dbg, 13);                                  // t5: stores issued
     }
 
     // ---- teardown: match the cluster barrier phases of the epilogue warps (2*MT-1 of them) ----
@@ -401,9 +502,10 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         cluster_wait();
     }
     __syncthreads();
+    if (threadIdx.x == 0) dbg_time(a.dbg, 14);                            // t6: teardown barrier passed
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc<MT * TC_TMEM_COLS>(tmem_base);
+        if (CG == 2) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<MT * TC_TMEM_COLS>(tmem_base);
     }
 }
 
@@ -485,25 +587,28 @@ int tc_bk() {
     return bk;
 }
 
-int tc_stages_for(int bn, int bk, int mt) {
+int tc_stages_for(int bn, int bk, int mt) {      // bn = weight rows staged per CTA
     const int stage = mt * 2 * TC_BM * bk * 2 + 2 * bn * bk * 2;
     int s = (200 * 1024) / stage;
     return s < 2 ? 2 : (s > TC_MAX_STAGES ? TC_MAX_STAGES : s);
 }
 
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, cudaStream_t s) {
+                       const CUtensorMap& w_lo, const CUtensorMap* io, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, int cg,
+                       cudaStream_t s) {
     static bool attr_set = false;
     const int max_smem = 227 * 1024;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         attr_set = true;
     }
     if (mt == 2 && bk != 32) throw std::runtime_error("conv_ln_tc: paired tiles need the 32-wide slab");
-    const size_t smem = (size_t)a.stages * (mt * 2 * TC_BM * bk * 2 + 2 * a.bn * bk * 2) + TC_AUX_BYTES + 1024;
+    if (cg == 2 && (bk != 64 || mt != 1 || (ncta & 1))) throw std::runtime_error("conv_ln_tc: bad CTA-pair configuration");
+    const size_t smem = (size_t)a.stages * (mt * 2 * TC_BM * bk * 2 + 2 * (a.bn / cg) * bk * 2) + TC_AUX_BYTES + 1024;
     if (smem > (size_t)max_smem) throw std::runtime_error("conv_ln_tc: shared memory budget exceeded");
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)ncta, (unsigned)ctas_y, 1);
@@ -516,10 +621,16 @@ void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    if (a.resid_tma && !io) throw std::runtime_error("conv_ln_tc: residual TMA needs the X / out tensor maps");
+    const CUtensorMap& x_hi = io ? io[0] : a_hi;      // unused placeholders when resid_tma == 0
+    const CUtensorMap& x_lo = io ? io[1] : a_lo;
+    const CUtensorMap& o_hi = io ? io[2] : a_hi;
+    const CUtensorMap& o_lo = io ? io[3] : a_lo;
     cudaError_t e;
-    if (mt == 2)       e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 2>, a_hi, a_lo, w_hi, w_lo, a);
-    else if (bk == 64) e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1>, a_hi, a_lo, w_hi, w_lo, a);
-    else               e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 1>, a_hi, a_lo, w_hi, w_lo, a);
+    if (cg == 2)       e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1, 2>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
+    else if (mt == 2)  e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 2, 1>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
+    else if (bk == 64) e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1, 1>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
+    else               e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 1, 1>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
     if (e != cudaSuccess) throw std::runtime_error(std::string("conv_ln_tc launch: ") + cudaGetErrorString(e));
 }
 

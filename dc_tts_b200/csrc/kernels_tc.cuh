@@ -34,6 +34,7 @@ struct TcArgs {
     // reduction schedule
     int ntaps; int shifts[3]; int kb_per_tap; int stages;   // kb_per_tap in units of the kernel's BK (64 or 32)
     int mcast;                     // 1: the A tile is fetched once per cluster (each CTA loads 128/ncta rows, TMA multicast)
+    int resid_tma;                 // 1 (hc, full sequences): residual tile via TMA into a drained stage, output planes staged there and TMA-stored
     // tiling: 128 rows = TT time rows x TB batch rows
     int TT, TB, tiles_t, ntiles;   // ntiles = batch groups x tiles_t (a CTA takes MT consecutive tiles)
     RowWin win;
@@ -57,7 +58,7 @@ int tc_stages_for(int bn, int bk, int mt);
 int tc_bk();
 // grid = (ncta, tiles); cluster (ncta,1,1)
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
-                       const CUtensorMap& w_lo, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, cudaStream_t s);
+                       const CUtensorMap& w_lo, const CUtensorMap* io /* [4]: X hi, X lo, out hi, out lo ({64,128,1} boxes) or null */, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, int cg, cudaStream_t s);
 
 // ---- tcgen05 attention (kernels_attn_tc.cu) ----
 struct AttnTcArgs {
