@@ -575,13 +575,19 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     static const bool no_rtma = getenv("DCTTS_TC_NO_RESID_TMA") != nullptr;
     CUtensorMap io[4];
     a.resid_tma = 0;
-    if (!no_rtma && p.mode == 1 && cg == 1 && mt == 1 && !win.jptr && TT == 128 && TB == 1 && out.hi &&
+    a.out_tma = 0;
+    if (!no_rtma && p.mode == 1 && cg == 1 && mt == 1 && TT == 128 && TB == 1 &&
         2 * a.half * 128 * 2 <= 2 * 128 * bk * 2 + 2 * a.bn * bk * 2) {
         a.resid_tma = 1;
+        // TMA stores only on full sequences: in the decode window the tile starts at a negative time coordinate
+        // (measured: the launch traps), and there the few output rows are cheap to store directly
+        a.out_tma = (out.hi && !win.jptr) ? 1 : 0;
         tc_make_act_map(&io[0], X.hi, l.cin, X.ld, win.L, win.B, 128, 1, 64);
         tc_make_act_map(&io[1], X.lo, l.cin, X.ld, win.L, win.B, 128, 1, 64);
-        tc_make_act_map(&io[2], out.hi, l.cout, out.ld, win.L, win.B, 128, 1, 64);
-        tc_make_act_map(&io[3], out.lo, l.cout, out.ld, win.L, win.B, 128, 1, 64);
+        if (a.out_tma) {
+            tc_make_act_map(&io[2], out.hi, l.cout, out.ld, win.L, win.B, 128, 1, 64);
+            tc_make_act_map(&io[3], out.lo, l.cout, out.ld, win.L, win.B, 128, 1, 64);
+        } else { io[2] = io[0]; io[3] = io[1]; }
     }
     launch_conv_ln_tc(mAh, mAl, mWh, mWl, a.resid_tma ? io : nullptr, a, p.ncta, (tiles + mt * cg - 1) / (mt * cg), bk, mt, cg,
                       lc.s); lc.count();

@@ -404,9 +404,85 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
     }
 }
 
+// Few rows (the decode step): one CTA of 128 threads per row, every thread owns <= 2 channels of
+// each half, so all split-K partial loads of the row are in flight at once (a single warp per row
+// needs nparts x C / 32 loads per lane in several dependent rounds -- it was the longest kernel of
+// the step).  Statistics by two block reductions (mean, then centred second moment).
+__device__ __forceinline__ float block_sum_128(float v, float* sm, int warp, int lane) {
+    v = warp_sum(v);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    const float t = sm[0] + sm[1] + sm[2] + sm[3];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(128) ln_row_cta_kernel(const LnArgs a) {
+    __shared__ float sm[4];
+    pdl_launch_dependents();
+    pdl_wait();
+    const int R = a.win.R, L = a.win.L;
+    const int rix = blockIdx.x;                                  // b * R + r
+    const int t_end = win_t_end(a.win);
+    const int b = rix / R, r = rix - b * R;
+    const int t = t_end - (R - 1) + r;
+    if (t < 0) return;                                           // whole CTA leaves together
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t row = (size_t)b * L + t;
+    const float* y = a.Y + (a.compact ? (size_t)rix : row) * a.ldy;
+    const int C = a.C;                                           // <= 256 on this path
+    const int c0 = tid, c1 = tid + 128;
+    const bool ok0 = c0 < C, ok1 = c1 < C;
+    float v0 = 0.f, v1 = 0.f, w0 = 0.f, w1 = 0.f;                // first half (2 channels), second half (hc)
+#pragma unroll 4
+    for (int p = 0; p < a.nparts; ++p) {
+        const float* yp = y + (size_t)p * a.part_stride;
+        if (ok0) v0 += yp[c0];
+        if (ok1) v1 += yp[c1];
+        if (a.mode == 1) { if (ok0) w0 += yp[C + c0]; if (ok1) w1 += yp[C + c1]; }
+    }
+    const float fC = (float)C;      // divide, never multiply by 1/C: with eps = 1e-12 a constant row must give d == 0 exactly
+    const float mean1 = block_sum_128((ok0 ? v0 : 0.f) + (ok1 ? v1 : 0.f), sm, warp, lane) / fC;
+    float d0 = ok0 ? v0 - mean1 : 0.f, d1 = ok1 ? v1 - mean1 : 0.f;
+    const float inv1 = 1.0f / sqrtf(block_sum_128(d0 * d0 + d1 * d1, sm, warp, lane) / fC + 1e-12f);
+    if (a.mode == 0) {
+        float* o = a.out + row * a.ldo;
+        float* o2 = a.out2 ? a.out2 + row * a.ldo2 : nullptr;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = u ? c1 : c0;
+            if (c < C) {
+                float z = (u ? d1 : d0) * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c);
+                if (a.act == 1) z = fmaxf(z, 0.f);
+                o[c] = z;
+                if (o2) o2[c] = sigmoidf_acc(z);
+            }
+        }
+    } else {
+        const float mean2 = block_sum_128((ok0 ? w0 : 0.f) + (ok1 ? w1 : 0.f), sm, warp, lane) / fC;
+        float e0 = ok0 ? w0 - mean2 : 0.f, e1 = ok1 ? w1 - mean2 : 0.f;
+        const float inv2 = 1.0f / sqrtf(block_sum_128(e0 * e0 + e1 * e1, sm, warp, lane) / fC + 1e-12f);
+        const float* x = a.X + row * a.ldx;
+        float* o = a.out + row * a.ldo;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int c = u ? c1 : c0;
+            if (c < C) {
+                const float h1 = sigmoidf_acc((u ? d1 : d0) * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c));
+                const float h2 = (u ? e1 : e0) * inv2 * __ldg(a.g2 + c) + __ldg(a.b2 + c);
+                o[c] = h1 * h2 + (1.0f - h1) * x[c];
+            }
+        }
+    }
+}
+
 void launch_ln_rows(const LnArgs& a, cudaStream_t s) {
     const int rows = a.win.B * a.win.R;
     if (rows <= 0) return;
+    if (a.C <= 256 && rows <= 1024) {                    // the decode step's blocks
+        launch_kernel(ln_row_cta_kernel, dim3(rows), dim3(128), 0, s, a);
+        return;
+    }
     const int warps_per_cta = rows >= 2048 ? 8 : 2;     // small launches: spread over SMs
     const int threads = warps_per_cta * 32;
     const int grid = (rows + warps_per_cta - 1) / warps_per_cta;

@@ -430,7 +430,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         float x = __half2float(xh[i]) + __half2float(xl[i]);
                         o[i] = h1 * z2 + (1.0f - h1) * x;
                     }
-                    if (a.resid_tma && a.out.hi) {
+                    if (a.out_tma) {
                         // stage the output planes in place of the residual just consumed (same swizzled slots)
                         __align__(16) __half oh[16];
                         __align__(16) __half ol[16];
@@ -449,7 +449,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                         for (int i = 0; i < 16; ++i) p[i] = o[i];
                     }
                 }
-                if (a.resid_tma && a.out.hi) {
+                if (a.out_tma) {
                     // whole tile staged: one thread hands it to the TMA engine (rows past the end are clipped)
                     fence_proxy_async_smem();
                     asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps only

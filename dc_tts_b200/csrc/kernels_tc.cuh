@@ -34,7 +34,8 @@ struct TcArgs {
     // reduction schedule
     int ntaps; int shifts[3]; int kb_per_tap; int stages;   // kb_per_tap in units of the kernel's BK (64 or 32)
     int mcast;                     // 1: the A tile is fetched once per cluster (each CTA loads 128/ncta rows, TMA multicast)
-    int resid_tma;                 // 1 (hc, full sequences): residual tile via TMA into a drained stage, output planes staged there and TMA-stored
+    int resid_tma;                 // 1 (hc): residual tile via TMA into a drained pipeline stage
+    int out_tma;                   // 1 (hc, full sequences, needs resid_tma): output planes staged in that stage and TMA-stored
     // tiling: 128 rows = TT time rows x TB batch rows
     int TT, TB, tiles_t, ntiles;   // ntiles = batch groups x tiles_t (a CTA takes MT consecutive tiles)
     RowWin win;
