@@ -94,6 +94,8 @@ struct dctts_handle_s {
     int device = 0;
     int F = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // device->host copies of finished spectrogram chunks (dctts_synthesize_host)
+    cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
     std::map<std::string, HostParam> staged;
@@ -140,6 +142,7 @@ struct dctts_handle_s {
         for (auto& b : attpl) b.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
+        if (copy_stream) { cudaStreamDestroy(copy_stream); for (auto e : chunk_done) if (e) cudaEventDestroy(e); }
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -1123,10 +1126,27 @@ int dctts_synthesize_host(dctts_handle h, const int32_t* L_host, int32_t B, floa
         cudaStream_t s = h->stream;
         CUDA_CHECK(cudaMemcpyAsync(h->lbuf.p, L_host, (size_t)B * N * sizeof(int), cudaMemcpyHostToDevice, s));
         text2mel_generate(h, h->lbuf.as<int>(), B, T, nullptr, nullptr, nullptr, nullptr, s);
-        Launch lc{h, s};
-        run_chain_full(lc, h->ssrn, h->ybuf.as<float>(), hp.n_mels, B, T, nullptr, h->zbuf.as<float>());
         if (Y_host) CUDA_CHECK(cudaMemcpyAsync(Y_host, h->ybuf.p, (size_t)B * T * hp.n_mels * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaMemcpyAsync(Z_host, h->zbuf.p, zbytes, cudaMemcpyDeviceToHost, s));
+        // SSRN in utterance chunks; the device->host copy of chunk i (copy stream) runs under the SSRN of chunk i+1.
+        // Z is 3.5 MB per utterance: at PCIe rates the copy of a 32-utterance batch is as long as its SSRN.
+        if (!h->copy_stream) {
+            CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+            for (auto& e : h->chunk_done) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const int nchunk = B >= 16 ? 4 : (B >= 4 ? 2 : 1);
+        const size_t zrow = (size_t)T * hp.r * h->F;
+        Launch lc{h, s};
+        for (int c = 0; c < nchunk; ++c) {
+            const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk);
+            if (b1 <= b0) continue;
+            float* zc = h->zbuf.as<float>() + (size_t)b0 * zrow;
+            run_chain_full(lc, h->ssrn, h->ybuf.as<float>() + (size_t)b0 * T * hp.n_mels, hp.n_mels, b1 - b0, T, nullptr, zc);
+            CUDA_CHECK(cudaEventRecord(h->chunk_done[c], s));
+            CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+            CUDA_CHECK(cudaMemcpyAsync(Z_host + (size_t)b0 * zrow, zc, (size_t)(b1 - b0) * zrow * sizeof(float),
+                                       cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
         CUDA_CHECK(cudaStreamSynchronize(s));
     });
 }
