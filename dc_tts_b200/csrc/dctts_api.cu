@@ -534,7 +534,12 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     // CTA pairs (tcgen05 cta_group::2): hc / transposed-conv blocks packed with 128-channel halves, on full
     // sequences.  Ranks (2s, 2s+1) of the cluster share channel slice s (256 channels), take consecutive tiles,
     // each stages half of the slice's weight slab; the accumulator is 512 columns (256 gate + 256 info).
-    static const bool no_cg2 = getenv("DCTTS_TC_NO_CG2") != nullptr;
+    // Two CTAs per SM (default for launches that fill the machine): 32-wide slab, two pipeline stages -> ~105 KB of
+    // shared memory and 256 TMEM columns per CTA, so one tile's epilogue runs under the other tile's main loop
+    // (SSRN at B=32: 5.61 -> 4.66 ms).  DCTTS_TC_NO_OCC2=1 turns it off; DCTTS_TC_CG2=1 selects CTA pairs instead
+    // (cta_group::2 needs all 512 TMEM columns, so the two cannot be combined).
+    static const bool occ2_mode = getenv("DCTTS_TC_NO_OCC2") == nullptr;
+    static const bool no_cg2 = getenv("DCTTS_TC_CG2") == nullptr;
     // Only when the paired grid still fills the machine: pairs halve the CTA count (B=1 SSRN: 1.09 vs 0.74 ms).
     const int cg = (!no_cg2 && p.mode != 0 && p.half == 128 && p.bn == 256 && (p.ncta % 2) == 0 && !win.jptr && TT == 128 &&
                     TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
@@ -543,14 +548,15 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     // Measured no gain (SSRN/HC_11: 1.27 vs 1.26 ms), like TMA multicast and a deeper pipeline.
     static const bool pair = getenv("DCTTS_TC_PAIR") != nullptr;
     const int mt = (cg == 1 && pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
-    const int bk = (mt == 2) ? 32 : (cg == 2 ? 64 : tc_bk());
+    const bool occ2 = occ2_mode && cg == 1 && mt == 1 && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 148;
+    const int bk = (mt == 2 || occ2) ? 32 : (cg == 2 ? 64 : tc_bk());
     a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap * (64 / bk);
     if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
     else {
         const int tot = (l.size - 1) * rate, left = causal ? tot : tot / 2;
         for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
     }
-    a.stages = std::min(tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
+    a.stages = std::min(occ2 ? 2 : tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
     a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.ntiles = tiles; a.win = win;
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
     // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the

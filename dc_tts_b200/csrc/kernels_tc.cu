@@ -32,7 +32,7 @@ constexpr int TC_BM = 128;
 constexpr int TC_THREADS = 192;
 constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_AUX_BYTES = 256 /*barriers*/ + 3 * 512 * 4 /*bias,gamma,beta*/ + 8 * 128 * 16 /*stats*/;
+constexpr int TC_AUX_BYTES = 256 /*barriers*/ + 3 * 512 * 4 /*bias,gamma,beta*/ + 128 * 16 /*this CTA's LN partials*/;
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
@@ -121,7 +121,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     float* s_bias = reinterpret_cast<float*>(aux + 256);
     float* s_gam = s_bias + 512;
     float* s_bet = s_gam + 512;
-    float4* s_part = reinterpret_cast<float4*>(s_bet + 512);            // [8 slices][128 rows]
+    float4* s_part = reinterpret_cast<float4*>(s_bet + 512);            // [128 rows]: this CTA's partial (sum, M2) x 2 halves, read by its peers
 
     pdl_wait();                       // upstream grid complete, its writes visible
     // ---- tile coordinates (MT tiles per CTA; a tile index past the end loads zeros and stores nothing) ----
@@ -339,18 +339,26 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         // combine over the cluster
         float mean1, rstd1, mean2 = 0.f, rstd2 = 0.f;
         if (ncta > 1) {
-            const uint32_t my_slot = smem_u32(&s_part[rank * 128 + r]);
-            for (int p = 0; p < nslices; ++p) st_cluster_f4(mapa(my_slot, (uint32_t)(p * CG + peer)), s1, q1, s2, q2);
-            if (r == 0) { dbg_mark(a.dbg, 6, 1); dbg_time(a.dbg, 11); }   // t3: sweeps 1+2 done, partials published
+            // each CTA publishes its partials in its OWN shared memory; after the cluster barrier every CTA reads
+            // the slices' partials through distributed shared memory (2 KB per CTA instead of a 16 KB mailbox)
+            s_part[r] = make_float4(s1, q1, s2, q2);
+            if (r == 0) { dbg_mark(a.dbg, 6, 1); dbg_time(a.dbg, 11); }   // t3: statistics sweep done, partials published
             cluster_arrive();                                              // phase 2: partials published
             cluster_wait();
             if (r == 0) { dbg_mark(a.dbg, 7, 1); dbg_time(a.dbg, 12); }   // t4: cluster barrier passed
+            const uint32_t my_slot = smem_u32(&s_part[r]);
+            float4 pv[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) pv[p] = (p < nslices) ? ld_cluster_f4(mapa(my_slot, (uint32_t)(p * CG + peer))) : make_float4(0.f, 0.f, 0.f, 0.f);
             float S1 = 0.f, S2 = 0.f;
-            for (int p = 0; p < nslices; ++p) { float4 v = s_part[p * 128 + r]; S1 += v.x; S2 += v.z; }
+#pragma unroll
+            for (int p = 0; p < 8; ++p) if (p < nslices) { S1 += pv[p].x; S2 += pv[p].z; }
             mean1 = S1 / (float)a.C; mean2 = S2 / (float)a.C;
             float M1 = 0.f, M2 = 0.f;
-            for (int p = 0; p < nslices; ++p) {
-                float4 v = s_part[p * 128 + r];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                if (p >= nslices) continue;
+                const float4 v = pv[p];
                 const int np = (a.mode == 0) ? min(max(a.C - p * bn, 0), bn) : half;
                 if (np > 0) { float d = v.x / (float)np - mean1; M1 += v.y + (float)np * d * d; }
                 if (a.mode != 0) { float d = v.z / (float)half - mean2; M2 += v.w + (float)half * d * d; }
