@@ -260,7 +260,7 @@ void pack_tc(H* h, LayerDev& l, const std::vector<float>& W /* [size][cin][ldw] 
         p.bn = roundup((l.cout + p.ncta - 1) / p.ncta, 16); p.half = p.bn;
     } else {
         p.mode = (l.kind == K_HC) ? 1 : 2; p.ntaps = (l.kind == K_HC) ? l.size : 2;
-        p.half = (l.cout <= 256) ? 64 : 128; p.bn = 2 * p.half; p.ncta = l.cout / p.half;
+        p.half = (l.cout <= 256) ? 32 : 128; p.bn = 2 * p.half; p.ncta = l.cout / p.half;   // decode nets: 8 narrow CTAs per tile
         if (l.cout % p.half) return;
     }
     if (p.ncta > 8) return;
@@ -556,7 +556,8 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
         const int tot = (l.size - 1) * rate, left = causal ? tot : tot / 2;
         for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
     }
-    a.stages = std::min(occ2 ? 2 : tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
+    // decode-window launches: two stages keep the CTA under half an SM's shared memory, so two of them co-reside
+    a.stages = std::min((occ2 || win.jptr) ? 2 : tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
     a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.ntiles = tiles; a.win = win;
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
     // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the
@@ -585,7 +586,7 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     CUtensorMap io[4];
     a.resid_tma = 0;
     a.out_tma = 0;
-    if (!no_rtma && p.mode == 1 && cg == 1 && mt == 1 && TT == 128 && TB == 1 &&
+    if (!no_rtma && p.mode == 1 && cg == 1 && mt == 1 && TT == 128 && TB == 1 && (a.half % 64) == 0 &&
         2 * a.half * 128 * 2 <= 2 * 128 * bk * 2 + 2 * a.bn * bk * 2) {
         a.resid_tma = 1;
         // TMA stores only on full sequences: in the decode window the tile starts at a negative time coordinate

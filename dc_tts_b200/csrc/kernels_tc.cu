@@ -324,14 +324,15 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
             for (int c = 0; c < half; c += 64) {
                 float v[2][32];
                 tmem_ld32_nowait(taddr + half + c, v[0]);
-                tmem_ld32_nowait(taddr + half + c + 32, v[1]);
+                if (c + 32 < half) tmem_ld32_nowait(taddr + half + c + 32, v[1]);
                 tmem_ld_wait();
                 if (c == 0) piv = fmaf(v[0][0], inv_s, s_bias[half]);
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
-                        const float d = fmaf(v[h][i], inv_s, s_bias[half + c + h * 32 + i]) - piv; S += d; Q = fmaf(d, d, Q);
+                        const int cc = c + h * 32 + i;
+                        if (cc < half) { const float d = fmaf(v[h][i], inv_s, s_bias[half + cc]) - piv; S += d; Q = fmaf(d, d, Q); }
                     }
             }
             s2 = piv * (float)half + S; m2 = s2 / (float)half; q2 = fmaxf(Q - S * S / (float)half, 0.f);
