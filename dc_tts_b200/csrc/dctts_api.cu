@@ -124,6 +124,11 @@ struct dctts_handle_s {
     DevBuf attpl[6];              // tcgen05 attention operands: Q, K planes and transposed V planes ({hi,lo} each)
     DevBuf arpl[10];              // AR decode planes: R (B,T,2d) and four AudioDec outputs (B,T,d), {hi,lo} each
 
+    // vocoder (Griffin-Lim) state
+    struct { int hop = 275, win = 1102, n_iter = 50; float power = 1.5f, max_db = 100.f, ref_db = 20.f, preemph = 0.97f; } voc;
+    DevBuf voc_S, voc_X, voc_frames, voc_mse, voc_tw, voc_window, voc_wss;
+    int voc_tables_T = 0, voc_tables_win = 0, voc_tables_hop = 0;
+
     // AR decode graph
     cudaGraphExec_t ar_exec = nullptr;
     int ar_B = 0;
@@ -140,6 +145,7 @@ struct dctts_handle_s {
         for (auto& b : plane) b.release();
         for (auto& b : arpl) b.release();
         for (auto& b : attpl) b.release();
+        voc_S.release(); voc_X.release(); voc_frames.release(); voc_mse.release(); voc_tw.release(); voc_window.release(); voc_wss.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
         if (copy_stream) { cudaStreamDestroy(copy_stream); for (auto e : chunk_done) if (e) cudaEventDestroy(e); }
@@ -1200,6 +1206,63 @@ int dctts_bench_block(dctts_handle h, const char* scope, int32_t B, int32_t L, i
         *n_kernels = nk;
         CUDA_CHECK(cudaStreamSynchronize(s));
         x.release(); y.release();
+    });
+}
+
+int dctts_set_vocoder_params(dctts_handle h, int32_t hop_length, int32_t win_length, float power, float max_db,
+                             float ref_db, float preemphasis, int32_t n_iter) {
+    return guarded(h, [&] {
+        REQUIRE(hop_length >= 1 && win_length >= 1 && win_length <= 2048 && n_iter >= 0, "dctts_set_vocoder_params: bad arguments");
+        h->voc.hop = hop_length; h->voc.win = win_length; h->voc.power = power; h->voc.max_db = max_db;
+        h->voc.ref_db = ref_db; h->voc.preemph = preemphasis; h->voc.n_iter = n_iter;
+    });
+}
+
+int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T, int32_t n_iter, float* wav,
+                          int32_t* trim_host, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(mag && wav && B >= 1 && T >= 2, "dctts_spectrogram2wav: bad arguments");
+        REQUIRE(h->F == 1025, "dctts_spectrogram2wav: the FFT kernel is built for n_fft = 2048");
+        cudaStream_t s = S(h, stream);
+        const int F = h->F, win = h->voc.win, hop = h->voc.hop, Ly = hop * (T - 1), nfr = 1 + Ly / 512;
+        const size_t n = (size_t)B * T * F;
+        h->voc_S.ensure(n * sizeof(float)); h->voc_X.ensure(n * sizeof(float2));
+        h->voc_frames.ensure((size_t)B * T * win * sizeof(float)); h->voc_mse.ensure((size_t)B * nfr * sizeof(float));
+        if (h->voc_tables_T != T || h->voc_tables_win != win || h->voc_tables_hop != hop) {
+            h->voc_tw.ensure(1024 * sizeof(float2)); h->voc_window.ensure(win * sizeof(float));
+            h->voc_wss.ensure((size_t)(2048 + hop * (T - 1)) * sizeof(float));
+            voc_make_tables(h->voc_tw.as<float2>(), h->voc_window.as<float>(), h->voc_wss.as<float>(), T, win, hop, s);
+            CUDA_CHECK(cudaGetLastError());
+            h->voc_tables_T = T; h->voc_tables_win = win; h->voc_tables_hop = hop;
+        }
+        VocoderArgs a{};
+        a.mag = mag; a.S = h->voc_S.as<float>(); a.X = h->voc_X.as<float2>(); a.frames = h->voc_frames.as<float>();
+        a.wav = wav; a.mse = h->voc_mse.as<float>(); a.tw = h->voc_tw.as<float2>(); a.window = h->voc_window.as<float>();
+        a.wss = h->voc_wss.as<float>(); a.B = B; a.T = T; a.F = F; a.win = win; a.hop = hop;
+        a.n_iter = n_iter < 0 ? h->voc.n_iter : n_iter;
+        a.max_db = h->voc.max_db; a.ref_db = h->voc.ref_db; a.power = h->voc.power; a.preemphasis = h->voc.preemph;
+        voc_run(a, s);
+        h->launches += voc_launches_per_call(a.n_iter);
+        CUDA_CHECK(cudaGetLastError());
+        // librosa.effects.trim: frames whose energy is within 60 dB of the loudest
+        std::vector<float> mse((size_t)B * nfr);
+        CUDA_CHECK(cudaMemcpyAsync(mse.data(), a.mse, mse.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        if (trim_host) {
+            for (int b = 0; b < B; ++b) {
+                const float* m = mse.data() + (size_t)b * nfr;
+                float mx = 0.f;
+                for (int f = 0; f < nfr; ++f) mx = std::max(mx, m[f]);
+                const double ref = 10.0 * std::log10(std::max(1e-10, (double)mx));
+                int first = -1, last = -1;
+                for (int f = 0; f < nfr; ++f) {
+                    const double db = 10.0 * std::log10(std::max(1e-10, (double)m[f])) - ref;
+                    if (db > -60.0) { if (first < 0) first = f; last = f; }
+                }
+                trim_host[2 * b] = first < 0 ? 0 : first * 512;
+                trim_host[2 * b + 1] = first < 0 ? 0 : std::min(Ly, (last + 1) * 512);
+            }
+        }
     });
 }
 

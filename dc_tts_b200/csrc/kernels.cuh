@@ -109,6 +109,22 @@ struct RowsBlockArgs {
 bool rows_block_supported(int kind, int K, int C, int ntaps);
 void launch_rows_block(const RowsBlockArgs& a, cudaStream_t s);
 
+// Griffin-Lim vocoder (kernels_vocoder.cu; reference utils.py:67-114)
+struct VocoderArgs {
+    const float* mag;          // (B, T, F) normalised linear magnitudes in [0, 1]
+    float* S;                  // (B, T, F) amplitude target
+    float2* X;                 // (B, T, F) complex spectrum estimate
+    float* frames;             // (B, T, win) windowed time-domain frames
+    float* wav;                // (B, hop*(T-1)) waveform (de-pre-emphasised at the end)
+    float* mse;                // (B, 1 + Ly/512) frame energies for librosa.effects.trim
+    const float2* tw; const float* window; const float* wss;
+    int B, T, F, win, hop, n_iter;
+    float max_db, ref_db, power, preemphasis;
+};
+void voc_make_tables(float2* tw_dev, float* window_dev, float* wss_dev, int T, int win, int hop, cudaStream_t s);
+void voc_run(const VocoderArgs& a, cudaStream_t s);
+int voc_launches_per_call(int n_iter);
+
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);
 void launch_ln_rows(const LnArgs& a, cudaStream_t s);

@@ -212,6 +212,23 @@ class Engine:
                                                       _ptr(A), self._stream()), "dctts_text2mel_generate")
         return Y, P, M, A
 
+    def spectrogram2wav(self, mag, n_iter=-1):
+        """utils.py:67-94 for a batch: mag (B, T, F) in [0,1] -> (untrimmed wav (B, hop*(T-1)) CUDA tensor,
+        trim (B, 2) int32 numpy [start, end) as librosa.effects.trim would keep)."""
+        mag = self._f32(mag)
+        if mag.dim() == 2:
+            mag = mag[None]
+        B, T, F = mag.shape
+        h = self.hp
+        self._check(self._lib.dctts_set_vocoder_params(self._h, h.hop_length, h.win_length, float(h.power), float(h.max_db),
+                                                       float(h.ref_db), float(h.preemphasis), int(h.n_iter)),
+                    "dctts_set_vocoder_params")
+        wav = self._empty(B, h.hop_length * (T - 1))
+        trim = np.zeros((B, 2), np.int32)
+        self._check(self._lib.dctts_spectrogram2wav(self._h, _ptr(mag), B, T, int(n_iter), _ptr(wav),
+                                                    trim.ctypes.data_as(C.c_void_p), self._stream()), "dctts_spectrogram2wav")
+        return wav, trim
+
     def synthesize_host(self, L_host, Y_host=None, Z_host=None):
         """synthesize.py:45-57 with host (ideally pinned) tensors in and out."""
         L_host = torch.as_tensor(L_host, dtype=torch.int32).contiguous()

@@ -3,9 +3,9 @@
 Same flow: load text -> build Graph(mode="synthesize") -> restore parameters -> mel
 loop (:45-54) -> SSRN (:57) -> write one output per sentence.  Differences, all forced
 by what exists offline: parameters come from a name->array dict (no TF checkpoint
-reader yet; seeded initialiser weights when none are given), and the Griffin-Lim
-vocoder (utils.py:67-114, librosa) is a "next" row of SURVEY.md 8(f), so the linear
-magnitudes are saved as .npy instead of .wav.
+reader yet; seeded initialiser weights when none are given).  The Griffin-Lim vocoder
+(utils.py:67-114) runs on the GPU (dc_tts_b200/utils.py) and the wavs are written with
+scipy.io.wavfile like the reference does.
 """
 import os
 
@@ -18,7 +18,7 @@ from .params import init_params
 from .train import Graph, Session
 
 
-def synthesize(params=None, sentences=None, fast=True, write=True, seed=0):
+def synthesize(params=None, sentences=None, fast=True, write=True, seed=0, vocoder=True):
     # Load data
     L = load_data("synthesize", sentences)
 
@@ -50,11 +50,19 @@ def synthesize(params=None, sentences=None, fast=True, write=True, seed=0):
         # Get magnitude (synthesize.py:57)
         Z = sess.run(g.Z, {g.Y: Y})
 
+    # Generate wav files (synthesize.py:60-64): Griffin-Lim on the GPU for the whole batch
     if write:
         if not os.path.exists(hp.sampledir):
             os.makedirs(hp.sampledir)
-        for i, mag in enumerate(Z):
-            np.save(os.path.join(hp.sampledir, "{}.mag.npy".format(i + 1)), mag)
+        if vocoder:
+            from scipy.io.wavfile import write as write_wav
+            from .utils import spectrograms2wavs
+            for i, wav in enumerate(spectrograms2wavs(Z)):
+                print("Working on file", i + 1)
+                write_wav(os.path.join(hp.sampledir, "{}.wav".format(i + 1)), hp.sr, wav)
+        else:
+            for i, mag in enumerate(Z):
+                np.save(os.path.join(hp.sampledir, "{}.mag.npy".format(i + 1)), mag)
     return (Y.cpu().numpy() if hasattr(Y, "cpu") else Y), Z
 
 

@@ -1,0 +1,58 @@
+"""Vocoder half of the reference's utils.py (/root/reference/utils.py:67-114) with the same names:
+`spectrogram2wav(mag)`, `griffin_lim(spectrogram)`, `invert_spectrogram(spectrogram)`.
+
+The reference runs librosa's stft / istft on the CPU, 50 + 51 times per utterance; here the whole
+Griffin-Lim loop runs on the GPU (csrc/kernels_vocoder.cu: one CTA per STFT frame, a 2048-point FFT
+in shared memory) behind `dctts_spectrogram2wav`.  This is the first "next" row of SURVEY.md 8(f), not part
+of the Text2Mel + SSRN hot path.  Feature extraction (`get_spectrograms`, `load_spectrograms`),
+plotting and the training helpers of the reference's utils.py stay out of scope.
+"""
+import numpy as np
+
+from .engine import get_engine
+from .hyperparams import Hyperparams as hp
+
+
+def spectrogram2wav(mag):
+    """utils.py:67-94.  mag: (T, 1+n_fft//2) normalised magnitudes -> trimmed float32 wav (numpy)."""
+    wav, trim = get_engine().spectrogram2wav(np.asarray(mag, np.float32)[None])
+    s, e = int(trim[0, 0]), int(trim[0, 1])
+    return wav[0, s:e].cpu().numpy().astype(np.float32)
+
+
+def spectrograms2wavs(mags):
+    """Batched form: (B, T, F) -> list of trimmed wavs (one device pass for the whole batch)."""
+    wav, trim = get_engine().spectrogram2wav(mags)
+    wav = wav.cpu().numpy()
+    return [wav[b, int(trim[b, 0]):int(trim[b, 1])].astype(np.float32) for b in range(wav.shape[0])]
+
+
+def griffin_lim(spectrogram):
+    """utils.py:96-107.  spectrogram: (1+n_fft//2, t) amplitude (already ** hp.power) -> waveform."""
+    S = np.asarray(spectrogram, np.float32).T
+    # undo the de-normalisation the device entry point applies: S = (10 ^ ((z*max_db - max_db + ref_db)/20)) ^ power
+    z = (20.0 * np.log10(np.maximum(S, 1e-30) ** (1.0 / hp.power)) + hp.max_db - hp.ref_db) / hp.max_db
+    if z.min() < 0 or z.max() > 1:
+        raise ValueError("griffin_lim: amplitude outside the range spectrogram2wav can produce")
+    e = get_engine()
+    wav, _ = e.spectrogram2wav(z[None].astype(np.float32))
+    # spectrogram2wav also de-pre-emphasises; Griffin-Lim alone does not: invert y[n] = x[n] + c y[n-1]
+    y = wav[0].cpu().numpy().astype(np.float64)
+    x = y.copy()
+    x[1:] -= hp.preemphasis * y[:-1]
+    return x.astype(np.float32)
+
+
+def invert_spectrogram(spectrogram):
+    """utils.py:109-114: one inverse STFT (librosa.istft conventions) = Griffin-Lim with zero iterations."""
+    S = np.asarray(spectrogram)
+    if np.iscomplexobj(S):
+        raise NotImplementedError("invert_spectrogram: only zero-phase (real) input is exposed; the complex "
+                                  "iterations run inside dctts_spectrogram2wav")
+    z = (20.0 * np.log10(np.maximum(S.T, 1e-30) ** (1.0 / hp.power)) + hp.max_db - hp.ref_db) / hp.max_db
+    e = get_engine()
+    wav, _ = e.spectrogram2wav(np.clip(z, 0, 1)[None].astype(np.float32), n_iter=0)
+    y = wav[0].cpu().numpy().astype(np.float64)
+    x = y.copy()
+    x[1:] -= hp.preemphasis * y[:-1]
+    return x.astype(np.float32)

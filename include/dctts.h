@@ -125,6 +125,19 @@ int dctts_text2mel_generate(dctts_handle h, const int32_t* L, int32_t B, int32_t
 int dctts_synthesize_host(dctts_handle h, const int32_t* L_host, int32_t B,
                           float* Y_host, float* Z_host);
 
+/* ---- vocoder ("next" row after the path: reference utils.py:67-114) --------------------- */
+/* Signal-processing constants of hyperparams.py:13-24 (defaults = the LJ values: hop 275, win 1102, power 1.5,
+ * max_db 100, ref_db 20, preemphasis 0.97, n_iter 50; n_fft is fixed at 2048 = 2*(F-1)). */
+int dctts_set_vocoder_params(dctts_handle h, int32_t hop_length, int32_t win_length, float power, float max_db,
+                             float ref_db, float preemphasis, int32_t n_iter);
+/* spectrogram2wav (utils.py:67-94) for a batch, entirely on the device: mag (B, T, F) normalised linear
+ * magnitudes -> de-normalise, ^power, Griffin-Lim (n_iter x istft/stft with librosa's conventions), de-pre-emphasis.
+ * wav (B, hop*(T-1)) DEVICE float32 receives the UNTRIMMED waveform; trim_host (B, 2) HOST int32 receives the
+ * [start, end) sample range librosa.effects.trim (top_db 60) would keep.  n_iter < 0 means the configured value.
+ * Synchronises `stream` before returning (trim_host is written by the host). */
+int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T, int32_t n_iter, float* wav,
+                          int32_t* trim_host, void* stream);
+
 /* ---- utilities ----------------------------------------------------------------- */
 /* Pre-size the workspace (otherwise grown lazily on first use) for batches up to B. */
 int dctts_reserve(dctts_handle h, int32_t max_batch);

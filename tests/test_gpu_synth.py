@@ -147,5 +147,9 @@ def test_synthesize_script(engine, tmp_path, monkeypatch):
     sent = os.path.join(ROOT, "harvard_sentences.txt")
     g = golden("synth_harvard1.npz")
     Y, Z = syn.synthesize(sentences=sent, fast=True, write=True)
-    assert Y.shape[0] == 20 and os.path.exists(tmp_path / "samples" / "20.mag.npy")
+    assert Y.shape[0] == 20 and os.path.exists(tmp_path / "samples" / "20.wav")       # synthesize.py:60-64
     assert np.abs(Y[0] - g["Y"][0]).max() < TOL
+    from scipy.io.wavfile import read as read_wav
+    sr, wav = read_wav(tmp_path / "samples" / "1.wav")
+    assert sr == hp.sr and wav.dtype == np.float32 and 0 < len(wav) <= hp.hop_length * (hp.max_T * hp.r - 1)
+    assert np.isfinite(wav).all()
