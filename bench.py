@@ -269,6 +269,16 @@ def run_b200(args, rank, local_rank, world):
         audio_s = T * hp.r * hp.hop_length / float(hp.sr)
         single = {"text2mel_ms": t2m_ms, "ssrn_ms": ssrn_ms, "rtf_x_realtime": audio_s / ((t2m_ms + ssrn_ms) / 1e3)}
         cpu = cpu_reference(passes=args.cpu_passes) if (args.cpu_passes > 0 and world == 1) else None   # rank 0, N = 1 only
+        # ---- next row: Griffin-Lim vocoder on this rank's finished spectrograms (not part of `value`)
+        _, Zv = step() if world == 1 else (None, None)
+        voc = None
+        if Zv is not None:
+            eng.spectrogram2wav(Zv); torch.cuda.synchronize()
+            t0 = time.perf_counter(); wv, _ = eng.spectrogram2wav(Zv); torch.cuda.synchronize(); dtv = time.perf_counter() - t0
+            hbm = 50 * (2 * 8 + 4 + 2 * 4 * 1102 / 1025.0) * B * T * hp.r * F + 51 * 2 * 4 * B * wv.shape[1]   # X r/w, S, frames r/w, wav r/w
+            voc = {"what": "spectrogram2wav (Griffin-Lim, %d iterations, n_fft 2048) for %d utterances" % (hp.n_iter, B),
+                   "ms": dtv * 1e3, "x_realtime": B * wv.shape[1] / float(hp.sr) / dtv,
+                   "hbm_bytes_algorithmic": int(hbm), "hbm_frac_of_measured_peak": hbm / dtv / 1e9 / peaks["hbm_gbs"]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16x2 split operands on tcgen05, fp32 accumulate)" if args.tensor_path else "f32", "data": "synthetic",
@@ -278,6 +288,8 @@ def run_b200(args, rank, local_rank, world):
                         "d2h_bytes_per_step": int((Yh.numel() + Zh.numel()) * 4), "steps": e2e_steps,
                         "api": "dctts_synthesize_host (pinned host buffers)"},
                 "roofline": roof, "single_utterance": single}
+        if voc:
+            line["next_row_vocoder"] = voc
         if cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port",
                                     "sample": cpu["sample"]}
