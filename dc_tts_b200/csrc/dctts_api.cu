@@ -111,6 +111,7 @@ struct dctts_handle_s {
     // workspace (sized for ws_B utterances)
     int ws_B = 0;
     DevBuf scratch, act0, act1;
+    DevBuf tickets;               // arrival counters of the fused GEMM + LN launches (2 ints per 16-row block)
     DevBuf kv;                    // (B, N, 2d) TextEnc output
     DevBuf ybuf;                  // (B, T, n_mels) generated mels
     DevBuf rbuf;                  // (B, T, 2d)
@@ -140,7 +141,7 @@ struct dctts_handle_s {
     ~dctts_handle_s() {
         if (ar_exec) cudaGraphExecDestroy(ar_exec);
         for (void* p : param_allocs) cudaFree(p);
-        scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
+        tickets.release(); scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
         for (auto& b : plane) b.release();
         for (auto& b : arpl) b.release();
@@ -461,12 +462,20 @@ void run_block(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
         c.taps[j].shift = j * rate - left + extra_shift;
     }
     c.win = win; c.Lout = win.L; c.ostride = 1; c.ooff = 0;
-    GemmOut go = launch_conv_gemm(c, lc.s, h->scratch.bytes); lc.count();
-
     LnArgs n{};
     n.Y = c.Y; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2;
     n.X = X; n.ldx = ldx; n.out = out; n.ldo = ldo; n.out2 = out2; n.ldo2 = ldo2;
     n.C = l.cout; n.mode = (l.kind == K_HC) ? 1 : 0; n.act = act; n.win = win;
+    // DCTTS_FUSED_LN=1 (experiment): GEMM and LN epilogue in one launch, the last CTAs of each 16-row block
+    // waiting on an arrival counter.  Parity-green but SLOWER than two graph nodes (B=1: 220 vs 187 us per
+    // decode step, B=32: 339 vs 303): a kernel boundary inside a CUDA graph costs less than the
+    // ticket / spin / L2 round trips that replace it.
+    static const bool fuse_ln = getenv("DCTTS_FUSED_LN") != nullptr;
+    if (fuse_ln && h->tickets.p && conv_gemm_ln_fusable(c, n)) {
+        launch_conv_gemm_ln(c, n, h->tickets.as<int>(), lc.s, h->scratch.bytes); lc.count();
+        return;
+    }
+    GemmOut go = launch_conv_gemm(c, lc.s, h->scratch.bytes); lc.count();
     n.nparts = go.nparts; n.compact = go.compact; n.part_stride = go.part_stride;
     launch_ln_rows(n, lc.s); lc.count();
 }
@@ -961,6 +970,8 @@ int dctts_create(const dctts_hparams* hp, int device, dctts_handle* out) {
         CUDA_CHECK(cudaSetDevice(device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         build_tables(h.get());
+        h->tickets.ensure(64 * sizeof(int));
+        CUDA_CHECK(cudaMemset(h->tickets.p, 0, 64 * sizeof(int)));
         *out = h.release();
         return 0;
     } catch (const std::exception& e) {
@@ -1229,7 +1240,7 @@ int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T
         h->voc_S.ensure(n * sizeof(float)); h->voc_X.ensure(n * sizeof(float2));
         h->voc_frames.ensure((size_t)B * T * win * sizeof(float)); h->voc_mse.ensure((size_t)B * nfr * sizeof(float));
         if (h->voc_tables_T != T || h->voc_tables_win != win || h->voc_tables_hop != hop) {
-            h->voc_tw.ensure(1024 * sizeof(float2)); h->voc_window.ensure(win * sizeof(float));
+            h->voc_tw.ensure(2048 * sizeof(float2)); h->voc_window.ensure(win * sizeof(float));
             h->voc_wss.ensure((size_t)(2048 + hop * (T - 1)) * sizeof(float));
             voc_make_tables(h->voc_tw.as<float2>(), h->voc_window.as<float>(), h->voc_wss.as<float>(), T, win, hop, s);
             CUDA_CHECK(cudaGetLastError());

@@ -128,6 +128,8 @@ int voc_launches_per_call(int n_iter);
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);
 void launch_ln_rows(const LnArgs& a, cudaStream_t s);
+bool conv_gemm_ln_fusable(const ConvArgs& a, const LnArgs& n);
+void launch_conv_gemm_ln(const ConvArgs& a, LnArgs n, int* tickets, cudaStream_t s, size_t scratch_bytes);
 void launch_attention(const AttnArgs& a, cudaStream_t s);
 void launch_embed(const int* ids, const float* table, float* out, int rows, int e, cudaStream_t s);
 // p_cur = p_next; j += 1  (end of an AR step)

@@ -180,8 +180,22 @@ conv_gemm_tiled(const ConvArgs a) {
 // coalesced, by 96 CTAs instead of 8.  Partial sums go to Y[ks][m][n] (compact row index
 // m = b*R + r) and are reduced by the LN epilogue kernel, which needs whole rows anyway.
 // ------------------------------------------------------------------------------------
+__device__ void ln_row_256(const LnArgs& a, int rix, float* sm);
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// FUSED: the LayerNorm / highway epilogue runs in the same launch (one kernel boundary less per block of the
+// decode step).  Every CTA of a 16-row block takes a ticket after its partial sums are visible; the LAST <= 16
+// CTAs of the block in launch order are its finishers: they wait for the ticket count (they are dispatched after
+// the CTAs they wait for, so the wait cannot starve them), then each normalises its share of the rows exactly
+// like ln_row_cta_kernel (partials summed in ascending order).  The last finisher re-arms the counters.
+template <bool FUSED>
 __global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a, const int chunks_per_cta,
-                                                        const size_t part_stride) {
+                                                        const size_t part_stride, const LnArgs ln, int* tickets) {
     pdl_launch_dependents();
     pdl_wait();
     constexpr int BM = 16, BN = 64, BKS = 64, KG = 4, KPG = BKS / KG;
@@ -272,6 +286,31 @@ __global__ void __launch_bounds__(256) conv_gemm_skinny(const ConvArgs a, const 
             yp[((size_t)m * a.ostride + a.ooff) * a.ldy + n] = s;
         }
     }
+    if constexpr (FUSED) {
+        __threadfence();                                   // partial sums visible device-wide before the ticket
+        __syncthreads();
+        const int tot = gridDim.x * gridDim.y, lin = blockIdx.y * gridDim.x + blockIdx.x;
+        const int nfin = min(16, tot), f = lin - (tot - nfin);
+        int* cnt = tickets + 2 * blockIdx.z;
+        if (tid == 0) atomicAdd(cnt, 1);
+        if (f < 0) return;
+        if (tid == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu(cnt) < tot)
+                if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: fail loudly instead of hanging the device
+        }
+        __syncthreads();
+        float* sm = &red[0][0][0];
+        for (int i = f; i < BM; i += nfin) {
+            const int m = m0 + i;
+            if (m >= Mtot) break;
+            ln_row_256(ln, m, sm);
+        }
+        if (tid == 0) {
+            const int old = atomicAdd(cnt + 1, 1);
+            if (old == nfin - 1) { cnt[1] = 0; __threadfence(); atomicExch(cnt, 0); }
+        }
+    }
 }
 
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny) {
@@ -288,7 +327,7 @@ GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes
         const int cpc = (nchunks + max_parts - 1) / max_parts;
         const int nparts = (nchunks + cpc - 1) / cpc;
         dim3 grid((a.ldw + 63) / 64, nparts, (M + 15) / 16);
-        launch_kernel(conv_gemm_skinny, grid, dim3(256), 0, s, a, cpc, part);
+        launch_kernel(conv_gemm_skinny<false>, grid, dim3(256), 0, s, a, cpc, part, LnArgs{}, (int*)nullptr);
         out.nparts = nparts; out.compact = 1; out.part_stride = part;
     } else if (tiles128 >= 120) {
         dim3 grid((a.ldw + 127) / 128, (M + 127) / 128);
@@ -298,6 +337,26 @@ GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes
         launch_kernel(conv_gemm_tiled<64, 64, 16, 4, 4>, grid, dim3(256), 0, s, a);
     }
     return out;
+}
+
+// Decode-step blocks (M <= 256 rows, C <= 256): split-K GEMM and LN epilogue in one launch.
+bool conv_gemm_ln_fusable(const ConvArgs& a, const LnArgs& n) {
+    const int M = a.win.B * a.win.R;
+    return M > 0 && M <= 256 && n.C <= 256 && a.ostride == 1 && a.ooff == 0 && n.out != a.X && n.out2 != a.X;
+}
+
+void launch_conv_gemm_ln(const ConvArgs& a, LnArgs n, int* tickets, cudaStream_t s, size_t scratch_bytes) {
+    const int M = a.win.B * a.win.R;
+    const size_t part = (size_t)M * a.ldy;
+    const int nchunks = a.ntaps * ((a.K + 63) / 64);
+    int max_parts = (int)(scratch_bytes / sizeof(float) / (part ? part : 1));
+    if (max_parts < 1) max_parts = 1;
+    if (max_parts > 64) max_parts = 64;
+    const int cpc = (nchunks + max_parts - 1) / max_parts;
+    const int nparts = (nchunks + cpc - 1) / cpc;
+    n.Y = a.Y; n.ldy = a.ldy; n.nparts = nparts; n.compact = 1; n.part_stride = part;
+    dim3 grid((a.ldw + 63) / 64, nparts, (M + 15) / 16);
+    launch_kernel(conv_gemm_skinny<true>, grid, dim3(256), 0, s, a, cpc, part, n, tickets);
 }
 
 // ------------------------------------------------------------------------------------
@@ -472,6 +531,57 @@ __global__ void __launch_bounds__(128) ln_row_cta_kernel(const LnArgs a) {
                 const float h2 = (u ? e1 : e0) * inv2 * __ldg(a.g2 + c) + __ldg(a.b2 + c);
                 o[c] = h1 * h2 + (1.0f - h1) * x[c];
             }
+        }
+    }
+}
+
+// The same epilogue for one row by a 256-thread CTA (the fused tail of conv_gemm_skinny<true>): one channel of
+// each half per thread, partials read through L2 (they were written by other SMs in this launch).
+__device__ __forceinline__ float block_sum_256(float v, float* sm, int warp, int lane) {
+    v = warp_sum(v);
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    const float t = ((sm[0] + sm[1]) + (sm[2] + sm[3])) + ((sm[4] + sm[5]) + (sm[6] + sm[7]));
+    __syncthreads();
+    return t;
+}
+
+__device__ void ln_row_256(const LnArgs& a, int rix, float* sm) {
+    const int R = a.win.R, L = a.win.L;
+    const int t_end = win_t_end(a.win);
+    const int b = rix / R, r = rix - b * R;
+    const int t = t_end - (R - 1) + r;
+    if (t < 0) return;                                           // uniform over the CTA
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t row = (size_t)b * L + t;
+    const float* y = a.Y + (a.compact ? (size_t)rix : row) * a.ldy;
+    const int C = a.C, c = tid;
+    const bool ok = c < C;
+    float v = 0.f, w = 0.f;
+#pragma unroll 4
+    for (int p = 0; p < a.nparts; ++p) {
+        const float* yp = y + (size_t)p * a.part_stride;
+        if (ok) { v += __ldcg(yp + c); if (a.mode == 1) w += __ldcg(yp + C + c); }
+    }
+    const float fC = (float)C;
+    const float mean1 = block_sum_256(ok ? v : 0.f, sm, warp, lane) / fC;
+    const float d = ok ? v - mean1 : 0.f;
+    const float inv1 = 1.0f / sqrtf(block_sum_256(d * d, sm, warp, lane) / fC + 1e-12f);
+    if (a.mode == 0) {
+        if (ok) {
+            float z = d * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c);
+            if (a.act == 1) z = fmaxf(z, 0.f);
+            a.out[row * a.ldo + c] = z;
+            if (a.out2) a.out2[row * a.ldo2 + c] = sigmoidf_acc(z);
+        }
+    } else {
+        const float mean2 = block_sum_256(ok ? w : 0.f, sm, warp, lane) / fC;
+        const float e = ok ? w - mean2 : 0.f;
+        const float inv2 = 1.0f / sqrtf(block_sum_256(e * e, sm, warp, lane) / fC + 1e-12f);
+        if (ok) {
+            const float h1 = sigmoidf_acc(d * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c));
+            const float h2 = e * inv2 * __ldg(a.g2 + c) + __ldg(a.b2 + c);
+            a.out[row * a.ldo + c] = h1 * h2 + (1.0f - h1) * a.X[row * a.ldx + c];
         }
     }
 }

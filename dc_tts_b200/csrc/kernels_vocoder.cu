@@ -2,7 +2,8 @@
 // This is the first "next" row of SURVEY.md 8(f): the step right after the synthesis path, serial
 // per-utterance CPU work in the reference (librosa), 51 inverse + 50 forward STFTs per utterance.
 //
-// One CTA per STFT frame; a 2048-point radix-2 FFT lives entirely in shared memory (16 KB), the
+// One CTA per STFT frame; the 2048-point real transform is a 1024-point complex Stockham radix-4 FFT
+// (first and last pass in registers, three through 16 KB of shared memory), the
 // Hann window (1102 non-zero taps, centred in the 2048 frame) and librosa's conventions
 // (center=True reflect padding, division by the summed squared window, n_fft/2 trimmed at both
 // ends) are applied on the fly, so per Griffin-Lim iteration only the (B, T, 1025) complex
@@ -22,31 +23,49 @@ namespace dctts {
 constexpr int VC_N = 2048;
 constexpr int VC_THREADS = 256;
 
-__device__ __forceinline__ int bitrev11(int i) { return (int)(__brev((unsigned)i) >> 21); }
+constexpr int VC_H = VC_N / 2;                      // complex FFT length (real-input packing)
 
-// In-place radix-2 decimation-in-time FFT of s[2048] (input already in bit-reversed order).
-// tw[k] = exp(-2 pi i k / 2048), k < 1024; inverse = conjugated twiddles (no 1/N scaling).
-__device__ __forceinline__ void fft2048(float2* s, const float2* __restrict__ tw, bool inverse) {
-#pragma unroll 1
-    for (int st = 0; st < 11; ++st) {
-        const int half = 1 << st;
-        for (int j = threadIdx.x; j < VC_N / 2; j += VC_THREADS) {
-            const int pos = j & (half - 1);
-            const int i0 = ((j >> st) << (st + 1)) + pos, i1 = i0 + half;
-            float2 w = tw[pos << (10 - st)];
-            if (inverse) w.y = -w.y;
-            const float2 a = s[i0], b = s[i1];
-            const float2 t = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
-            s[i0] = make_float2(a.x + t.x, a.y + t.y);
-            s[i1] = make_float2(a.x - t.x, a.y - t.y);
-        }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// 1024-point complex FFT, Stockham autosort, radix 4, 256 threads, one butterfly per thread per pass.
+// Entry: v[k] = x[tid + 256 k]; exit: v[k] = X[tid + 256 k] (natural order, no scaling).  The first
+// pass reads and the last pass writes registers only; the three passes between go through the two
+// 8 KB ping-pong buffers (one __syncthreads each).  tw[k] = exp(-2 pi i k / 2048), k < 2048.
+template <bool INV>
+__device__ __forceinline__ void fft1024(float2 (&v)[4], float2* s0, float2* s1, const float2* __restrict__ tw) {
+    const int tid = threadIdx.x;
+    float2* buf = s0;
+#pragma unroll
+    for (int ls = 0; ls <= 8; ls += 2) {
+        const int str = 1 << ls, q = tid & (str - 1), p = tid >> ls;
+        const float2 a = v[0], b = v[1], c = v[2], d = v[3];
+        const float2 apc = make_float2(a.x + c.x, a.y + c.y), amc = make_float2(a.x - c.x, a.y - c.y);
+        const float2 bpd = make_float2(b.x + d.x, b.y + d.y), bmd = make_float2(b.x - d.x, b.y - d.y);
+        const float2 jb = INV ? make_float2(bmd.y, -bmd.x) : make_float2(-bmd.y, bmd.x);      // (+-i)(b - d), sign folded: y1 = amc - jb
+        float2 y0 = make_float2(apc.x + bpd.x, apc.y + bpd.y);
+        float2 y1 = make_float2(amc.x - jb.x, amc.y - jb.y);
+        float2 y2 = make_float2(apc.x - bpd.x, apc.y - bpd.y);
+        float2 y3 = make_float2(amc.x + jb.x, amc.y + jb.y);
+        if (ls == 8) { v[0] = y0; v[1] = y1; v[2] = y2; v[3] = y3; break; }                   // n = 4: p = 0, unit twiddles
+        const int i1 = 2 * (tid - q);
+        float2 w1 = tw[i1], w2 = tw[2 * i1], w3 = tw[3 * i1];
+        if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+        y1 = cmul(y1, w1); y2 = cmul(y2, w2); y3 = cmul(y3, w3);
+        float2* o = buf + q + str * 4 * p;
+        if (ls == 0) {
+            reinterpret_cast<float4*>(o)[0] = make_float4(y0.x, y0.y, y1.x, y1.y);
+            reinterpret_cast<float4*>(o)[1] = make_float4(y2.x, y2.y, y3.x, y3.y);
+        } else { o[0] = y0; o[str] = y1; o[2 * str] = y2; o[3 * str] = y3; }
         __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = buf[tid + 256 * k];
+        buf = (buf == s0) ? s1 : s0;
     }
 }
 
 __global__ void voc_twiddle_kernel(float2* tw) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < VC_N / 2) {
+    if (k < VC_N) {
         double s, c;
         sincospi(-2.0 * (double)k / (double)VC_N, &s, &c);
         tw[k] = make_float2((float)c, (float)s);
@@ -65,23 +84,36 @@ __global__ void voc_prepare_kernel(const float* __restrict__ mag, float* __restr
 }
 
 // librosa.core.istft, one frame: grid (T, B).  fr: (B, T, win) windowed time-domain frames.
+// The 2048-point Hermitian inverse is a 1024-point complex one: with E/O the spectra of the even/odd
+// samples, X[k] = E[k] + W^k O[k], X[k+1024] = conj(X[1024-k]) = E[k] - W^k O[k]; z = IFFT(E + i O)
+// carries x[2n] in its real and x[2n+1] in its imaginary part.
 __global__ void __launch_bounds__(VC_THREADS) voc_istft_kernel(const float2* __restrict__ X, float* __restrict__ fr,
                                                                const float2* __restrict__ tw, const float* __restrict__ window,
                                                                int T, int F, int win, int lpad) {
-    __shared__ float2 s[VC_N];
-    const int t = blockIdx.x, b = blockIdx.y;
+    __shared__ __align__(16) float2 s0[VC_H];
+    __shared__ __align__(16) float2 s1[VC_H];
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const float2* x = X + ((size_t)b * T + t) * F;
-    for (int k = threadIdx.x; k < VC_N; k += VC_THREADS) {
-        float2 v;
-        if (k < F) v = x[k];
-        else { v = x[VC_N - k]; v.y = -v.y; }            // spec[-2:0:-1].conj()
-        s[bitrev11(k)] = v;
+    float2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int kk = tid + 256 * k;
+        float2 xk = x[kk], xc = x[VC_H - kk];
+        if (kk == 0) { xk.y = 0.f; xc.y = 0.f; }        // ifft(...).real drops the imaginary parts of bins 0 and n_fft/2
+        xc.y = -xc.y;
+        const float2 e = make_float2(xk.x + xc.x, xk.y + xc.y), d = make_float2(xk.x - xc.x, xk.y - xc.y);
+        float2 w = tw[kk]; w.y = -w.y;
+        const float2 o = cmul(d, w);
+        v[k] = make_float2(e.x - o.y, e.y + o.x);        // E + i O (the halves are folded into the 1/2048 below)
     }
-    __syncthreads();
-    fft2048(s, tw, true);
+    fft1024<true>(v, s0, s1, tw);
     float* o = fr + ((size_t)b * T + t) * win;
-    for (int n = threadIdx.x; n < win; n += VC_THREADS)
-        o[n] = s[lpad + n].x * (1.0f / VC_N) * window[n];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int m = 2 * (tid + 256 * k) - lpad;        // frame sample 2n -> position in the window
+        if (m >= 0 && m < win) o[m] = v[k].x * (1.0f / VC_N) * window[m];
+        if (m + 1 >= 0 && m + 1 < win) o[m + 1] = v[k].y * (1.0f / VC_N) * window[m + 1];
+    }
 }
 
 // overlap-add + window sum-square normalisation + centre trim: y (B, Ly), Ly = hop*(T-1)
@@ -102,33 +134,48 @@ __global__ void voc_ola_kernel(const float* __restrict__ fr, const float* __rest
 }
 
 // librosa.core.stft of the current estimate, one frame, fused with the Griffin-Lim phase update
-// (utils.py:101-104): X = S * est / max(1e-8, |est|).  grid (T, B).
+// (utils.py:101-104): X = S * est / max(1e-8, |est|).  grid (T, B).  Real input packed as
+// z[n] = x[2n] + i x[2n+1]; est[k] = (Z[k] + conj Z[1024-k]) / 2 - i W^k (Z[k] - conj Z[1024-k]) / 2.
 __global__ void __launch_bounds__(VC_THREADS) voc_stft_phase_kernel(const float* __restrict__ y, const float* __restrict__ S,
                                                                     float2* __restrict__ X, const float2* __restrict__ tw,
                                                                     const float* __restrict__ window, int T, int F, int win,
                                                                     int lpad, int hop, int Ly) {
-    __shared__ float2 s[VC_N];
-    const int t = blockIdx.x, b = blockIdx.y;
+    __shared__ __align__(16) float2 s0[VC_H];
+    __shared__ __align__(16) float2 s1[VC_H];
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const float* yb = y + (size_t)b * Ly;
-    for (int n = threadIdx.x; n < VC_N; n += VC_THREADS) {
-        float v = 0.f;
-        if (n >= lpad && n < lpad + win) {
-            int u = t * hop + n - VC_N / 2;               // np.pad(y, n_fft//2, mode='reflect')
-            if (u < 0) u = -u;
-            if (u >= Ly) u = 2 * (Ly - 1) - u;
-            v = yb[u] * window[n - lpad];
-        }
-        s[bitrev11(n)] = make_float2(v, 0.f);
-    }
+    auto sample = [&](int n) -> float {
+        const int m = n - lpad;
+        if (m < 0 || m >= win) return 0.f;
+        int u = t * hop + n - VC_N / 2;                   // np.pad(y, n_fft//2, mode='reflect')
+        if (u < 0) u = -u;
+        if (u >= Ly) u = 2 * (Ly - 1) - u;
+        return yb[u] * window[m];
+    };
+    float2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int n = 2 * (tid + 256 * k); v[k] = make_float2(sample(n), sample(n + 1)); }
+    fft1024<false>(v, s0, s1, tw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s0[tid + 256 * k] = v[k];          // s0 was last read before the final barrier of the FFT
     __syncthreads();
-    fft2048(s, tw, false);
     const float* Sb = S + ((size_t)b * T + t) * F;
     float2* x = X + ((size_t)b * T + t) * F;
-    for (int k = threadIdx.x; k < F; k += VC_THREADS) {
-        const float2 e = s[k];
+    auto emit = [&](int kk, float2 e) {
         const float mag = fmaxf(1e-8f, sqrtf(e.x * e.x + e.y * e.y));
-        const float a = Sb[k];
-        x[k] = make_float2(a * (e.x / mag), a * (e.y / mag));
+        const float a = Sb[kk];
+        x[kk] = make_float2(a * (e.x / mag), a * (e.y / mag));
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int kk = tid + 256 * k;
+        const float2 zk = v[k];
+        float2 zc = s0[(VC_H - kk) & (VC_H - 1)]; zc.y = -zc.y;
+        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+        const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+        const float2 o = cmul(make_float2(d.y, -d.x), tw[kk]);     // -i d W^k
+        emit(kk, make_float2(e.x + o.x, e.y + o.y));
+        if (kk == 0) emit(VC_H, make_float2(zk.x - zk.y, 0.f));    // bin n_fft/2: E[0] - O[0]
     }
 }
 
@@ -167,7 +214,7 @@ __global__ void __launch_bounds__(256) voc_frame_mse_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------- host
 void voc_make_tables(float2* tw_dev, float* window_dev, float* wss_dev, int T, int win, int hop, cudaStream_t s) {
-    voc_twiddle_kernel<<<(VC_N / 2 + 255) / 256, 256, 0, s>>>(tw_dev);
+    voc_twiddle_kernel<<<(VC_N + 255) / 256, 256, 0, s>>>(tw_dev);
     // periodic Hann of win taps (scipy get_window('hann', win, fftbins=True)) and librosa's window_sumsquare,
     // accumulated in float32 in frame order like the reference
     std::vector<float> w(win);
