@@ -127,7 +127,7 @@ struct dctts_handle_s {
 
     // vocoder (Griffin-Lim) state
     struct { int hop = 275, win = 1102, n_iter = 50; float power = 1.5f, max_db = 100.f, ref_db = 20.f, preemph = 0.97f; } voc;
-    DevBuf voc_S, voc_X, voc_frames, voc_mse, voc_tw, voc_window, voc_wss;
+    DevBuf voc_S, voc_X, voc_frames, voc_mse, voc_tw, voc_window, voc_wss, voc_deemph;
     int voc_tables_T = 0, voc_tables_win = 0, voc_tables_hop = 0;
 
     // AR decode graph
@@ -146,7 +146,7 @@ struct dctts_handle_s {
         for (auto& b : plane) b.release();
         for (auto& b : arpl) b.release();
         for (auto& b : attpl) b.release();
-        voc_S.release(); voc_X.release(); voc_frames.release(); voc_mse.release(); voc_tw.release(); voc_window.release(); voc_wss.release();
+        voc_S.release(); voc_X.release(); voc_frames.release(); voc_mse.release(); voc_tw.release(); voc_window.release(); voc_wss.release(); voc_deemph.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
         if (copy_stream) { cudaStreamDestroy(copy_stream); for (auto e : chunk_done) if (e) cudaEventDestroy(e); }
@@ -1239,6 +1239,7 @@ int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T
         const size_t n = (size_t)B * T * F;
         h->voc_S.ensure(n * sizeof(float)); h->voc_X.ensure(n * sizeof(float2));
         h->voc_frames.ensure((size_t)B * T * win * sizeof(float)); h->voc_mse.ensure((size_t)B * nfr * sizeof(float));
+        h->voc_deemph.ensure(voc_deemph_scratch_bytes(B, T, hop));
         if (h->voc_tables_T != T || h->voc_tables_win != win || h->voc_tables_hop != hop) {
             h->voc_tw.ensure(2048 * sizeof(float2)); h->voc_window.ensure(win * sizeof(float));
             h->voc_wss.ensure((size_t)(2048 + hop * (T - 1)) * sizeof(float));
@@ -1249,7 +1250,7 @@ int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T
         VocoderArgs a{};
         a.mag = mag; a.S = h->voc_S.as<float>(); a.X = h->voc_X.as<float2>(); a.frames = h->voc_frames.as<float>();
         a.wav = wav; a.mse = h->voc_mse.as<float>(); a.tw = h->voc_tw.as<float2>(); a.window = h->voc_window.as<float>();
-        a.wss = h->voc_wss.as<float>(); a.B = B; a.T = T; a.F = F; a.win = win; a.hop = hop;
+        a.wss = h->voc_wss.as<float>(); a.deemph = h->voc_deemph.as<double>(); a.B = B; a.T = T; a.F = F; a.win = win; a.hop = hop;
         a.n_iter = n_iter < 0 ? h->voc.n_iter : n_iter;
         a.max_db = h->voc.max_db; a.ref_db = h->voc.ref_db; a.power = h->voc.power; a.preemphasis = h->voc.preemph;
         voc_run(a, s);

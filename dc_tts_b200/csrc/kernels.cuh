@@ -118,12 +118,14 @@ struct VocoderArgs {
     float* wav;                // (B, hop*(T-1)) waveform (de-pre-emphasised at the end)
     float* mse;                // (B, 1 + Ly/512) frame energies for librosa.effects.trim
     const float2* tw; const float* window; const float* wss;
+    double* deemph;                // (B, chunks) float64 states of the de-pre-emphasis recurrence
     int B, T, F, win, hop, n_iter;
     float max_db, ref_db, power, preemphasis;
 };
 void voc_make_tables(float2* tw_dev, float* window_dev, float* wss_dev, int T, int win, int hop, cudaStream_t s);
 void voc_run(const VocoderArgs& a, cudaStream_t s);
 int voc_launches_per_call(int n_iter);
+size_t voc_deemph_scratch_bytes(int B, int T, int hop);
 
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);
