@@ -554,17 +554,23 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     // (SSRN at B=32: 5.61 -> 4.66 ms).  DCTTS_TC_NO_OCC2=1 turns it off; DCTTS_TC_CG2=1 selects CTA pairs instead
     // (cta_group::2 needs all 512 TMEM columns, so the two cannot be combined).
     static const bool occ2_mode = getenv("DCTTS_TC_NO_OCC2") == nullptr;
-    static const bool no_cg2 = getenv("DCTTS_TC_CG2") == nullptr;
+    // DCTTS_TC_CG2: 1 = wide pairs (N = 512 per pair, all of TMEM, one CTA per SM), 2 = narrow pairs (N = 256 per pair,
+    // 256 TMEM columns per CTA, so two CTAs per SM still overlap epilogue and main loop; the cluster doubles to
+    // 2 x slices CTAs, 16 for the C = 1024 blocks)
+    static const int cg2_mode = getenv("DCTTS_TC_CG2") ? atoi(getenv("DCTTS_TC_CG2")) : 0;
+    const bool pairable = p.mode != 0 && p.half == 128 && p.bn == 256 && !win.jptr && TT == 128 && TB == 1;
     // Only when the paired grid still fills the machine: pairs halve the CTA count (B=1 SSRN: 1.09 vs 0.74 ms).
-    const int cg = (!no_cg2 && p.mode != 0 && p.half == 128 && p.bn == 256 && (p.ncta % 2) == 0 && !win.jptr && TT == 128 &&
-                    TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
-    if (cg == 2) { a.bn = 512; a.half = 256; }
+    const bool wide_pairs = cg2_mode == 1 && pairable && (p.ncta % 2) == 0 && tiles * p.ncta >= 4 * 148;
+    const bool narrow_pairs = cg2_mode == 2 && pairable && 2 * p.ncta <= 16 && tiles * p.ncta >= 2 * 148;
+    const int cg = (wide_pairs || narrow_pairs) ? 2 : 1;
+    if (wide_pairs) { a.bn = 512; a.half = 256; }
+    const int cluster = narrow_pairs ? 2 * p.ncta : p.ncta;
     // DCTTS_TC_PAIR=1: two 128-row tiles per CTA sharing one weight slab (a third fewer bytes per MMA).
     // Measured no gain (SSRN/HC_11: 1.27 vs 1.26 ms), like TMA multicast and a deeper pipeline.
     static const bool pair = getenv("DCTTS_TC_PAIR") != nullptr;
     const int mt = (cg == 1 && pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
     const bool occ2 = occ2_mode && cg == 1 && mt == 1 && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 148;
-    const int bk = (mt == 2 || occ2) ? 32 : (cg == 2 ? 64 : tc_bk());
+    const int bk = (mt == 2 || occ2 || narrow_pairs) ? 32 : (cg == 2 ? 64 : tc_bk());
     a.ntaps = p.ntaps; a.kb_per_tap = p.kb_per_tap * (64 / bk);
     if (p.mode == 2) { a.shifts[0] = 0; a.shifts[1] = -1; }
     else {
@@ -572,7 +578,7 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
         for (int j = 0; j < l.size; ++j) a.shifts[j] = j * rate - left + extra_shift;
     }
     // decode-window launches: two stages keep the CTA under half an SM's shared memory, so two of them co-reside
-    a.stages = std::min((occ2 || win.jptr) ? 2 : tc_stages_for(p.bn, bk, mt), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
+    a.stages = std::min(narrow_pairs ? 3 : ((occ2 || win.jptr) ? 2 : tc_stages_for(p.bn, bk, mt)), std::max(1, a.ntaps * a.kb_per_tap));   // p.bn = weight rows staged per CTA
     a.TT = TT; a.TB = TB; a.tiles_t = tiles_t; a.ntiles = tiles; a.win = win;
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
     // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the
@@ -594,7 +600,8 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
                 a.mode, p.ncta, a.bn, a.half, a.stages, a.ntaps * a.kb_per_tap, tiles, TT, TB, win.L, win.B);
     }
     CUtensorMap mWh = p.mWhi, mWl = p.mWlo;
-    if (bk != tc_bk()) { tc_make_w_map(&mWh, p.Whi, p.Ktot, p.nrows, p.bn, bk); tc_make_w_map(&mWl, p.Wlo, p.Ktot, p.nrows, p.bn, bk); }
+    if (cg == 2) { tc_make_w_map(&mWh, p.Whi, p.Ktot, p.nrows, a.half / 2, bk); tc_make_w_map(&mWl, p.Wlo, p.Ktot, p.nrows, a.half / 2, bk); }   // gate / info boxes
+    else if (bk != tc_bk()) { tc_make_w_map(&mWh, p.Whi, p.Ktot, p.nrows, p.bn, bk); tc_make_w_map(&mWl, p.Wlo, p.Ktot, p.nrows, p.bn, bk); }
     // hc on full sequences: the residual tile comes in by TMA and the output planes leave by TMA (staged in the
     // same drained pipeline stage), instead of row-scattered 32-byte loads / stores from the epilogue threads
     static const bool no_rtma = getenv("DCTTS_TC_NO_RESID_TMA") != nullptr;
@@ -614,7 +621,7 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
             tc_make_act_map(&io[3], out.lo, l.cout, out.ld, win.L, win.B, 128, 1, 64);
         } else { io[2] = io[0]; io[3] = io[1]; }
     }
-    launch_conv_ln_tc(mAh, mAl, mWh, mWl, a.resid_tma ? io : nullptr, a, p.ncta, (tiles + mt * cg - 1) / (mt * cg), bk, mt, cg,
+    launch_conv_ln_tc(mAh, mAl, mWh, mWl, a.resid_tma ? io : nullptr, a, cluster, (tiles + mt * cg - 1) / (mt * cg), bk, mt, cg,
                       lc.s); lc.count();
     if (debug) {
         cudaError_t e = cudaStreamSynchronize(lc.s);

@@ -148,7 +148,10 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         fence_mbar_init();
     }
     if (CG == 2) { cluster_arrive(); cluster_wait(); }      // the pair allocator needs both CTAs up
-    if (warp == 1) { if (CG == 2) tmem_alloc_pair<512>(tmem_ptr_smem); else tmem_alloc<MT * TC_TMEM_COLS>(tmem_ptr_smem); }
+    if (warp == 1) {
+        if (CG == 2) { if (bn > 256) tmem_alloc_pair<512>(tmem_ptr_smem); else tmem_alloc_pair<256>(tmem_ptr_smem); }
+        else tmem_alloc<MT * TC_TMEM_COLS>(tmem_ptr_smem);
+    }
     if (warp >= 2) {
         // epilogue vectors, indexed by accumulator column
         for (int c = threadIdx.x - 64; c < bn; c += 128) {
@@ -205,8 +208,15 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                     }
                 }
                 if (CG == 2) {
-                    tma_load_2d_pair(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, crank * bn_load);
-                    tma_load_2d_pair(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, crank * bn_load);
+                    // this CTA's half/2 gate channels and the matching info channels: two boxes of the slab, which is
+                    // packed in 128-channel halves [gate 128 | info 128] (pack_tc)
+                    const int ch0 = rank * half + peer * (half / 2);
+                    const int g0 = (ch0 / 128) * 256 + (ch0 % 128);
+                    const int wbox_bytes = (half / 2) * SW;
+                    tma_load_2d_pair(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, g0);
+                    tma_load_2d_pair(&mapW_hi, &full_bar[s], st + A_BYTES + wbox_bytes, kb * TC_BK, g0 + 128);
+                    tma_load_2d_pair(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, g0);
+                    tma_load_2d_pair(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane + wbox_bytes, kb * TC_BK, g0 + 128);
                 } else {
                     tma_load_2d(&mapW_hi, &full_bar[s], st + A_BYTES, kb * TC_BK, rank * bn);
                     tma_load_2d(&mapW_lo, &full_bar[s], st + A_BYTES + b_plane, kb * TC_BK, rank * bn);
@@ -230,7 +240,7 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
         __syncwarp();
     } else if (warp == 1 && peer == 0) {
         // =========================== MMA issuer (the pair's leader only) ===========================
-        const uint32_t idesc = (CG == 2) ? umma_idesc_f16(256, 256) : umma_idesc_f16(TC_BM, (uint32_t)bn);
+        const uint32_t idesc = (CG == 2) ? umma_idesc_f16(256, (uint32_t)half) : umma_idesc_f16(TC_BM, (uint32_t)bn);
         const uint16_t pair_mask = (uint16_t)(3u << (crank & ~1));
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % stages;
@@ -242,12 +252,13 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
                 const uint64_t dB_hi = umma_desc_kmajor<SW>(st + A_BYTES);
                 const uint64_t dB_lo = umma_desc_kmajor<SW>(st + A_BYTES + b_plane);
                 if (CG == 2) {
-                    // two N = 256 chunks: rows [0,128) / [128,256) of each CTA's weight tile -> TMEM columns [0,256) / [256,512)
+                    // two N = half chunks: the gate box / the info box of each CTA's weight tile (half/2 rows from each CTA
+                    // of the pair, in channel order) -> TMEM columns [0,half) / [half,2 half)
                     const uint64_t dA_hi = umma_desc_kmajor<SW>(st), dA_lo = umma_desc_kmajor<SW>(st + TC_A_PLANE);
 #pragma unroll
                     for (int ck = 0; ck < 2; ++ck) {
-                        const uint64_t cb = (uint64_t)((ck * 128 * SW) >> 4);
-                        const uint32_t acc = tmem_base + ck * 256;
+                        const uint64_t cb = (uint64_t)((ck * (half / 2) * SW) >> 4);
+                        const uint32_t acc = tmem_base + ck * half;
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k) {
                             const uint64_t adv = (uint64_t)(k * 32 >> 4);
@@ -514,7 +525,8 @@ conv_ln_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_cons
     if (threadIdx.x == 0) dbg_time(a.dbg, 14);                            // t6: teardown barrier passed
     if (warp == 1) {
         tc_fence_after();
-        if (CG == 2) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc<MT * TC_TMEM_COLS>(tmem_base);
+        if (CG == 2) { if (bn > 256) tmem_dealloc_pair<512>(tmem_base); else tmem_dealloc_pair<256>(tmem_base); }
+        else tmem_dealloc<MT * TC_TMEM_COLS>(tmem_base);
     }
 }
 
@@ -612,11 +624,15 @@ void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        // C = 1024 blocks as CTA pairs span 16 CTAs (8 slices x 2): larger than the portable cluster size
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<32, 1, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (e != cudaSuccess) throw std::runtime_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
         attr_set = true;
     }
     if (mt == 2 && bk != 32) throw std::runtime_error("conv_ln_tc: paired tiles need the 32-wide slab");
-    if (cg == 2 && (bk != 64 || mt != 1 || (ncta & 1))) throw std::runtime_error("conv_ln_tc: bad CTA-pair configuration");
+    if (cg == 2 && (mt != 1 || (ncta & 1) || ncta > 16)) throw std::runtime_error("conv_ln_tc: bad CTA-pair configuration");
     const size_t smem = (size_t)a.stages * (mt * 2 * TC_BM * bk * 2 + 2 * (a.bn / cg) * bk * 2) + TC_AUX_BYTES + 1024;
     if (smem > (size_t)max_smem) throw std::runtime_error("conv_ln_tc: shared memory budget exceeded");
     cudaLaunchConfig_t cfg{};
@@ -636,7 +652,8 @@ void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const C
     const CUtensorMap& o_hi = io ? io[2] : a_hi;
     const CUtensorMap& o_lo = io ? io[3] : a_lo;
     cudaError_t e;
-    if (cg == 2)       e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1, 2>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
+    if (cg == 2 && bk == 64) e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1, 2>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
+    else if (cg == 2)  e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 1, 2>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
     else if (mt == 2)  e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 2, 1>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
     else if (bk == 64) e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<64, 1, 1>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
     else               e = cudaLaunchKernelEx(&cfg, conv_ln_tc_kernel<32, 1, 1>, a_hi, a_lo, w_hi, w_lo, x_hi, x_lo, o_hi, o_lo, a);
