@@ -46,6 +46,7 @@ SIGNATURES = {
     "dctts_spectrogram2wav": (C.c_int, [Handle, _p, _i32, _i32, _i32, _p, _p, _p]),
     "dctts_reserve": (C.c_int, [Handle, _i32]),
     "dctts_launch_count": (_i64, [Handle]),
+    "dctts_crc32c": (C.c_uint32, [C.c_uint32, _p, _i64]),
     "dctts_set_tensor_path": (C.c_int, [Handle, _i32]),
     "dctts_malloc": (C.c_int, [Handle, C.POINTER(_p), _i64]),
     "dctts_free": (C.c_int, [Handle, _p]),

@@ -1291,6 +1291,35 @@ int dctts_reserve(dctts_handle h, int32_t max_batch) {
 
 int64_t dctts_launch_count(dctts_handle h) { return h ? h->launches : -1; }
 
+// CRC-32C (polynomial 0x1EDC6F41, reflected 0x82F63B78), slicing-by-8 on the host.
+uint32_t dctts_crc32c(uint32_t crc, const void* data, int64_t n) {
+    static uint32_t T[8][256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+            T[0][i] = c;
+        }
+        for (uint32_t i = 0; i < 256; ++i)
+            for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xffu];
+        init = true;
+    }
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint32_t c = ~crc;
+    while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 7u)) { c = (c >> 8) ^ T[0][(c ^ *p++) & 0xffu]; --n; }
+    while (n >= 8) {
+        uint64_t v;
+        memcpy(&v, p, 8);
+        const uint32_t lo = (uint32_t)v ^ c, hi = (uint32_t)(v >> 32);
+        c = T[7][lo & 0xffu] ^ T[6][(lo >> 8) & 0xffu] ^ T[5][(lo >> 16) & 0xffu] ^ T[4][lo >> 24] ^
+            T[3][hi & 0xffu] ^ T[2][(hi >> 8) & 0xffu] ^ T[1][(hi >> 16) & 0xffu] ^ T[0][hi >> 24];
+        p += 8; n -= 8;
+    }
+    while (n-- > 0) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xffu];
+    return ~c;
+}
+
 int dctts_set_tensor_path(dctts_handle h, int32_t mode) {
     return guarded(h, [&] {
         REQUIRE(mode >= 0 && mode <= 2, "dctts_set_tensor_path: mode must be 0, 1 or 2");

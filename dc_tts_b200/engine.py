@@ -75,17 +75,33 @@ class Engine:
         return torch.empty(shape, device=self.device, dtype=dtype)
 
     # ------------------------------------------------------------------ parameters
-    def load_params(self, params):
-        """Stage every variable (TF names, SURVEY.md App. C) and commit them to the device."""
-        check_params(params)
+    def stage_params(self, params):
+        """Stage some variables (e.g. one of the two checkpoints of synthesize.py:31-41); commit_params() uploads."""
         for name, arr in params.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             shape = (C.c_int64 * a.ndim)(*a.shape)
             self._check(self._lib.dctts_set_param(self._h, name.encode(), a.ctypes.data_as(C.c_void_p),
                                                    shape, a.ndim), "dctts_set_param(%s)" % name)
+
+    def commit_params(self):
+        """Fails (library error) when a variable of the path is missing or mis-shaped."""
         self._check(self._lib.dctts_commit_params(self._h), "dctts_commit_params")
         self.params_loaded = True
         return int(self._lib.dctts_num_params(self._h))
+
+    def load_params(self, params):
+        """Stage every variable (TF names, SURVEY.md App. C) and commit them to the device."""
+        check_params(params)
+        self.stage_params(params)
+        return self.commit_params()
+
+    def restore(self, text2mel_dir, ssrn_dir=None):
+        """synthesize.py:31-41: the latest Text2Mel checkpoint of `<logdir>-1` and SSRN checkpoint of `<logdir>-2`
+        (TF tensor bundles, read without TensorFlow by dc_tts_b200/checkpoint.py)."""
+        from .checkpoint import Saver, latest_checkpoint
+        Saver(var_list=["Text2Mel"]).restore(self, latest_checkpoint(text2mel_dir))
+        Saver(var_list=["SSRN", "gs"]).restore(self, latest_checkpoint(ssrn_dir if ssrn_dir is not None else text2mel_dir))
+        return self.commit_params()
 
     def set_tensor_path(self, mode):
         self._check(self._lib.dctts_set_tensor_path(self._h, int(mode)), "dctts_set_tensor_path")

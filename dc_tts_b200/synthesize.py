@@ -2,8 +2,9 @@
 
 Same flow: load text -> build Graph(mode="synthesize") -> restore parameters -> mel
 loop (:45-54) -> SSRN (:57) -> write one output per sentence.  Differences, all forced
-by what exists offline: parameters come from a name->array dict (no TF checkpoint
-reader yet; seeded initialiser weights when none are given).  The Griffin-Lim vocoder
+by what exists offline: parameters are restored from the TF checkpoints under
+hp.logdir-1 / hp.logdir-2 when they exist (dc_tts_b200/checkpoint.py reads the tensor
+bundles without TensorFlow), else come from a name->array dict or the seeded initialiser.  The Griffin-Lim vocoder
 (utils.py:67-114) runs on the GPU (dc_tts_b200/utils.py) and the wavs are written with
 scipy.io.wavfile like the reference does.
 """
@@ -11,6 +12,7 @@ import os
 
 import numpy as np
 
+from .checkpoint import latest_checkpoint
 from .data_load import load_data
 from .engine import get_engine
 from .hyperparams import Hyperparams as hp
@@ -28,8 +30,12 @@ def synthesize(params=None, sentences=None, fast=True, write=True, seed=0, vocod
 
     with Session() as sess:
         # Restore parameters (synthesize.py:31-41)
-        if not g.engine.params_loaded:
-            g.engine.load_params(params if params is not None else init_params(seed))
+        if params is not None:
+            g.engine.load_params(params)
+        elif latest_checkpoint(hp.logdir + "-1") and latest_checkpoint(hp.logdir + "-2"):
+            g.engine.restore(hp.logdir + "-1", hp.logdir + "-2")
+        elif not g.engine.params_loaded:
+            g.engine.load_params(init_params(seed))
         print("Text2Mel Restored!")
         print("SSRN Restored!")
 

@@ -144,6 +144,10 @@ int dctts_reserve(dctts_handle h, int32_t max_batch);
 /* Number of kernels this library has launched on the handle since creation (graph
  * replays count their kernel nodes). */
 int64_t dctts_launch_count(dctts_handle h);
+/* Host utility for the checkpoint reader (dc_tts_b200/checkpoint.py): CRC-32C (Castagnoli) of `n` bytes,
+ * continuing from `crc` (0 to start) -- the checksum TF's tensor bundle stores (masked) for every index
+ * block and every tensor restored at synthesize.py:31-41.  No handle, no GPU. */
+uint32_t dctts_crc32c(uint32_t crc, const void* data, int64_t n);
 /* Selects the kernel set: 0 = one fp32 CUDA-core GEMM + one LN kernel per block (baseline),
  * 1 = default: tcgen05 split-fp16 (3-MMA, fp32-grade) fused blocks where they apply (whole
  * networks, full-sequence attention, and the wide AudioDec rows of the decode step when B >= 8),
