@@ -44,6 +44,7 @@ SIGNATURES = {
                                     C.POINTER(_i32), _p]),
     "dctts_set_vocoder_params": (C.c_int, [Handle, _i32, _i32, C.c_float, C.c_float, C.c_float, C.c_float, _i32]),
     "dctts_spectrogram2wav": (C.c_int, [Handle, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "dctts_get_spectrograms": (C.c_int, [Handle, _p, _i64, _i32, _p, _p, _i32, C.POINTER(_i32), C.POINTER(_i32), _p]),
     "dctts_reserve": (C.c_int, [Handle, _i32]),
     "dctts_launch_count": (_i64, [Handle]),
     "dctts_crc32c": (C.c_uint32, [C.c_uint32, _p, _i64]),

@@ -127,6 +127,8 @@ struct dctts_handle_s {
 
     // vocoder (Griffin-Lim) state
     struct { int hop = 275, win = 1102, n_iter = 50; float power = 1.5f, max_db = 100.f, ref_db = 20.f, preemph = 0.97f; } voc;
+    DevBuf feat_melw, feat_range, feat_tw, feat_window, feat_wss;   // feature extraction tables (dctts_get_spectrograms)
+    int feat_sr = 0, feat_win = 0;
     DevBuf voc_S, voc_X, voc_frames, voc_mse, voc_tw, voc_window, voc_wss, voc_deemph;
     int voc_tables_T = 0, voc_tables_win = 0, voc_tables_hop = 0;
 
@@ -147,6 +149,7 @@ struct dctts_handle_s {
         for (auto& b : arpl) b.release();
         for (auto& b : attpl) b.release();
         voc_S.release(); voc_X.release(); voc_frames.release(); voc_mse.release(); voc_tw.release(); voc_window.release(); voc_wss.release(); voc_deemph.release();
+        feat_melw.release(); feat_range.release(); feat_tw.release(); feat_window.release(); feat_wss.release();
         for (auto& b : ae_out) b.release();
         for (auto& b : ad_out) b.release();
         if (copy_stream) { cudaStreamDestroy(copy_stream); for (auto e : chunk_done) if (e) cudaEventDestroy(e); }
@@ -951,6 +954,20 @@ void ensure_scratch(H* h, size_t bytes) {
     h->scratch.ensure(bytes);
 }
 
+// librosa.effects.trim(y)[1] from the per-frame mean squares: frames within 60 dB of the loudest one
+void trim_from_mse(const float* m, int nfr, int Ly, int32_t* out) {
+    float mx = 0.f;
+    for (int f = 0; f < nfr; ++f) mx = std::max(mx, m[f]);
+    const double ref = 10.0 * std::log10(std::max(1e-10, (double)mx));
+    int first = -1, last = -1;
+    for (int f = 0; f < nfr; ++f) {
+        const double db = 10.0 * std::log10(std::max(1e-10, (double)m[f])) - ref;
+        if (db > -60.0) { if (first < 0) first = f; last = f; }
+    }
+    out[0] = first < 0 ? 0 : first * 512;
+    out[1] = first < 0 ? 0 : std::min(Ly, (last + 1) * 512);
+}
+
 }  // namespace
 
 // ==================================================================================== C-ABI
@@ -1267,21 +1284,48 @@ int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T
         std::vector<float> mse((size_t)B * nfr);
         CUDA_CHECK(cudaMemcpyAsync(mse.data(), a.mse, mse.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
         CUDA_CHECK(cudaStreamSynchronize(s));
-        if (trim_host) {
-            for (int b = 0; b < B; ++b) {
-                const float* m = mse.data() + (size_t)b * nfr;
-                float mx = 0.f;
-                for (int f = 0; f < nfr; ++f) mx = std::max(mx, m[f]);
-                const double ref = 10.0 * std::log10(std::max(1e-10, (double)mx));
-                int first = -1, last = -1;
-                for (int f = 0; f < nfr; ++f) {
-                    const double db = 10.0 * std::log10(std::max(1e-10, (double)m[f])) - ref;
-                    if (db > -60.0) { if (first < 0) first = f; last = f; }
-                }
-                trim_host[2 * b] = first < 0 ? 0 : first * 512;
-                trim_host[2 * b + 1] = first < 0 ? 0 : std::min(Ly, (last + 1) * 512);
-            }
+        if (trim_host)
+            for (int b = 0; b < B; ++b) trim_from_mse(mse.data() + (size_t)b * nfr, nfr, Ly, trim_host + 2 * b);
+    });
+}
+
+int dctts_get_spectrograms(dctts_handle h, const float* wav, int64_t n_samples, int32_t sample_rate, float* mel, float* mag,
+                           int32_t t_capacity, int32_t* t_out, int32_t* trim_host, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(wav && mel && mag && t_out && n_samples >= 2 && n_samples < (1ll << 30) && sample_rate > 0,
+                "dctts_get_spectrograms: bad arguments");
+        REQUIRE(h->F == 1025, "dctts_get_spectrograms: the FFT kernel is built for n_fft = 2048");
+        cudaStream_t s = S(h, stream);
+        const int n = (int)n_samples, F = h->F, win = h->voc.win, hop = h->voc.hop, n_mels = h->hp.n_mels;
+        if (h->feat_sr != sample_rate || h->feat_win != win) {
+            std::vector<float> w; std::vector<int> range;
+            feat_make_mel_basis(sample_rate, h->hp.n_fft, n_mels, w, range);
+            h->feat_melw.ensure(w.size() * sizeof(float)); h->feat_range.ensure(range.size() * sizeof(int));
+            h->feat_tw.ensure(2048 * sizeof(float2)); h->feat_window.ensure(win * sizeof(float)); h->feat_wss.ensure(2048 * sizeof(float));
+            CUDA_CHECK(cudaMemcpyAsync(h->feat_melw.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+            CUDA_CHECK(cudaMemcpyAsync(h->feat_range.p, range.data(), range.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+            voc_make_tables(h->feat_tw.as<float2>(), h->feat_window.as<float>(), h->feat_wss.as<float>(), 1, win, hop, s);   // synchronises
+            h->feat_sr = sample_rate; h->feat_win = win;
         }
+        // librosa.effects.trim (utils.py:36): frame energies on the device, threshold on the host
+        const int nfr = 1 + n / 512;
+        h->voc_mse.ensure((size_t)nfr * sizeof(float));
+        feat_frame_mse(wav, h->voc_mse.as<float>(), n, nfr, s);
+        std::vector<float> mse(nfr);
+        CUDA_CHECK(cudaMemcpyAsync(mse.data(), h->voc_mse.p, mse.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        int se[2];
+        trim_from_mse(mse.data(), nfr, n, se);
+        if (trim_host) { trim_host[0] = se[0]; trim_host[1] = se[1]; }
+        const int len = se[1] - se[0];
+        REQUIRE(len >= 2, "dctts_get_spectrograms: nothing left after trimming (silent input)");
+        const int T = 1 + len / hop;
+        *t_out = T;
+        REQUIRE(T <= t_capacity, "dctts_get_spectrograms: output buffers too small (need 1 + n_samples / hop_length rows)");
+        feat_run(wav + se[0], len, h->voc.preemph, mag, mel, h->feat_melw.as<float>(), h->feat_range.as<int>(), h->feat_tw.as<float2>(),
+                 h->feat_window.as<float>(), T, F, n_mels, win, hop, h->voc.ref_db, h->voc.max_db, s);
+        h->launches += 2;
+        CUDA_CHECK(cudaGetLastError());
     });
 }
 

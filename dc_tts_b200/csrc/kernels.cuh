@@ -7,6 +7,7 @@
 // falls outside [0, L) contributes zeros (TF zero padding, reference modules.py:121-125).
 // With R == L and jptr == nullptr this is the plain full-sequence case.
 #pragma once
+#include <vector>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -126,6 +127,12 @@ void voc_make_tables(float2* tw_dev, float* window_dev, float* wss_dev, int T, i
 void voc_run(const VocoderArgs& a, cudaStream_t s);
 int voc_launches_per_call(int n_iter);
 size_t voc_deemph_scratch_bytes(int B, int T, int hop);
+// feature extraction (reference utils.py:20-65)
+void feat_make_mel_basis(int sr, int n_fft, int n_mels, std::vector<float>& w, std::vector<int>& range);
+void feat_frame_mse(const float* y, float* mse, int n, int nfr, cudaStream_t s);
+void feat_run(const float* y, int len, float preemph, float* mag, float* mel, const float* melw, const int* melrange,
+              const float2* tw, const float* window, int T, int F, int n_mels, int win, int hop, float ref_db, float max_db,
+              cudaStream_t s);
 
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);

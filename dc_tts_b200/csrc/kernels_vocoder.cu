@@ -240,6 +240,70 @@ __global__ void __launch_bounds__(256) voc_frame_mse_kernel(const float* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------- features
+// get_spectrograms (reference utils.py:20-65) for one trimmed utterance, one CTA per STFT frame: pre-emphasis
+// (float32 multiply then subtract, like numpy), reflect-padded Hann frame, the same real-packed FFT, |X|,
+// the mel filterbank (each mel bin is a contiguous run of FFT bins), 20 log10, normalisation.  grid (T).
+__global__ void __launch_bounds__(VC_THREADS) feat_stft_mel_kernel(const float* __restrict__ y, int len, float preemph,
+                                                                   float* __restrict__ mag_out, float* __restrict__ mel_out,
+                                                                   const float* __restrict__ melw, const int2* __restrict__ melrange,
+                                                                   const float2* __restrict__ tw, const float* __restrict__ window,
+                                                                   int F, int n_mels, int win, int lpad, int hop, float ref_db,
+                                                                   float max_db) {
+    __shared__ __align__(16) float2 s0[VC_H];
+    __shared__ __align__(16) float2 s1[VC_H];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    auto sample = [&](int n) -> float {
+        const int m = n - lpad;
+        if (m < 0 || m >= win) return 0.f;
+        int u = t * hop + n - VC_N / 2;                   // np.pad(y, n_fft//2, mode='reflect')
+        if (u < 0) u = -u;
+        if (u >= len) u = 2 * (len - 1) - u;
+        u = min(max(u, 0), len - 1);
+        const float v = (u > 0) ? __fsub_rn(y[u], __fmul_rn(preemph, y[u - 1])) : y[0];      // utils.py:39
+        return v * window[m];
+    };
+    float2 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int n = 2 * (tid + 256 * k); v[k] = make_float2(sample(n), sample(n + 1)); }
+    fft1024<false>(v, s0, s1, tw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s0[tid + 256 * k] = v[k];
+    __syncthreads();
+    float* lin = reinterpret_cast<float*>(s1);             // |X[k]|, k <= 1024 (s1 was last read inside the FFT)
+    float* mo = mag_out + (size_t)t * F;
+    auto emit = [&](int kk, float2 e) {
+        const float a = sqrtf(e.x * e.x + e.y * e.y);
+        lin[kk] = a;
+        const float db = 20.0f * log10f(fmaxf(1e-5f, a));
+        mo[kk] = fminf(fmaxf((db - ref_db + max_db) / max_db, 1e-8f), 1.0f);
+    };
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int kk = tid + 256 * k;
+        const float2 zk = v[k];
+        float2 zc = s0[(VC_H - kk) & (VC_H - 1)]; zc.y = -zc.y;
+        const float2 e = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+        const float2 d = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+        const float2 o = cmul(make_float2(d.y, -d.x), tw[kk]);
+        emit(kk, make_float2(e.x + o.x, e.y + o.y));
+        if (kk == 0) emit(VC_H, make_float2(zk.x - zk.y, 0.f));
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int m = warp; m < n_mels; m += VC_THREADS / 32) {
+        const int2 r = melrange[m];
+        const float* w = melw + (size_t)m * F;
+        float acc = 0.f;
+        for (int k = r.x + lane; k < r.y; k += 32) acc = fmaf(w[k], lin[k], acc);
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            const float db = 20.0f * log10f(fmaxf(1e-5f, acc));
+            mel_out[(size_t)t * n_mels + m] = fminf(fmaxf((db - ref_db + max_db) / max_db, 1e-8f), 1.0f);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------- host
 void voc_make_tables(float2* tw_dev, float* window_dev, float* wss_dev, int T, int win, int hop, cudaStream_t s) {
     voc_twiddle_kernel<<<(VC_N + 255) / 256, 256, 0, s>>>(tw_dev);
@@ -257,6 +321,45 @@ void voc_make_tables(float2* tw_dev, float* window_dev, float* wss_dev, int T, i
     cudaMemcpyAsync(window_dev, w.data(), win * sizeof(float), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(wss_dev, wss.data(), n_tot * sizeof(float), cudaMemcpyHostToDevice, s);
     cudaStreamSynchronize(s);
+}
+
+// librosa.filters.mel(sr, n_fft, n_mels): Slaney scale, fmin 0, fmax sr/2, area-normalised triangles (float64 here,
+// float32 on the device); range[m] = [first, last+1) non-zero FFT bin of mel bin m.
+void feat_make_mel_basis(int sr, int n_fft, int n_mels, std::vector<float>& w, std::vector<int>& range) {
+    const int F = 1 + n_fft / 2;
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    auto hz2mel = [&](double f) { return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp; };
+    auto mel2hz = [&](double m) { return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m; };
+    std::vector<double> mel_f(n_mels + 2);
+    const double m_lo = hz2mel(0.0), m_hi = hz2mel(sr / 2.0);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel2hz(m_lo + (m_hi - m_lo) * (double)i / (double)(n_mels + 1));
+    w.assign((size_t)n_mels * F, 0.f);
+    range.assign(2 * (size_t)n_mels, 0);
+    for (int i = 0; i < n_mels; ++i) {
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        int first = -1, last = -1;
+        for (int k = 0; k < F; ++k) {
+            const double f = (sr / 2.0) * (double)k / (double)(F - 1);
+            const double lower = (f - mel_f[i]) / (mel_f[i + 1] - mel_f[i]);
+            const double upper = (mel_f[i + 2] - f) / (mel_f[i + 2] - mel_f[i + 1]);
+            const double v = std::max(0.0, std::min(lower, upper)) * enorm;
+            w[(size_t)i * F + k] = (float)v;
+            if (v > 0.0) { if (first < 0) first = k; last = k; }
+        }
+        range[2 * i] = first < 0 ? 0 : first;
+        range[2 * i + 1] = first < 0 ? 0 : last + 1;
+    }
+}
+
+void feat_frame_mse(const float* y, float* mse, int n, int nfr, cudaStream_t s) {
+    voc_frame_mse_kernel<<<dim3(nfr, 1), 256, 0, s>>>(y, mse, n, nfr, 2048, 512);
+}
+
+void feat_run(const float* y, int len, float preemph, float* mag, float* mel, const float* melw, const int* melrange,
+              const float2* tw, const float* window, int T, int F, int n_mels, int win, int hop, float ref_db, float max_db,
+              cudaStream_t s) {
+    feat_stft_mel_kernel<<<T, VC_THREADS, 0, s>>>(y, len, preemph, mag, mel, melw, reinterpret_cast<const int2*>(melrange), tw,
+                                                  window, F, n_mels, win, (VC_N - win) / 2, hop, ref_db, max_db);
 }
 
 int voc_launches_per_call(int n_iter) { return 1 + 3 * n_iter + 2 + 3 + 1; }

@@ -245,6 +245,24 @@ class Engine:
                                                     trim.ctypes.data_as(C.c_void_p), self._stream()), "dctts_spectrogram2wav")
         return wav, trim
 
+    def get_spectrograms(self, wav, sr=None):
+        """utils.py:20-65 from a loaded waveform (1-D float32, hp.sr): -> (mel (T, n_mels), mag (T, F)) CUDA tensors and
+        the [start, end) sample range librosa.effects.trim keeps."""
+        h = self.hp
+        wav = self._f32(wav).reshape(-1)
+        n = wav.numel()
+        self._check(self._lib.dctts_set_vocoder_params(self._h, h.hop_length, h.win_length, float(h.power), float(h.max_db),
+                                                       float(h.ref_db), float(h.preemphasis), int(h.n_iter)),
+                    "dctts_set_vocoder_params")
+        cap = 1 + n // h.hop_length
+        mel = self._empty(cap, h.n_mels)
+        mag = self._empty(cap, self.F)
+        t = C.c_int32(0)
+        trim = (C.c_int32 * 2)()
+        self._check(self._lib.dctts_get_spectrograms(self._h, _ptr(wav), n, int(sr or h.sr), _ptr(mel), _ptr(mag), cap,
+                                                     C.byref(t), trim, self._stream()), "dctts_get_spectrograms")
+        return mel[:t.value], mag[:t.value], (int(trim[0]), int(trim[1]))
+
     def synthesize_host(self, L_host, Y_host=None, Z_host=None):
         """synthesize.py:45-57 with host (ideally pinned) tensors in and out."""
         L_host = torch.as_tensor(L_host, dtype=torch.int32).contiguous()

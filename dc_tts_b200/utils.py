@@ -4,9 +4,14 @@
 The reference runs librosa's stft / istft on the CPU, 50 + 51 times per utterance; here the whole
 Griffin-Lim loop runs on the GPU (csrc/kernels_vocoder.cu: one CTA per STFT frame, a 2048-point FFT
 in shared memory) behind `dctts_spectrogram2wav`.  This is the first "next" row of SURVEY.md 8(f), not part
-of the Text2Mel + SSRN hot path.  Feature extraction (`get_spectrograms`, `load_spectrograms`),
-plotting and the training helpers of the reference's utils.py stay out of scope.
+of the Text2Mel + SSRN hot path.  Feature extraction (`get_spectrograms`, `load_spectrograms`,
+utils.py:20-65,147-162) runs on the GPU too (`dctts_get_spectrograms`: trim, pre-emphasis, STFT, mel
+filterbank, dB, normalisation in one kernel per utterance); `librosa.load` is replaced by scipy's WAV reader
+for files that already have hp.sr (LJ Speech does) -- resampling, plotting and the training helpers of the
+reference's utils.py stay out of scope.
 """
+import os
+
 import numpy as np
 
 from .engine import get_engine
@@ -56,3 +61,40 @@ def invert_spectrogram(spectrogram):
     x = y.copy()
     x[1:] -= hp.preemphasis * y[:-1]
     return x.astype(np.float32)
+
+
+def _load_wav(fpath):
+    """What `librosa.load(fpath, sr=hp.sr)` returns for a mono PCM / float WAV that already has hp.sr."""
+    from scipy.io import wavfile
+    sr, y = wavfile.read(fpath)
+    if sr != hp.sr:
+        raise ValueError("%s: sample rate %d != hp.sr %d (resampling is not implemented)" % (fpath, sr, hp.sr))
+    if y.ndim > 1:
+        y = y.mean(axis=1)
+    if y.dtype == np.int16:
+        y = y.astype(np.float32) / 32768.0
+    elif y.dtype == np.int32:
+        y = y.astype(np.float32) / 2147483648.0
+    elif y.dtype == np.uint8:
+        y = (y.astype(np.float32) - 128.0) / 128.0
+    return np.ascontiguousarray(y, np.float32)
+
+
+def get_spectrograms(fpath):
+    """utils.py:20-65.  `fpath`: a WAV file path, or the already loaded waveform (1-D float array at hp.sr).
+    Returns normalised mel (T, n_mels) and linear magnitude (T, 1+n_fft/2), float32 numpy."""
+    y = _load_wav(fpath) if isinstance(fpath, (str, bytes, os.PathLike)) else np.asarray(fpath, np.float32)
+    mel, mag, _ = get_engine().get_spectrograms(y)
+    return mel.cpu().numpy(), mag.cpu().numpy()
+
+
+def load_spectrograms(fpath):
+    """utils.py:147-162: pads T to a multiple of hp.r and keeps every r-th mel frame."""
+    fname = os.path.basename(fpath) if isinstance(fpath, (str, bytes, os.PathLike)) else None
+    mel, mag = get_spectrograms(fpath)
+    t = mel.shape[0]
+    num_paddings = hp.r - (t % hp.r) if t % hp.r != 0 else 0
+    mel = np.pad(mel, [[0, num_paddings], [0, 0]], mode="constant")
+    mag = np.pad(mag, [[0, num_paddings], [0, 0]], mode="constant")
+    mel = mel[::hp.r, :]
+    return fname, mel, mag

@@ -138,6 +138,15 @@ int dctts_set_vocoder_params(dctts_handle h, int32_t hop_length, int32_t win_len
 int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T, int32_t n_iter, float* wav,
                           int32_t* trim_host, void* stream);
 
+/* Feature extraction (next row): get_spectrograms -- utils.py:20-65 -- for ONE utterance from the
+ * loaded waveform on: trim (librosa.effects.trim), pre-emphasis, STFT, |.|, mel filterbank
+ * (librosa.filters.mel(sample_rate, n_fft, n_mels)), 20 log10, normalisation with the constants of
+ * dctts_set_vocoder_params.  `wav` DEVICE float32 [n_samples]; `mel` (t_capacity, n_mels) and `mag`
+ * (t_capacity, 1 + n_fft/2) DEVICE outputs, rows [0, *t_out) written, t_capacity >= 1 + n_samples / hop_length;
+ * `trim_host` (optional) receives the [start, end) sample range kept.  Synchronises the stream once. */
+int dctts_get_spectrograms(dctts_handle h, const float* wav, int64_t n_samples, int32_t sample_rate, float* mel, float* mag,
+                           int32_t t_capacity, int32_t* t_out, int32_t* trim_host, void* stream);
+
 /* ---- utilities ----------------------------------------------------------------- */
 /* Pre-size the workspace (otherwise grown lazily on first use) for batches up to B. */
 int dctts_reserve(dctts_handle h, int32_t max_batch);
