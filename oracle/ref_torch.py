@@ -6,6 +6,10 @@ no checkpoint, and its TF1 code cannot run here (TensorFlow absent, `tf.contrib`
 TF 1.x / Python <= 3.7).  This file is therefore a literal restatement of the
 reference's algorithm, with the TF op semantics of SURVEY.md App. B, cross-checked
 against the independent numpy/fp64 restatement in `ref_numpy.py` (tests/test_oracle.py).
+PINNED since: the reference's own modules.py / networks.py / train.py executed under the TF API stand-in
+tests/golden/tf_shim.py reproduce this file to <= 2.4e-6 with the same window trajectory and variable schema
+(tests/test_reference_shim.py, fixtures tests/golden/refshim_*.npz) -- that pins the wiring; the numerics of
+the TF ops themselves remain restated, not observed.
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference`
 legs may import it; the product path never does.
 
