@@ -125,6 +125,22 @@ struct dctts_handle_s {
     DevBuf attpl[6];              // tcgen05 attention operands: Q, K planes and transposed V planes ({hi,lo} each)
     DevBuf arpl[10];              // AR decode planes: R (B,T,2d) and four AudioDec outputs (B,T,d), {hi,lo} each
 
+    // training step (Text2Mel, reference train.py mode "train"): see the "training" section below
+    struct TrainLayer {
+        LayerDev* l = nullptr; int li = 0; long long rows = 0; int L = 0; const float* in = nullptr; int ld_in = 0;
+        float* pre = nullptr; float* out = nullptr; int extra_shift = 0; bool need_dgrad = true;
+        float *dW = nullptr, *dbias = nullptr, *dg1 = nullptr, *db1 = nullptr, *dg2 = nullptr, *db2 = nullptr;
+    };
+    struct TrainTensor { float* p; float* g; float* m; float* v; long long n; };
+    struct {
+        bool ready = false; int B = 0; float rate = 0.f;
+        std::vector<TrainLayer> layers;
+        std::map<std::string, TrainTensor> tensors;            // by TF variable name
+        DevBuf pre, out, emb, R, align, dS, gbuf[4], dy, wT, zeros, gts, sums, ids, grads, mom, vel, entries;
+        long long n_grad = 0; int n_entries = 0; float* d_table = nullptr;
+        int first[3] = {0, 0, 0}, last[3] = {0, 0, 0};         // layer index ranges: TextEnc, AudioEnc, AudioDec
+    } tr;
+
     // vocoder (Griffin-Lim) state
     struct { int hop = 275, win = 1102, n_iter = 50; float power = 1.5f, max_db = 100.f, ref_db = 20.f, preemph = 0.97f; } voc;
     DevBuf feat_melw, feat_range, feat_tw, feat_window, feat_wss;   // feature extraction tables (dctts_get_spectrograms)
@@ -143,6 +159,8 @@ struct dctts_handle_s {
     ~dctts_handle_s() {
         if (ar_exec) cudaGraphExecDestroy(ar_exec);
         for (void* p : param_allocs) cudaFree(p);
+        for (DevBuf* b : {&tr.pre, &tr.out, &tr.emb, &tr.R, &tr.align, &tr.dS, &tr.gbuf[0], &tr.gbuf[1], &tr.gbuf[2], &tr.gbuf[3], &tr.dy,
+                          &tr.wT, &tr.zeros, &tr.gts, &tr.sums, &tr.ids, &tr.grads, &tr.mom, &tr.vel, &tr.entries}) b->release();
         tickets.release(); scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
         for (auto& b : plane) b.release();
@@ -954,6 +972,210 @@ void ensure_scratch(H* h, size_t bytes) {
     h->scratch.ensure(bytes);
 }
 
+// ---------------------------------------------------------------------------- training (Text2Mel)
+// One optimiser step of the reference's Text2Mel trainer (train.py:43-68 graph, losses :83-99, Adam :122-132) for
+// fixed-size batches (B, max_N) / (B, max_T, n_mels) -- BASELINE config 5.  Forward = the fp32 block kernels with every
+// pre-LN tensor kept; backward = kernels_train.cu.  Gradients, Adam moments and the pointers of all 23.97 M Text2Mel
+// variables live in three arenas with identical offsets (the gradient arena is what a data-parallel all-reduce sums).
+void train_init(H* h, int B, float rate) {
+    REQUIRE(h->committed, "dctts_train_init: parameters must be committed first");
+    REQUIRE(B >= 1 && rate >= 0.f && rate < 1.f, "dctts_train_init: bad arguments");
+    auto& tr = h->tr;
+    if (tr.ready && tr.B == B) { tr.rate = rate; return; }
+    CUDA_CHECK(cudaDeviceSynchronize());
+    if (h->ar_exec) { cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
+    h->tensor_path = 0;            // the optimiser updates the fp32 weights only: this handle stops using the packed fp16 planes
+    const dctts_hparams& hp = h->hp;
+    const int N = hp.max_N, T = hp.max_T, d = hp.d;
+    tr.layers.clear(); tr.tensors.clear();
+    std::vector<LayerDev>* nets[3] = {&h->textenc, &h->audioenc, &h->audiodec};
+    size_t pre_f = 0, out_f = 0;
+    long long n_grad = 0;
+    auto reserve = [&](long long n) { long long o = n_grad; n_grad += (n + 3) / 4 * 4; return o; };
+    struct Off { long long W, bias, g1, b1, g2, b2; };
+    std::vector<Off> offs;
+    const long long table_off = reserve((long long)hp.vocab_size * hp.e);
+    int li = 0;
+    for (int net = 0; net < 3; ++net) {
+        tr.first[net] = li;
+        for (auto& l : *nets[net]) {
+            H::TrainLayer t;
+            t.l = &l; t.li = li++; t.L = net == 0 ? N : T; t.rows = (long long)B * t.L;
+            REQUIRE(l.kind != K_D && l.ldw == l.nconv, "training: unexpected layer layout");
+            pre_f += (size_t)t.rows * l.ldw; out_f += (size_t)t.rows * l.cout;
+            Off o{};
+            o.W = reserve((long long)l.size * l.cin * l.ldw); o.bias = reserve(l.ldw);
+            o.g1 = reserve(l.cout); o.b1 = reserve(l.cout);
+            if (l.kind == K_HC) { o.g2 = reserve(l.cout); o.b2 = reserve(l.cout); }
+            offs.push_back(o);
+            tr.layers.push_back(t);
+        }
+        tr.last[net] = li - 1;
+    }
+    tr.pre.ensure(pre_f * sizeof(float)); tr.out.ensure(out_f * sizeof(float));
+    tr.emb.ensure((size_t)B * N * hp.e * sizeof(float)); tr.R.ensure((size_t)B * T * 2 * d * sizeof(float));
+    tr.align.ensure((size_t)B * N * T * sizeof(float)); tr.dS.ensure((size_t)B * T * N * sizeof(float));
+    const size_t gmax = (size_t)B * std::max(N, T) * std::max(2 * d, hp.e);
+    for (auto& g : tr.gbuf) g.ensure(gmax * sizeof(float));
+    tr.dy.ensure((size_t)B * std::max(N, T) * 4 * d * sizeof(float));
+    tr.wT.ensure((size_t)3 * 4 * d * 2 * d * sizeof(float));
+    tr.zeros.ensure(4096 * sizeof(float)); CUDA_CHECK(cudaMemset(tr.zeros.p, 0, 4096 * sizeof(float)));
+    tr.gts.ensure((size_t)N * T * sizeof(float)); launch_guided_attention(tr.gts.as<float>(), N, T, h->stream);
+    tr.sums.ensure(4 * sizeof(double)); tr.ids.ensure((size_t)B * N * sizeof(int));
+    tr.grads.ensure(n_grad * sizeof(float)); tr.mom.ensure(n_grad * sizeof(float)); tr.vel.ensure(n_grad * sizeof(float));
+    CUDA_CHECK(cudaMemset(tr.grads.p, 0, n_grad * sizeof(float)));
+    CUDA_CHECK(cudaMemset(tr.mom.p, 0, n_grad * sizeof(float))); CUDA_CHECK(cudaMemset(tr.vel.p, 0, n_grad * sizeof(float)));
+    tr.n_grad = n_grad;
+    float* G = tr.grads.as<float>(); float* M = tr.mom.as<float>(); float* V = tr.vel.as<float>();
+    std::vector<AdamEntry> entries;
+    auto reg = [&](const std::string& name, float* p, long long off, long long n) {
+        tr.tensors[name] = H::TrainTensor{p, G + off, M + off, V + off, n};
+        entries.push_back(AdamEntry{p, G + off, M + off, V + off, n});
+        return G + off;
+    };
+    tr.d_table = reg("Text2Mel/TextEnc/embed_1/lookup_table", h->embed_table, table_off, (long long)hp.vocab_size * hp.e);
+    float* pre = tr.pre.as<float>(); float* out = tr.out.as<float>();
+    for (size_t i = 0; i < tr.layers.size(); ++i) {
+        auto& t = tr.layers[i]; LayerDev& l = *t.l; const Off& o = offs[i];
+        t.pre = pre; pre += (size_t)t.rows * l.ldw;
+        t.out = out; out += (size_t)t.rows * l.cout;
+        t.dW = reg(l.scope + "/conv1d/kernel", l.W, o.W, (long long)l.size * l.cin * l.ldw);
+        t.dbias = reg(l.scope + "/conv1d/bias", l.bias, o.bias, l.ldw);
+        const std::string n1 = l.kind == K_HC ? "/H1" : "/normalize";
+        t.dg1 = reg(l.scope + n1 + "/gamma", l.g1, o.g1, l.cout); t.db1 = reg(l.scope + n1 + "/beta", l.b1, o.b1, l.cout);
+        if (l.kind == K_HC) { t.dg2 = reg(l.scope + "/H2/gamma", l.g2, o.g2, l.cout); t.db2 = reg(l.scope + "/H2/beta", l.b2, o.b2, l.cout); }
+    }
+    // inputs: TextEnc <- embedding; AudioEnc <- mels shifted by one frame (train.py:51), set per step; AudioDec <- R
+    for (int net = 0; net < 3; ++net)
+        for (int i = tr.first[net]; i <= tr.last[net]; ++i) {
+            auto& t = tr.layers[i];
+            if (i > tr.first[net]) { t.in = tr.layers[i - 1].out; t.ld_in = tr.layers[i - 1].l->cout; }
+        }
+    tr.layers[tr.first[0]].in = tr.emb.as<float>(); tr.layers[tr.first[0]].ld_in = hp.e;
+    tr.layers[tr.first[1]].ld_in = hp.n_mels; tr.layers[tr.first[1]].extra_shift = -1; tr.layers[tr.first[1]].need_dgrad = false;
+    tr.layers[tr.first[2]].in = tr.R.as<float>(); tr.layers[tr.first[2]].ld_in = 2 * d;
+    tr.entries.ensure(entries.size() * sizeof(AdamEntry));
+    CUDA_CHECK(cudaMemcpy(tr.entries.p, entries.data(), entries.size() * sizeof(AdamEntry), cudaMemcpyHostToDevice));
+    tr.n_entries = (int)entries.size();
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    tr.B = B; tr.rate = rate; tr.ready = true;
+}
+
+void layer_shifts(const LayerDev& l, int extra, int* shifts) {
+    const int tot = (l.size - 1) * l.rate, left = l.causal ? tot : tot / 2;
+    for (int j = 0; j < l.size; ++j) shifts[j] = j * l.rate - left + extra;
+}
+
+DropArgs drop_args(float rate, int li, uint32_t seed) {
+    DropArgs d;
+    if (rate > 0.f) {
+        d.thresh = (uint32_t)std::min<double>((double)rate * 4294967296.0, 4294967295.0);
+        d.scale = 1.0f / (1.0f - rate);
+    }
+    d.layer = (uint32_t)li; d.seed = seed;
+    return d;
+}
+
+void train_forward_backward(H* h, const int* L, const float* mels, int B, uint32_t seed, float* losses_host, cudaStream_t s) {
+    auto& tr = h->tr;
+    REQUIRE(tr.ready && tr.B == B, "dctts_train_step: call dctts_train_init with this batch size first");
+    const dctts_hparams& hp = h->hp;
+    const int N = hp.max_N, T = hp.max_T, d = hp.d;
+    Launch lc{h, s};
+    CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
+    CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
+    tr.layers[tr.first[1]].in = mels;
+    // ---------------- forward, every pre-LN tensor and block output kept ----------------
+    launch_embed(L, h->embed_table, tr.emb.as<float>(), B * N, hp.e, s); lc.count();
+    auto fwd = [&](int first, int last) {
+        for (int i = first; i <= last; ++i) {
+            auto& t = tr.layers[i]; const LayerDev& l = *t.l;
+            ConvArgs c{};
+            c.X = t.in; c.ldx = t.ld_in; c.Y = t.pre; c.ldy = l.ldw; c.bias = l.bias; c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
+            c.ntaps = l.size;
+            int sh[3]; layer_shifts(l, t.extra_shift, sh);
+            for (int j = 0; j < l.size; ++j) { c.taps[j].W = l.W + (size_t)j * l.cin * l.ldw; c.taps[j].shift = sh[j]; }
+            c.win = RowWin{B, t.L, t.L, nullptr}; c.Lout = t.L; c.ostride = 1; c.ooff = 0;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+            LnArgs n{};
+            n.Y = t.pre; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2; n.X = t.in; n.ldx = t.ld_in;
+            n.out = t.out; n.ldo = l.cout; n.C = l.cout; n.mode = l.kind == K_HC ? 1 : 0; n.act = l.act; n.win = c.win;
+            launch_ln_rows(n, s); lc.count();
+            if (tr.rate > 0.f) { launch_train_dropout(t.out, t.rows * l.cout, drop_args(tr.rate, t.li, seed), s); lc.count(); }
+        }
+    };
+    fwd(tr.first[0], tr.last[0]);
+    fwd(tr.first[1], tr.last[1]);
+    const float* KV = tr.layers[tr.last[0]].out;               // (B, N, 2d): K | V
+    const float* Q = tr.layers[tr.last[1]].out;                // (B, T, d)
+    run_attention(lc, Q, d, KV, 2 * d, KV + d, 2 * d, RowWin{B, T, T, nullptr}, N, nullptr, tr.R.as<float>(), tr.align.as<float>(),
+                  nullptr, nullptr, nullptr);
+    fwd(tr.first[2], tr.last[2]);
+    // ---------------- losses ----------------
+    const float* logits = tr.layers[tr.last[2]].out;
+    const long long n_el = (long long)B * T * hp.n_mels;
+    launch_train_loss(logits, mels, tr.gbuf[0].as<float>(), tr.sums.as<double>(), n_el, s); lc.count();
+    // ---------------- backward ----------------
+    auto bwd = [&](int first, int last, float* g_cur, float* g_other) -> float* {
+        for (int i = last; i >= first; --i) {
+            auto& t = tr.layers[i]; const LayerDev& l = *t.l;
+            BlockBwdArgs a{};
+            a.pre = t.pre; a.ldy = l.ldw; a.gout = g_cur; a.X = t.in; a.ldx = t.ld_in;
+            a.g1 = l.g1; a.b1 = l.b1; a.g2 = l.g2; a.b2 = l.b2; a.dy = tr.dy.as<float>(); a.gin = g_other;
+            a.dg1 = t.dg1; a.db1 = t.db1; a.dg2 = t.dg2; a.db2 = t.db2; a.dbias = t.dbias;
+            a.rows = t.rows; a.C = l.cout; a.mode = l.kind == K_HC ? 1 : 0; a.act = l.act; a.drop = drop_args(tr.rate, t.li, seed);
+            launch_train_block_bwd(a, s); lc.count();
+            WgradArgs w{};
+            w.X = t.in; w.ldx = t.ld_in; w.dy = tr.dy.as<float>(); w.ldy = l.ldw; w.dW = t.dW; w.ldw = l.ldw;
+            w.rows = t.rows; w.L = t.L; w.K = l.cin; w.N = l.nconv; w.ntaps = l.size;
+            layer_shifts(l, t.extra_shift, w.shifts);
+            launch_conv_wgrad(w, s); lc.count();
+            if (!t.need_dgrad) continue;
+            launch_transpose_w(l.W, tr.wT.as<float>(), l.size, l.cin, l.nconv, l.ldw, s); lc.count();
+            ConvArgs c{};
+            c.X = tr.dy.as<float>(); c.ldx = l.ldw; c.Y = g_other; c.ldy = l.cin; c.bias = tr.zeros.as<float>();
+            c.K = l.nconv; c.N = l.cin; c.ldw = l.cin; c.ntaps = l.size;
+            for (int j = 0; j < l.size; ++j) { c.taps[j].W = tr.wT.as<float>() + (size_t)j * l.nconv * l.cin; c.taps[j].shift = -w.shifts[j]; }
+            c.win = RowWin{B, t.L, t.L, nullptr}; c.Lout = t.L; c.ostride = 1; c.ooff = 0; c.accumulate = a.mode;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+            std::swap(g_cur, g_other);
+        }
+        return g_cur;
+    };
+    float* gR = bwd(tr.first[2], tr.last[2], tr.gbuf[0].as<float>(), tr.gbuf[1].as<float>());
+    AttnBwdArgs ab{};
+    ab.gR = gR; ab.Q = Q; ab.ldq = d; ab.K = KV; ab.V = KV + d; ab.ldkv = 2 * d; ab.align = tr.align.as<float>();
+    ab.gts = tr.gts.as<float>(); ab.dS = tr.dS.as<float>(); ab.gQ = tr.gbuf[2].as<float>(); ab.gKV = tr.gbuf[3].as<float>();
+    ab.B = B; ab.T = T; ab.N = N; ab.d = d; ab.att_scale = 1.0f / ((float)B * (float)N * (float)T);
+    launch_attn_bwd(ab, tr.sums.as<double>(), s); lc.count(3);
+    float* free_a = (gR == tr.gbuf[0].as<float>()) ? tr.gbuf[1].as<float>() : tr.gbuf[0].as<float>();
+    bwd(tr.first[1], tr.last[1], tr.gbuf[2].as<float>(), free_a);
+    float* gEmb = bwd(tr.first[0], tr.last[0], tr.gbuf[3].as<float>(), free_a);
+    launch_embed_bwd(L, gEmb, tr.d_table, B * N, hp.e, s); lc.count();
+    CUDA_CHECK(cudaGetLastError());
+    if (losses_host) {
+        double sums[4];
+        CUDA_CHECK(cudaMemcpyAsync(sums, tr.sums.p, sizeof(sums), cudaMemcpyDeviceToHost, s));
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        losses_host[1] = (float)(sums[0] / (double)n_el);
+        losses_host[2] = (float)(sums[1] / (double)n_el);
+        losses_host[3] = (float)(sums[2] / ((double)B * N * T));
+        losses_host[0] = losses_host[1] + losses_host[2] + losses_host[3];
+    }
+}
+
+void train_apply(H* h, long long global_step, float lr, cudaStream_t s) {
+    auto& tr = h->tr;
+    REQUIRE(tr.ready, "dctts_train_apply: no training state");
+    const double beta1 = 0.9, beta2 = 0.999, warm = 4000.0;
+    const double step = (double)(global_step + 1);
+    const double lr_now = (double)(lr > 0.f ? lr : 0.001f) * std::sqrt(warm) * std::min(step * std::pow(warm, -1.5), 1.0 / std::sqrt(step));   // utils.py:141-145
+    const double lr_t = lr_now * std::sqrt(1.0 - std::pow(beta2, step)) / (1.0 - std::pow(beta1, step));
+    launch_adam(reinterpret_cast<const AdamEntry*>(tr.entries.p), tr.n_entries, (float)lr_t, (float)beta1, (float)beta2, 1e-8f, s);
+    h->launches += 1;
+    CUDA_CHECK(cudaGetLastError());
+}
+
 // librosa.effects.trim(y)[1] from the per-frame mean squares: frames within 60 dB of the loudest one
 void trim_from_mse(const float* m, int nfr, int Ly, int32_t* out) {
     float mx = 0.f;
@@ -1326,6 +1548,43 @@ int dctts_get_spectrograms(dctts_handle h, const float* wav, int64_t n_samples, 
                  h->feat_window.as<float>(), T, F, n_mels, win, hop, h->voc.ref_db, h->voc.max_db, s);
         h->launches += 2;
         CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int dctts_train_init(dctts_handle h, int32_t B, float dropout_rate) {
+    return guarded(h, [&] { train_init(h, B, dropout_rate); });
+}
+
+int dctts_train_step(dctts_handle h, const int32_t* L, const float* mels, int32_t B, int64_t global_step, uint32_t seed, float lr,
+                     int32_t apply, float* losses_host, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(L && mels && B >= 1 && global_step >= 0, "dctts_train_step: bad arguments");
+        cudaStream_t s = S(h, stream);
+        train_forward_backward(h, reinterpret_cast<const int*>(L), mels, B, seed, losses_host, s);
+        if (apply) train_apply(h, global_step, lr, s);
+    });
+}
+
+int dctts_train_apply(dctts_handle h, int64_t global_step, float lr, void* stream) {
+    return guarded(h, [&] { REQUIRE(global_step >= 0, "dctts_train_apply: bad step"); train_apply(h, global_step, lr, S(h, stream)); });
+}
+
+int dctts_train_grads(dctts_handle h, float** grads, int64_t* count) {
+    return guarded(h, [&] {
+        REQUIRE(h->tr.ready && grads && count, "dctts_train_grads: no training state");
+        *grads = h->tr.grads.as<float>(); *count = h->tr.n_grad;
+    });
+}
+
+int dctts_train_tensor(dctts_handle h, const char* tf_name, int32_t what, float* host_out, int64_t count) {
+    return guarded(h, [&] {
+        REQUIRE(h->tr.ready && tf_name && host_out && what >= 0 && what <= 3, "dctts_train_tensor: bad arguments");
+        auto it = h->tr.tensors.find(tf_name);
+        REQUIRE(it != h->tr.tensors.end(), "dctts_train_tensor: not a Text2Mel variable");
+        REQUIRE(count == it->second.n, "dctts_train_tensor: element count mismatch");
+        const float* src = what == 0 ? it->second.p : what == 1 ? it->second.g : what == 2 ? it->second.m : it->second.v;
+        CUDA_CHECK(cudaDeviceSynchronize());
+        CUDA_CHECK(cudaMemcpy(host_out, src, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
     });
 }
 

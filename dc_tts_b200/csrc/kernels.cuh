@@ -59,6 +59,7 @@ struct ConvArgs {
     int ntaps; ConvTap taps[3];
     RowWin win;
     int Lout, ostride, ooff;       // output row = b*Lout + t*ostride + ooff
+    int accumulate = 0;            // tiled kernels only: Y += result (data gradient on top of the highway path)
 };
 
 // Row-wise epilogue on the pre-LN scratch.
@@ -133,6 +134,46 @@ void feat_frame_mse(const float* y, float* mse, int n, int nfr, cudaStream_t s);
 void feat_run(const float* y, int len, float preemph, float* mag, float* mel, const float* melw, const int* melrange,
               const float2* tw, const float* window, int T, int F, int n_mels, int win, int hop, float ref_db, float max_db,
               cudaStream_t s);
+
+
+// ---- training step (kernels_train.cu; reference train.py mode "train") ----
+struct DropArgs { uint32_t thresh = 0, layer = 0, seed = 0; float scale = 1.f; };   // keep iff mix32(i, layer, seed) >= thresh
+struct BlockBwdArgs {
+    const float* pre; int ldy;         // pre-LN conv output (rows, nconv)
+    const float* gout;                 // gradient w.r.t. the block output (rows, C), dense
+    const float* X; int ldx;           // block input (highway residual), mode 1
+    const float* g1; const float* b1; const float* g2; const float* b2;
+    float* dy;                         // out: gradient w.r.t. the conv output (rows, nconv), leading dimension ldy
+    float* gin;                        // out, mode 1: highway part of the input gradient (rows, C)
+    float* dg1; float* db1; float* dg2; float* db2; float* dbias;   // accumulated (+=)
+    long long rows; int C; int mode; int act;
+    DropArgs drop;
+};
+struct WgradArgs {
+    const float* X; int ldx; const float* dy; int ldy; float* dW; int ldw;
+    long long rows; int L, K, N, ntaps; int shifts[3];
+    int nsplit = 1, rows_per_split = 0;
+};
+struct AttnBwdArgs {
+    const float* gR;                   // (B,T,2d) gradient of [ctx ; Q]
+    const float* Q; int ldq; const float* K; const float* V; int ldkv;
+    const float* align;                // (B,N,T) probabilities of the forward pass
+    const float* gts;                  // (N,T) guided-attention weights
+    float* dS;                         // (B,T,N) scratch
+    float* gQ;                         // (B,T,d)
+    float* gKV;                        // (B,N,2d)
+    int B, T, N, d; float att_scale;   // att_scale = 1 / (B N T)
+};
+struct AdamEntry { float* p; float* g; float* m; float* v; long long n; };
+void launch_train_dropout(float* x, long long n, const DropArgs& d, cudaStream_t s);
+void launch_train_loss(const float* logits, const float* mels, float* dlogits, double* sums, long long n, cudaStream_t s);
+void launch_train_block_bwd(const BlockBwdArgs& a, cudaStream_t s);
+void launch_conv_wgrad(WgradArgs a, cudaStream_t s);
+void launch_transpose_w(const float* W, float* WT, int ntaps, int K, int N, int ldw, cudaStream_t s);
+void launch_attn_bwd(const AttnBwdArgs& a, double* sums, cudaStream_t s);
+void launch_guided_attention(float* W, int N, int T, cudaStream_t s);
+void launch_embed_bwd(const int* ids, const float* g, float* dtable, int rows, int e, cudaStream_t s);
+void launch_adam(const AdamEntry* entries_dev, int n_entries, float lr_t, float beta1, float beta2, float eps, cudaStream_t s);
 
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);

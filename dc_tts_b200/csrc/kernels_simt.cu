@@ -166,6 +166,10 @@ conv_gemm_tiled(const ConvArgs a) {
                     o.y = acc[gi * 4 + ii][gj * 4 + 1] + bsv.y;
                     o.z = acc[gi * 4 + ii][gj * 4 + 2] + bsv.z;
                     o.w = acc[gi * 4 + ii][gj * 4 + 3] + bsv.w;
+                    if (a.accumulate) {
+                        const float4 prev = *reinterpret_cast<const float4*>(yrow + n);
+                        o.x += prev.x; o.y += prev.y; o.z += prev.z; o.w += prev.w;
+                    }
                     *reinterpret_cast<float4*>(yrow + n) = o;
                 }
             }

@@ -263,6 +263,45 @@ class Engine:
                                                      C.byref(t), trim, self._stream()), "dctts_get_spectrograms")
         return mel[:t.value], mag[:t.value], (int(trim[0]), int(trim[1]))
 
+    # ------------------------------------------------------------------ training step (BASELINE config 5)
+    def train_init(self, B, dropout_rate=None):
+        """Allocates the training workspace for batches of B utterances (train.py mode "train", num=1)."""
+        rate = self.hp.dropout_rate if dropout_rate is None else dropout_rate
+        self._check(self._lib.dctts_train_init(self._h, int(B), float(rate)), "dctts_train_init")
+
+    def train_step(self, L, mels, global_step=0, seed=0, lr=None, apply=True):
+        """One Text2Mel optimiser step on L (B, max_N) int32 / mels (B, max_T, n_mels): forward with dropout, losses
+        (train.py:83-99), backward, clip, Adam (train.py:122-132).  Returns {loss, loss_mels, loss_bd1, loss_att}."""
+        L = self._i32(L); mels = self._f32(mels)
+        out = (C.c_float * 4)()
+        self._check(self._lib.dctts_train_step(self._h, _ptr(L), _ptr(mels), L.shape[0], int(global_step), int(seed) & 0xffffffff,
+                                               float(self.hp.lr if lr is None else lr), 1 if apply else 0, out, self._stream()),
+                    "dctts_train_step")
+        return {"loss": out[0], "loss_mels": out[1], "loss_bd1": out[2], "loss_att": out[3]}
+
+    def train_apply(self, global_step, lr=None):
+        self._check(self._lib.dctts_train_apply(self._h, int(global_step), float(self.hp.lr if lr is None else lr), self._stream()),
+                    "dctts_train_apply")
+
+    def train_grads(self):
+        """The flat float32 gradient arena as a CUDA tensor sharing the library's memory (all-reduce it in a
+        data-parallel job between train_step(apply=False) and train_apply)."""
+        ptr, n = C.c_void_p(), C.c_int64(0)
+        self._check(self._lib.dctts_train_grads(self._h, C.byref(ptr), C.byref(n)), "dctts_train_grads")
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
+        return torch.as_tensor(_View(), device="cuda:%d" % self.device)
+
+    def train_tensor(self, name, what="param"):
+        """Copy of a Text2Mel variable / its gradient / Adam m / v, in the TF variable's shape."""
+        from .arch import param_shapes
+        shape = param_shapes()[name]
+        out = np.empty(shape, np.float32)
+        self._check(self._lib.dctts_train_tensor(self._h, name.encode(), {"param": 0, "grad": 1, "m": 2, "v": 3}[what],
+                                                 out.ctypes.data_as(C.c_void_p), out.size), "dctts_train_tensor(%s)" % name)
+        return out
+
     def synthesize_host(self, L_host, Y_host=None, Z_host=None):
         """synthesize.py:45-57 with host (ideally pinned) tensors in and out."""
         L_host = torch.as_tensor(L_host, dtype=torch.int32).contiguous()

@@ -147,6 +147,25 @@ int dctts_spectrogram2wav(dctts_handle h, const float* mag, int32_t B, int32_t T
 int dctts_get_spectrograms(dctts_handle h, const float* wav, int64_t n_samples, int32_t sample_rate, float* mel, float* mag,
                            int32_t t_capacity, int32_t* t_out, int32_t* trim_host, void* stream);
 
+/* ---- training step (BASELINE config 5) --------------------------------------
+ * One optimiser step of the reference's Text2Mel trainer -- graph train.py:43-68 in mode "train" (dropout after
+ * every block, full softmax attention), losses train.py:83-99 (L1 + sigmoid cross-entropy on the mels + guided
+ * attention), elementwise clipping to [-1, 1] and tf.train.AdamOptimizer defaults with the Noam learning rate
+ * (train.py:122-132, utils.py:141-145) -- for fixed-size batches L (B, max_N) int32, mels (B, max_T, n_mels), DEVICE
+ * pointers.  float32 CUDA-core kernels (first correct path).  dctts_train_init allocates the saved activations and the
+ * gradient / Adam arenas and switches the handle to the fp32 kernel set (the optimiser updates the fp32 weights only).
+ * Dropout uses a stateless hash of (element, block index, seed) -- TF's random stream cannot be reproduced.
+ * losses_host (optional): {total, mels L1, binary divergence, guided attention}; reading them synchronises.
+ * apply = 0 leaves the gradients in the arena (dctts_train_grads: one flat device buffer, what a data-parallel job
+ * all-reduces) for dctts_train_apply.  dctts_train_tensor copies a variable (what = 0), its gradient (1) or Adam
+ * moments (2, 3) to the host, in the TF variable's own layout. */
+int dctts_train_init(dctts_handle h, int32_t B, float dropout_rate);
+int dctts_train_step(dctts_handle h, const int32_t* L, const float* mels, int32_t B, int64_t global_step, uint32_t seed, float lr,
+                     int32_t apply, float* losses_host, void* stream);
+int dctts_train_apply(dctts_handle h, int64_t global_step, float lr, void* stream);
+int dctts_train_grads(dctts_handle h, float** grads, int64_t* count);
+int dctts_train_tensor(dctts_handle h, const char* tf_name, int32_t what, float* host_out, int64_t count);
+
 /* ---- utilities ----------------------------------------------------------------- */
 /* Pre-size the workspace (otherwise grown lazily on first use) for batches up to B. */
 int dctts_reserve(dctts_handle h, int32_t max_batch);

@@ -64,6 +64,8 @@ class _State:
     scope = []
     feeds = []
     layer_counts = {}
+    dropout_hook = None
+    dropout_calls = 0
 
 
 def _full(name):
@@ -148,8 +150,15 @@ def layers_conv2d_transpose(inputs, filters, kernel_size, strides=(1, 1), paddin
 
 
 def layers_dropout(inputs, rate=0.5, training=False, name=None):
-    assert not training, "the shim covers the synthesis graph only"
-    return inputs
+    """Identity at inference.  In training TF draws from its own random stream, which cannot be reproduced: the
+    caller plugs a deterministic mask in (`_State.dropout_hook(x, rate, call_index)`), so that the PLACEMENT and
+    scaling of every dropout in the reference's graph is what gets exercised."""
+    if not training or rate == 0:
+        return inputs
+    assert _State.dropout_hook is not None, "training-mode dropout needs a mask hook"
+    out = _State.dropout_hook(np.asarray(inputs), rate, _State.dropout_calls)
+    _State.dropout_calls += 1
+    return _t(out)
 
 
 def contrib_layer_norm(inputs, begin_norm_axis=1, begin_params_axis=-1, scope=None, reuse=None, center=True, scale=True):
@@ -201,7 +210,6 @@ def install(store):
     tf.ones = lambda shape, dtype=np.float32, name=None: _t(np.ones(shape, dtype))
     tf.zeros_like = lambda x, **k: _t(np.zeros_like(np.asarray(x)))
     tf.ones_like = lambda x, **k: _t(np.ones_like(np.asarray(x)))
-    tf.pad = lambda x, paddings, **k: _t(np.pad(np.asarray(x), paddings))
     tf.split = lambda x, n, axis=0, **k: [_t(p) for p in np.split(np.asarray(x), n, axis)]
     tf.expand_dims = lambda x, axis, **k: _t(np.expand_dims(np.asarray(x), axis))
     tf.squeeze = lambda x, axis=None, **k: _t(np.squeeze(np.asarray(x), axis))
@@ -217,7 +225,25 @@ def install(store):
     tf.matmul = matmul
     tf.sequence_mask = sequence_mask
     tf.convert_to_tensor = lambda x, **k: _t(x)
-    tf.nn = types.SimpleNamespace(relu=lambda x, name=None: _t(np.maximum(np.asarray(x), 0)), sigmoid=sigmoid, softmax=softmax,
+    tf.abs = lambda x, **k: _t(np.abs(np.asarray(x)))
+    tf.reduce_mean = lambda x, axis=None, **k: np.asarray(x).mean(axis, dtype=np.float64).astype(np.float32)
+    tf.reduce_sum = lambda x, axis=None, **k: np.asarray(x).sum(axis, dtype=np.float64).astype(np.float32)
+    tf.minimum = lambda a, b, **k: np.minimum(a, b)
+    tf.clip_by_value = lambda x, lo, hi, **k: _t(np.clip(np.asarray(x), lo, hi))
+
+    def _pad(x, paddings, mode="CONSTANT", constant_values=0, **k):
+        return _t(np.pad(np.asarray(x), paddings, mode="constant", constant_values=constant_values))
+    tf.pad = _pad
+
+    class _Adam:                                     # the optimiser itself is not exercised under the shim
+        def __init__(self, learning_rate=None, **k): self.learning_rate = learning_rate
+        def compute_gradients(self, loss): return []
+        def apply_gradients(self, gvs, global_step=None): return None
+    tf.train = types.SimpleNamespace(AdamOptimizer=_Adam)
+    def _bce(logits=None, labels=None, **k):
+        x, z = np.asarray(logits, np.float32), np.asarray(labels, np.float32)
+        return _t(np.maximum(x, 0) - x * z + np.log1p(np.exp(-np.abs(x))))          # TF's documented stable form
+    tf.nn = types.SimpleNamespace(sigmoid_cross_entropy_with_logits=_bce, relu=lambda x, name=None: _t(np.maximum(np.asarray(x), 0)), sigmoid=sigmoid, softmax=softmax,
                                   embedding_lookup=lambda table, ids, **k: _t(np.asarray(table)[np.asarray(ids)]))
     tf.layers = types.SimpleNamespace(conv1d=layers_conv1d, conv2d_transpose=layers_conv2d_transpose, dropout=layers_dropout)
     tf.contrib = types.SimpleNamespace(layers=types.SimpleNamespace(layer_norm=contrib_layer_norm,
@@ -285,3 +311,22 @@ def synthesize(L, steps=None, with_ssrn=True):
         prev = out["max_attentions"][:, j].astype(np.int32)
     Z = run_ssrn(Y)[1] if with_ssrn else None
     return {"Y": Y, "Z": Z, "p_hist": hist, "max_attentions": out["max_attentions"], "alignments": out["alignments"]}
+
+
+def run_train_graph(L, mels, dropout_hook):
+    """The reference's TRAINING graph for Text2Mel (train.py Graph(num=1, mode="train")): get_batch() is replaced
+    by the given fixed-size batch, the optimiser by a stub; returns the three losses and the total."""
+    import train as ref_train
+    _State.scope = []
+    _State.layer_counts = {}
+    _State.dropout_hook = dropout_hook
+    _State.dropout_calls = 0
+    L = _t(np.asarray(L, np.int32)); mels = _t(np.asarray(mels, np.float32))
+    real = ref_train.get_batch
+    ref_train.get_batch = lambda: (L, mels, None, None, 1)
+    try:
+        g = ref_train.Graph(num=1, mode="train")
+    finally:
+        ref_train.get_batch = real
+        _State.dropout_hook = None
+    return {k: float(np.asarray(getattr(g, k))) for k in ("loss", "loss_mels", "loss_bd1", "loss_att")}, _State.dropout_calls

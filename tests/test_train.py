@@ -1,0 +1,136 @@
+"""One Text2Mel training step (BASELINE config 5; reference train.py mode "train", num=1).
+CPU: the autograd oracle against the reference's OWN training graph executed under the TF API stand-in (losses with
+the shared deterministic dropout mask), optimiser arithmetic.  GPU: CUDA losses, every gradient, and the Adam update
+against the oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from dc_tts_b200.hyperparams import Hyperparams as hp
+from dc_tts_b200.params import init_params, synthetic_text
+from oracle import ref_train as rtr
+
+HAVE_REF = os.path.isfile("/root/reference/train.py")
+
+
+def _batch(B, seed=3):
+    L = synthetic_text(B, 50, seed=7)
+    mels = np.random.default_rng(seed).uniform(0, 1, (B, hp.max_T, hp.n_mels)).astype(np.float32)
+    return L, mels
+
+
+def test_dropout_hash_properties():
+    k = rtr.dropout_keep((4, 100, 256), 5, 11, 0.05)
+    assert set(np.unique(k)) == {np.float32(0), np.float32(1 / 0.95)}
+    assert abs((k == 0).mean() - 0.05) < 0.005
+    assert np.array_equal(k, rtr.dropout_keep((4, 100, 256), 5, 11, 0.05))            # stateless
+    assert not np.array_equal(k, rtr.dropout_keep((4, 100, 256), 6, 11, 0.05))        # per block
+    assert not np.array_equal(k, rtr.dropout_keep((4, 100, 256), 5, 12, 0.05))        # per step
+    assert np.all(rtr.dropout_keep((3, 7), 0, 0, 0.0) == 1)
+
+
+def test_schedule_and_guided_attention():
+    assert abs(rtr.learning_rate(0) - 0.001 * 4000 ** 0.5 * 4000 ** -1.5) < 1e-15       # utils.py:141-145
+    assert abs(rtr.learning_rate(3999) - 0.001) < 1e-12 and rtr.learning_rate(15999) == pytest.approx(0.0005)
+    W = rtr.guided_attention()
+    assert W.shape == (hp.max_N, hp.max_T) and W[0, 0] == 0 and W.max() < 1
+    assert abs(W[90, 0] - (1 - np.exp(-(0.5 ** 2) / 0.08))) < 1e-6
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not present on this machine")
+def test_oracle_losses_vs_reference_training_graph():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tf_shim
+    P = init_params(0, "perturbed")
+    tf_shim.install(tf_shim.Store(P))
+    L, mels = _batch(2)
+    for seed, rate in ((11, hp.dropout_rate), (0, 0.0)):
+        import hyperparams as ref_hp
+        ref_hp.Hyperparams.dropout_rate = rate
+        try:
+            hook = lambda x, r, i: x * rtr.dropout_keep(x.shape, i, seed, r)
+            ref, ncalls = tf_shim.run_train_graph(L, mels, hook)
+        finally:
+            ref_hp.Hyperparams.dropout_rate = 0.05
+        assert ncalls == (38 if rate > 0 else 0)                                       # one dropout per block
+        T = {n: torch.tensor(np.asarray(P[n], np.float32)) for n in rtr.text2mel_names()}
+        with torch.no_grad():
+            o = rtr.forward(T, L, mels, seed, rate)
+        for k in ("loss", "loss_mels", "loss_bd1", "loss_att"):
+            assert abs(float(o[k]) - ref[k]) < 2e-6 * max(1.0, abs(ref[k])), (k, float(o[k]), ref[k])
+
+
+def test_oracle_step_arithmetic():
+    P = init_params(0, "perturbed")
+    L, mels = _batch(1)
+    newP, st, info = rtr.train_step(P, L, mels, global_step=0, seed=5)
+    g = info["grads"]
+    assert len(g) == len(rtr.text2mel_names()) == 209 and all(np.abs(v).max() <= 1 for v in g.values())
+    assert np.abs(g["Text2Mel/TextEnc/embed_1/lookup_table"][0]).max() == 0            # zero-padded row gets no gradient
+    n = "Text2Mel/AudioDec/C_11/conv1d/bias"
+    # first Adam step: m = 0.1 g, v = 0.001 g^2, update = lr_t m / (sqrt v + eps) ~ lr sign(g)
+    lr = rtr.learning_rate(0)
+    upd = P[n] - newP[n]
+    big = np.abs(g[n]) > 1e-6
+    assert np.array_equal(np.sign(upd[big]), np.sign(g[n][big]))
+    assert np.all(np.abs(np.abs(upd[big]) / lr - 1) < 0.1)                              # (float32 resolution of the parameter)
+    assert "SSRN/C_1/conv1d/kernel" in newP and newP["SSRN/C_1/conv1d/kernel"] is P["SSRN/C_1/conv1d/kernel"]
+
+
+# ------------------------------------------------------------------------------------------- GPU
+def _compare_grads(eng, grads, names=None, rtol=2e-3):
+    worst = 0.0
+    for n in (names or grads):
+        g = eng.train_tensor(n, "grad")
+        ref = grads[n]
+        assert g.shape == ref.shape, n
+        scale = max(np.abs(ref).max(), 1e-8)
+        err = np.abs(np.clip(g, -1, 1) - ref).max() / scale
+        worst = max(worst, err)
+        assert err < rtol, (n, err, scale)
+    return worst
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,rate,seed", [(2, 0.0, 0), (2, 0.05, 11), (3, 0.05, 4)])
+def test_cuda_train_step_vs_oracle(B, rate, seed):
+    from dc_tts_b200.engine import Engine
+    P = init_params(0, "perturbed")
+    eng = Engine(0)
+    eng.load_params(P)
+    eng.train_init(B, rate)
+    L, mels = _batch(B)
+    newP, st, info = rtr.train_step(P, L, mels, global_step=7, seed=seed, rate=rate)
+    out = eng.train_step(L, mels, global_step=7, seed=seed, apply=False)
+    for k in ("loss", "loss_mels", "loss_bd1", "loss_att"):
+        assert abs(out[k] - info[k]) < 1e-5 * max(1.0, abs(info[k])), (k, out[k], info[k])
+    _compare_grads(eng, info["grads"])
+    assert eng.train_grads().numel() >= 23970288
+    # the optimiser: parameters, m and v after the update
+    eng.train_apply(7)
+    for n in ("Text2Mel/TextEnc/embed_1/lookup_table", "Text2Mel/TextEnc/HC_7/conv1d/kernel", "Text2Mel/AudioEnc/C_1/conv1d/kernel",
+              "Text2Mel/AudioDec/HC_3/H2/gamma", "Text2Mel/AudioDec/C_11/conv1d/bias", "Text2Mel/AudioEnc/HC_9/H1/beta"):
+        m, v = st[n]
+        np.testing.assert_allclose(eng.train_tensor(n, "m"), m, rtol=2e-3, atol=1e-9)
+        np.testing.assert_allclose(eng.train_tensor(n, "v"), v, rtol=4e-3, atol=1e-14)
+        step = np.abs(newP[n] - P[n]).max()
+        assert np.abs(eng.train_tensor(n, "param") - newP[n]).max() <= 0.05 * step + 2.4e-7, n      # + 2 ulp at 1.0
+
+
+@pytest.mark.gpu
+def test_cuda_training_reduces_loss_and_is_deterministic():
+    from dc_tts_b200.engine import Engine
+    P = init_params(1)
+    L, mels = _batch(4, seed=9)
+    runs = []
+    for _ in range(2):
+        eng = Engine(0)
+        eng.load_params(P)
+        eng.train_init(4)
+        runs.append([eng.train_step(L, mels, global_step=4000 + i, seed=i)["loss"] for i in range(8)])
+    assert runs[0][-1] < runs[0][0]                                                    # same batch, lr 1e-3: the loss falls
+    assert np.allclose(runs[0], runs[1], rtol=1e-4)                                    # float atomics reorder sums only
