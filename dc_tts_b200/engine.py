@@ -291,7 +291,7 @@ class Engine:
 
         class _View:
             __cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (ptr.value, False), "version": 2}
-        return torch.as_tensor(_View(), device="cuda:%d" % self.device)
+        return torch.as_tensor(_View(), device=self.device)
 
     def train_tensor(self, name, what="param"):
         """Copy of a Text2Mel variable / its gradient / Adam m / v, in the TF variable's shape."""

@@ -1,0 +1,72 @@
+"""BASELINE config 5: Text2Mel training step, B = 32 per GPU, fixed N = 180 / T = 210, synthetic batch, dropout on,
+data-parallel over the launched ranks (gradient all-reduce of the flat arena over NCCL).  Prints one JSON line.
+    python tools/bench_train.py [--steps 10 --warmup 3 --batch 32]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_train.py"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from dc_tts_b200.engine import Engine
+from dc_tts_b200.hyperparams import Hyperparams as hp
+from dc_tts_b200.params import init_params, synthetic_text
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--steps", type=int, default=10)
+ap.add_argument("--warmup", type=int, default=3)
+ap.add_argument("--batch", type=int, default=32)
+a = ap.parse_args()
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+eng = Engine(local)
+eng.load_params(init_params(0))
+B = a.batch
+eng.train_init(B)
+L = torch.from_numpy(synthetic_text(B, 100, seed=rank)).cuda()
+mels = torch.from_numpy(np.random.default_rng(rank).uniform(0, 1, (B, hp.max_T, hp.n_mels)).astype(np.float32)).cuda()
+grads = eng.train_grads()
+
+
+def step(i):
+    out = eng.train_step(L, mels, global_step=4000 + i, seed=i * world + rank, apply=(world == 1))
+    if world > 1:
+        dist.all_reduce(grads)
+        grads.mul_(1.0 / world)
+        eng.train_apply(4000 + i)
+    return out
+
+
+for i in range(a.warmup):
+    first = step(i)
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n0 = eng.launch_count()
+t0.record()
+for i in range(a.steps):
+    last = step(a.warmup + i)
+t1.record()
+torch.cuda.synchronize()
+ms = torch.tensor([t0.elapsed_time(t1) / a.steps], device="cuda")
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+if rank == 0:
+    ms = float(ms)
+    flops = 3 * 2 * B * (hp.max_N * 17.10e6 + hp.max_T * (4.08e6 + 2.71e6 + 0.09e6))          # fwd MACs x 2 x 3
+    print(json.dumps({"metric": "train_steps_per_sec", "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "ms_per_step": ms,
+                      "mel_frames_per_sec": world * B * hp.max_T * 1e3 / ms, "steps": a.steps, "warmup": a.warmup,
+                      "config": {"workload": "BASELINE config 5: Text2Mel train step (fwd + bwd + clip + Adam), B=%d per GPU, N=180, T=210, dropout %.2f" % (B, hp.dropout_rate),
+                                 "parallelism": "dp%d (all-reduce of %d gradients)" % (world, grads.numel())},
+                      "dtype": "f32 (CUDA-core kernels, first correct path)", "data": "synthetic",
+                      "achieved_tflops": world * flops / (ms * 1e-3) / 1e12, "gpu_launches_per_step": (eng.launch_count() - n0) // a.steps,
+                      "loss_first": first["loss"], "loss_last": last["loss"]}))
+if world > 1:
+    dist.destroy_process_group()
