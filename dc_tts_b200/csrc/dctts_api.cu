@@ -1626,6 +1626,8 @@ uint32_t dctts_crc32c(uint32_t crc, const void* data, int64_t n) {
 int dctts_set_tensor_path(dctts_handle h, int32_t mode) {
     return guarded(h, [&] {
         REQUIRE(mode >= 0 && mode <= 2, "dctts_set_tensor_path: mode must be 0, 1 or 2");
+        REQUIRE(!(h->tr.ready && mode == 1), "dctts_set_tensor_path: this handle has been trained -- its packed fp16 weight planes "
+                "are stale; load the trained variables (dctts_train_tensor) into a new handle for the tcgen05 kernel set");
         if (mode != h->tensor_path && h->ar_exec) {      // the captured AR step depends on the mode
             CUDA_CHECK(cudaDeviceSynchronize());
             cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0;

@@ -134,3 +134,32 @@ def test_cuda_training_reduces_loss_and_is_deterministic():
         runs.append([eng.train_step(L, mels, global_step=4000 + i, seed=i)["loss"] for i in range(8)])
     assert runs[0][-1] < runs[0][0]                                                    # same batch, lr 1e-3: the loss falls
     assert np.allclose(runs[0], runs[1], rtol=1e-4)                                    # float atomics reorder sums only
+
+
+@pytest.mark.gpu
+def test_cuda_train_checkpoint_roundtrip(tmp_path):
+    """train -> save (TF bundle, train.py:152) -> restore into a fresh handle (synthesize.py:31-41) -> same outputs as
+    the trained handle; and the trained handle refuses the stale tcgen05 weight planes."""
+    from dc_tts_b200 import checkpoint as ck
+    from dc_tts_b200.engine import Engine
+    P = init_params(2)
+    L, mels = _batch(2, seed=5)
+    eng = Engine(0)
+    eng.load_params(P)
+    eng.train_init(2)
+    for i in range(3):
+        eng.train_step(L, mels, global_step=4000 + i, seed=i)
+    prefix = eng.save_text2mel_checkpoint(str(tmp_path / "LJ01-1" / "model_gs_004k"), 4003)
+    ck.save_checkpoint(str(tmp_path / "LJ01-2" / "model_gs_000k"), {k: v for k, v in P.items() if k.startswith("SSRN/")})
+    got = ck.load_checkpoint(prefix, names=["gs/global_step", "Text2Mel/AudioDec/C_11/conv1d/bias", "Text2Mel/AudioDec/C_11/conv1d/bias/Adam"])
+    assert int(got["gs/global_step"]) == 4003 and np.abs(got["Text2Mel/AudioDec/C_11/conv1d/bias/Adam"]).max() > 0
+    assert np.abs(got["Text2Mel/AudioDec/C_11/conv1d/bias"] - P["Text2Mel/AudioDec/C_11/conv1d/bias"]).max() > 1e-4   # it moved
+    fresh = Engine(0)
+    fresh.restore(str(tmp_path / "LJ01-1"), str(tmp_path / "LJ01-2"))
+    fresh.set_tensor_path(0)
+    pma = np.zeros(2, np.int32)
+    ya = eng.text2mel_forward(L, mels, pma)[0]
+    yb = fresh.text2mel_forward(L, mels, pma)[0]
+    assert torch.equal(ya, yb)
+    with pytest.raises(RuntimeError):
+        eng.set_tensor_path(1)
