@@ -127,13 +127,13 @@ struct dctts_handle_s {
 
     // training step (Text2Mel, reference train.py mode "train"): see the "training" section below
     struct TrainLayer {
-        LayerDev* l = nullptr; int li = 0; long long rows = 0; int L = 0; const float* in = nullptr; int ld_in = 0;
+        LayerDev* l = nullptr; int li = 0; long long rows = 0; int L = 0, L_in = 0, ld_out = 0; const float* in = nullptr; int ld_in = 0;
         float* pre = nullptr; float* out = nullptr; int extra_shift = 0; bool need_dgrad = true;
         float *dW = nullptr, *dbias = nullptr, *dg1 = nullptr, *db1 = nullptr, *dg2 = nullptr, *db2 = nullptr;
     };
-    struct TrainTensor { float* p; float* g; float* m; float* v; long long n; };
+    struct TrainTensor { float* p; float* g; float* m; float* v; long long n; int layout, d0, d1, d2, ld; };
     struct {
-        bool ready = false; int B = 0; float rate = 0.f;
+        bool ready = false; int B = 0, num = 1, T_in = 0; float rate = 0.f;
         std::vector<TrainLayer> layers;
         std::map<std::string, TrainTensor> tensors;            // by TF variable name
         DevBuf pre, out, emb, R, align, dS, gbuf[4], dy, wT, zeros, gts, sums, ids, grads, mom, vel, entries;
@@ -972,37 +972,45 @@ void ensure_scratch(H* h, size_t bytes) {
     h->scratch.ensure(bytes);
 }
 
-// ---------------------------------------------------------------------------- training (Text2Mel)
-// One optimiser step of the reference's Text2Mel trainer (train.py:43-68 graph, losses :83-99, Adam :122-132) for
-// fixed-size batches (B, max_N) / (B, max_T, n_mels) -- BASELINE config 5.  Forward = the fp32 block kernels with every
-// pre-LN tensor kept; backward = kernels_train.cu.  Gradients, Adam moments and the pointers of all 23.97 M Text2Mel
-// variables live in three arenas with identical offsets (the gradient arena is what a data-parallel all-reduce sums).
-void train_init(H* h, int B, float rate) {
+// ---------------------------------------------------------------------------- training
+// One optimiser step of the reference's trainers (train.py mode "train"): num = 1 Text2Mel (graph :43-68, losses :83-99),
+// num = 2 SSRN on ground-truth mels (:69-72, losses :100-108); Adam + clipping :122-132 -- fixed-size batches (BASELINE
+// config 5).  Forward = the fp32 block kernels with every pre-LN tensor kept; backward = kernels_train.cu.  Gradients, Adam
+// moments and the pointers of all trained variables live in three arenas with identical offsets (the gradient arena is
+// what a data-parallel all-reduce sums).  Activation / gradient rows use a leading dimension rounded to 4 floats (F = 1025).
+void train_init(H* h, int B, float rate, int num, int T_in) {
     REQUIRE(h->committed, "dctts_train_init: parameters must be committed first");
-    REQUIRE(B >= 1 && rate >= 0.f && rate < 1.f, "dctts_train_init: bad arguments");
+    REQUIRE(B >= 1 && rate >= 0.f && rate < 1.f && (num == 1 || num == 2) && T_in >= 1, "dctts_train_init: bad arguments");
     auto& tr = h->tr;
-    if (tr.ready && tr.B == B) { tr.rate = rate; return; }
+    if (tr.ready && tr.B == B && tr.num == num && tr.T_in == T_in) { tr.rate = rate; return; }
     CUDA_CHECK(cudaDeviceSynchronize());
     if (h->ar_exec) { cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
     h->tensor_path = 0;            // the optimiser updates the fp32 weights only: this handle stops using the packed fp16 planes
+    tr.ready = false;
     const dctts_hparams& hp = h->hp;
-    const int N = hp.max_N, T = hp.max_T, d = hp.d;
+    const int N = hp.max_N, T = T_in, d = hp.d;
     tr.layers.clear(); tr.tensors.clear();
-    std::vector<LayerDev>* nets[3] = {&h->textenc, &h->audioenc, &h->audiodec};
-    size_t pre_f = 0, out_f = 0;
+    std::vector<std::vector<LayerDev>*> nets;
+    if (num == 1) nets = {&h->textenc, &h->audioenc, &h->audiodec}; else nets = {&h->ssrn};
+    size_t pre_f = 0, out_f = 0, g_f = 0, dy_f = 0, wt_f = 0;
     long long n_grad = 0;
     auto reserve = [&](long long n) { long long o = n_grad; n_grad += (n + 3) / 4 * 4; return o; };
     struct Off { long long W, bias, g1, b1, g2, b2; };
     std::vector<Off> offs;
-    const long long table_off = reserve((long long)hp.vocab_size * hp.e);
+    const long long table_off = num == 1 ? reserve((long long)hp.vocab_size * hp.e) : 0;
     int li = 0;
-    for (int net = 0; net < 3; ++net) {
+    for (size_t net = 0; net < nets.size(); ++net) {
         tr.first[net] = li;
+        int L = (num == 1 && net == 0) ? N : T;
         for (auto& l : *nets[net]) {
             H::TrainLayer t;
-            t.l = &l; t.li = li++; t.L = net == 0 ? N : T; t.rows = (long long)B * t.L;
-            REQUIRE(l.kind != K_D && l.ldw == l.nconv, "training: unexpected layer layout");
-            pre_f += (size_t)t.rows * l.ldw; out_f += (size_t)t.rows * l.cout;
+            t.l = &l; t.li = li++; t.L_in = L;
+            if (l.kind == K_D) L *= 2;
+            t.L = L; t.rows = (long long)B * L; t.ld_out = roundup(l.cout, 4);
+            pre_f += (size_t)t.rows * l.ldw; out_f += (size_t)t.rows * t.ld_out;
+            g_f = std::max(g_f, (size_t)t.rows * std::max(t.ld_out, roundup(l.cin, 4)));
+            dy_f = std::max(dy_f, (size_t)t.rows * l.ldw);
+            wt_f = std::max(wt_f, (size_t)l.size * l.ldw * roundup(l.cin, 4));
             Off o{};
             o.W = reserve((long long)l.size * l.cin * l.ldw); o.bias = reserve(l.ldw);
             o.g1 = reserve(l.cout); o.b1 = reserve(l.cout);
@@ -1013,52 +1021,65 @@ void train_init(H* h, int B, float rate) {
         tr.last[net] = li - 1;
     }
     tr.pre.ensure(pre_f * sizeof(float)); tr.out.ensure(out_f * sizeof(float));
-    tr.emb.ensure((size_t)B * N * hp.e * sizeof(float)); tr.R.ensure((size_t)B * T * 2 * d * sizeof(float));
-    tr.align.ensure((size_t)B * N * T * sizeof(float)); tr.dS.ensure((size_t)B * T * N * sizeof(float));
-    const size_t gmax = (size_t)B * std::max(N, T) * std::max(2 * d, hp.e);
-    for (auto& g : tr.gbuf) g.ensure(gmax * sizeof(float));
-    tr.dy.ensure((size_t)B * std::max(N, T) * 4 * d * sizeof(float));
-    tr.wT.ensure((size_t)3 * 4 * d * 2 * d * sizeof(float));
+    if (num == 1) {
+        tr.emb.ensure((size_t)B * N * hp.e * sizeof(float)); tr.R.ensure((size_t)B * T * 2 * d * sizeof(float));
+        tr.align.ensure((size_t)B * N * T * sizeof(float)); tr.dS.ensure((size_t)B * T * N * sizeof(float));
+        g_f = std::max(g_f, (size_t)B * std::max(N, T) * (size_t)std::max(2 * d, hp.e));
+        tr.gts.ensure((size_t)N * T * sizeof(float)); launch_guided_attention(tr.gts.as<float>(), N, T, h->stream);
+    }
+    for (auto& g : tr.gbuf) g.ensure(g_f * sizeof(float));
+    tr.dy.ensure(dy_f * sizeof(float)); tr.wT.ensure(wt_f * sizeof(float));
     tr.zeros.ensure(4096 * sizeof(float)); CUDA_CHECK(cudaMemset(tr.zeros.p, 0, 4096 * sizeof(float)));
-    tr.gts.ensure((size_t)N * T * sizeof(float)); launch_guided_attention(tr.gts.as<float>(), N, T, h->stream);
-    tr.sums.ensure(4 * sizeof(double)); tr.ids.ensure((size_t)B * N * sizeof(int));
+    tr.sums.ensure(4 * sizeof(double));
     tr.grads.ensure(n_grad * sizeof(float)); tr.mom.ensure(n_grad * sizeof(float)); tr.vel.ensure(n_grad * sizeof(float));
     CUDA_CHECK(cudaMemset(tr.grads.p, 0, n_grad * sizeof(float)));
     CUDA_CHECK(cudaMemset(tr.mom.p, 0, n_grad * sizeof(float))); CUDA_CHECK(cudaMemset(tr.vel.p, 0, n_grad * sizeof(float)));
     tr.n_grad = n_grad;
     float* G = tr.grads.as<float>(); float* M = tr.mom.as<float>(); float* V = tr.vel.as<float>();
     std::vector<AdamEntry> entries;
-    auto reg = [&](const std::string& name, float* p, long long off, long long n) {
-        tr.tensors[name] = H::TrainTensor{p, G + off, M + off, V + off, n};
+    // layout: 0 = the TF variable's own layout, 1 = [k][cin][ldw] with ldw > n columns, 2 = transposed conv [tap][cin][ldw] vs TF [1][k][cout][cin]
+    auto reg = [&](const std::string& name, float* p, long long off, long long n, int layout = 0, int d0 = 0, int d1 = 0, int d2 = 0, int ld = 0) {
+        tr.tensors[name] = H::TrainTensor{p, G + off, M + off, V + off, n, layout, d0, d1, d2, ld};
         entries.push_back(AdamEntry{p, G + off, M + off, V + off, n});
         return G + off;
     };
-    tr.d_table = reg("Text2Mel/TextEnc/embed_1/lookup_table", h->embed_table, table_off, (long long)hp.vocab_size * hp.e);
+    if (num == 1) tr.d_table = reg("Text2Mel/TextEnc/embed_1/lookup_table", h->embed_table, table_off, (long long)hp.vocab_size * hp.e);
     float* pre = tr.pre.as<float>(); float* out = tr.out.as<float>();
     for (size_t i = 0; i < tr.layers.size(); ++i) {
         auto& t = tr.layers[i]; LayerDev& l = *t.l; const Off& o = offs[i];
         t.pre = pre; pre += (size_t)t.rows * l.ldw;
-        t.out = out; out += (size_t)t.rows * l.cout;
-        t.dW = reg(l.scope + "/conv1d/kernel", l.W, o.W, (long long)l.size * l.cin * l.ldw);
-        t.dbias = reg(l.scope + "/conv1d/bias", l.bias, o.bias, l.ldw);
+        t.out = out; out += (size_t)t.rows * t.ld_out;
+        const long long wn = (long long)l.size * l.cin * l.ldw;
+        if (l.kind == K_D) {
+            t.dW = reg(l.scope + "/conv2d_transpose/kernel", l.W, o.W, wn, 2, l.size, l.cin, l.cout, l.ldw);
+            t.dbias = reg(l.scope + "/conv2d_transpose/bias", l.bias, o.bias, l.ldw, l.ldw != l.cout ? 1 : 0, 1, 1, l.cout, l.ldw);
+        } else {
+            t.dW = reg(l.scope + "/conv1d/kernel", l.W, o.W, wn, l.ldw != l.nconv ? 1 : 0, l.size, l.cin, l.nconv, l.ldw);
+            t.dbias = reg(l.scope + "/conv1d/bias", l.bias, o.bias, l.ldw, l.ldw != l.nconv ? 1 : 0, 1, 1, l.nconv, l.ldw);
+        }
         const std::string n1 = l.kind == K_HC ? "/H1" : "/normalize";
         t.dg1 = reg(l.scope + n1 + "/gamma", l.g1, o.g1, l.cout); t.db1 = reg(l.scope + n1 + "/beta", l.b1, o.b1, l.cout);
         if (l.kind == K_HC) { t.dg2 = reg(l.scope + "/H2/gamma", l.g2, o.g2, l.cout); t.db2 = reg(l.scope + "/H2/beta", l.b2, o.b2, l.cout); }
     }
-    // inputs: TextEnc <- embedding; AudioEnc <- mels shifted by one frame (train.py:51), set per step; AudioDec <- R
-    for (int net = 0; net < 3; ++net)
+    // inputs: each block reads the previous block's output; the first block of a network reads the embedding (TextEnc), the
+    // mels shifted by one frame (AudioEnc, train.py:51; set per step), R (AudioDec) or the ground-truth mels (SSRN, per step)
+    for (size_t net = 0; net < nets.size(); ++net)
         for (int i = tr.first[net]; i <= tr.last[net]; ++i) {
             auto& t = tr.layers[i];
-            if (i > tr.first[net]) { t.in = tr.layers[i - 1].out; t.ld_in = tr.layers[i - 1].l->cout; }
+            if (i > tr.first[net]) { t.in = tr.layers[i - 1].out; t.ld_in = tr.layers[i - 1].ld_out; }
         }
-    tr.layers[tr.first[0]].in = tr.emb.as<float>(); tr.layers[tr.first[0]].ld_in = hp.e;
-    tr.layers[tr.first[1]].ld_in = hp.n_mels; tr.layers[tr.first[1]].extra_shift = -1; tr.layers[tr.first[1]].need_dgrad = false;
-    tr.layers[tr.first[2]].in = tr.R.as<float>(); tr.layers[tr.first[2]].ld_in = 2 * d;
+    if (num == 1) {
+        tr.layers[tr.first[0]].in = tr.emb.as<float>(); tr.layers[tr.first[0]].ld_in = hp.e;
+        tr.layers[tr.first[1]].ld_in = hp.n_mels; tr.layers[tr.first[1]].extra_shift = -1; tr.layers[tr.first[1]].need_dgrad = false;
+        tr.layers[tr.first[2]].in = tr.R.as<float>(); tr.layers[tr.first[2]].ld_in = 2 * d;
+    } else {
+        tr.layers[0].ld_in = hp.n_mels; tr.layers[0].need_dgrad = false;
+    }
     tr.entries.ensure(entries.size() * sizeof(AdamEntry));
     CUDA_CHECK(cudaMemcpy(tr.entries.p, entries.data(), entries.size() * sizeof(AdamEntry), cudaMemcpyHostToDevice));
     tr.n_entries = (int)entries.size();
     CUDA_CHECK(cudaStreamSynchronize(h->stream));
-    tr.B = B; tr.rate = rate; tr.ready = true;
+    tr.B = B; tr.rate = rate; tr.num = num; tr.T_in = T_in; tr.ready = true;
 }
 
 void layer_shifts(const LayerDev& l, int extra, int* shifts) {
@@ -1076,92 +1097,154 @@ DropArgs drop_args(float rate, int li, uint32_t seed) {
     return d;
 }
 
+// forward of blocks [first, last], every pre-LN tensor and block output kept
+void train_fwd(H* h, Launch& lc, int first, int last, int B, uint32_t seed) {
+    auto& tr = h->tr;
+    cudaStream_t s = lc.s;
+    for (int i = first; i <= last; ++i) {
+        auto& t = tr.layers[i]; const LayerDev& l = *t.l;
+        ConvArgs c{};
+        c.X = t.in; c.ldx = t.ld_in; c.Y = t.pre; c.ldy = l.ldw; c.bias = l.bias; c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
+        c.win = RowWin{B, t.L_in, t.L_in, nullptr};
+        LnArgs n{};
+        n.Y = t.pre; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2; n.X = t.in; n.ldx = t.ld_in;
+        n.out = t.out; n.ldo = t.ld_out; n.C = l.cout; n.mode = l.kind == K_HC ? 1 : 0; n.act = l.kind == K_D ? 0 : l.act;
+        n.win = RowWin{B, t.L, t.L, nullptr};
+        if (l.kind == K_D) {                                        // modules.py:232-239, like run_deconv
+            const size_t tapsz = (size_t)l.cin * l.ldw;
+            c.Lout = 2 * t.L_in; c.ostride = 2;
+            c.ntaps = 2; c.taps[0] = ConvTap{l.W + 0 * tapsz, 0}; c.taps[1] = ConvTap{l.W + 2 * tapsz, -1}; c.ooff = 0;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+            c.ntaps = 1; c.taps[0] = ConvTap{l.W + 1 * tapsz, 0}; c.ooff = 1;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+        } else {
+            c.ntaps = l.size;
+            int sh[3]; layer_shifts(l, t.extra_shift, sh);
+            for (int j = 0; j < l.size; ++j) { c.taps[j].W = l.W + (size_t)j * l.cin * l.ldw; c.taps[j].shift = sh[j]; }
+            c.Lout = t.L; c.ostride = 1; c.ooff = 0;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+        }
+        launch_ln_rows(n, s); lc.count();
+        if (tr.rate > 0.f) { launch_train_dropout(t.out, t.rows, l.cout, t.ld_out, drop_args(tr.rate, t.li, seed), s); lc.count(); }
+    }
+}
+
+// backward of blocks [first, last]: g_cur holds the gradient w.r.t. the last block's output; returns the buffer with the
+// gradient w.r.t. the first block's input (g_cur and g_other alternate)
+float* train_bwd(H* h, Launch& lc, int first, int last, int B, uint32_t seed, float* g_cur, float* g_other) {
+    auto& tr = h->tr;
+    cudaStream_t s = lc.s;
+    float* dy = tr.dy.as<float>(); float* wT = tr.wT.as<float>();
+    for (int i = last; i >= first; --i) {
+        auto& t = tr.layers[i]; const LayerDev& l = *t.l;
+        const int cin_p = roundup(l.cin, 4);
+        BlockBwdArgs a{};
+        a.pre = t.pre; a.ldy = l.ldw; a.gout = g_cur; a.ldg = t.ld_out; a.X = t.in; a.ldx = t.ld_in;
+        a.g1 = l.g1; a.b1 = l.b1; a.g2 = l.g2; a.b2 = l.b2; a.dy = dy; a.gin = g_other;
+        a.dg1 = t.dg1; a.db1 = t.db1; a.dg2 = t.dg2; a.db2 = t.db2; a.dbias = t.dbias;
+        a.rows = t.rows; a.C = l.cout; a.mode = l.kind == K_HC ? 1 : 0; a.act = l.kind == K_D ? 0 : l.act;
+        a.drop = drop_args(tr.rate, t.li, seed);
+        launch_train_block_bwd(a, s); lc.count();
+        if (t.need_dgrad) {
+            if (cin_p != l.cin) CUDA_CHECK(cudaMemsetAsync(wT, 0, (size_t)l.size * l.ldw * cin_p * sizeof(float), s));   // zero pad columns
+            launch_transpose_w(l.W, wT, l.size, l.cin, l.ldw, l.ldw, cin_p, s); lc.count();
+        }
+        ConvArgs c{};
+        c.Y = g_other; c.ldy = cin_p; c.bias = tr.zeros.as<float>(); c.K = l.nconv; c.N = l.cin; c.ldw = cin_p;
+        c.win = RowWin{B, t.L_in, t.L_in, nullptr}; c.Lout = t.L_in; c.ostride = 1; c.ooff = 0;
+        const size_t tsz = (size_t)l.ldw * cin_p;                    // one transposed tap: [ldw rows (conv channels)][cin_p]
+        WgradArgs w{};
+        w.X = t.in; w.ldx = t.ld_in; w.ldw = l.ldw; w.L = t.L_in; w.K = l.cin;
+        if (l.kind == K_D) {
+            // rows of dy viewed as (B * L_in, 2 ldw): columns [0, C) belong to output row 2t, [ldw, ldw + C) to row 2t + 1.
+            // forward: out[2t] = W0 x[t] + W2 x[t-1], out[2t+1] = W1 x[t]
+            const size_t tapsz = (size_t)l.cin * l.ldw;
+            w.rows = (long long)B * t.L_in; w.ldy = 2 * l.ldw; w.N = l.cout; w.ntaps = 1;
+            w.dy = dy;         w.dW = t.dW + 0 * tapsz; w.shifts[0] = 0;  launch_conv_wgrad(w, s); lc.count();
+            w.dy = dy;         w.dW = t.dW + 2 * tapsz; w.shifts[0] = -1; launch_conv_wgrad(w, s); lc.count();
+            w.dy = dy + l.ldw; w.dW = t.dW + 1 * tapsz; w.shifts[0] = 0;  launch_conv_wgrad(w, s); lc.count();
+            if (!t.need_dgrad) continue;
+            // dx[u] = dyE[u] W0^T + dyE[u+1] W2^T + dyO[u] W1^T
+            c.K = l.cout;
+            c.X = dy; c.ldx = 2 * l.ldw; c.ntaps = 2; c.taps[0] = ConvTap{wT + 0 * tsz, 0}; c.taps[1] = ConvTap{wT + 2 * tsz, 1}; c.accumulate = 0;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+            c.X = dy + l.ldw; c.ntaps = 1; c.taps[0] = ConvTap{wT + 1 * tsz, 0}; c.accumulate = 1;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+        } else {
+            w.rows = t.rows; w.dy = dy; w.ldy = l.ldw; w.dW = t.dW; w.N = l.nconv; w.ntaps = l.size;
+            layer_shifts(l, t.extra_shift, w.shifts);
+            launch_conv_wgrad(w, s); lc.count();
+            if (!t.need_dgrad) continue;
+            c.X = dy; c.ldx = l.ldw; c.ntaps = l.size;
+            for (int j = 0; j < l.size; ++j) { c.taps[j].W = wT + (size_t)j * tsz; c.taps[j].shift = -w.shifts[j]; }
+            c.accumulate = a.mode;
+            launch_conv_gemm(c, s, 0, false); lc.count();
+        }
+        std::swap(g_cur, g_other);
+    }
+    return g_cur;
+}
+
+void train_read_losses(H* h, float* losses_host, double n_el, double n_att, cudaStream_t s) {
+    if (!losses_host) return;
+    double sums[4];
+    CUDA_CHECK(cudaMemcpyAsync(sums, h->tr.sums.p, sizeof(sums), cudaMemcpyDeviceToHost, s));
+    CUDA_CHECK(cudaStreamSynchronize(s));
+    losses_host[1] = (float)(sums[0] / n_el);
+    losses_host[2] = (float)(sums[1] / n_el);
+    losses_host[3] = n_att > 0 ? (float)(sums[2] / n_att) : 0.f;
+    losses_host[0] = losses_host[1] + losses_host[2] + losses_host[3];
+}
+
 void train_forward_backward(H* h, const int* L, const float* mels, int B, uint32_t seed, float* losses_host, cudaStream_t s) {
     auto& tr = h->tr;
-    REQUIRE(tr.ready && tr.B == B, "dctts_train_step: call dctts_train_init with this batch size first");
+    REQUIRE(tr.ready && tr.num == 1 && tr.B == B, "dctts_train_step: call dctts_train_init with this batch size first");
     const dctts_hparams& hp = h->hp;
     const int N = hp.max_N, T = hp.max_T, d = hp.d;
     Launch lc{h, s};
     CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
     tr.layers[tr.first[1]].in = mels;
-    // ---------------- forward, every pre-LN tensor and block output kept ----------------
     launch_embed(L, h->embed_table, tr.emb.as<float>(), B * N, hp.e, s); lc.count();
-    auto fwd = [&](int first, int last) {
-        for (int i = first; i <= last; ++i) {
-            auto& t = tr.layers[i]; const LayerDev& l = *t.l;
-            ConvArgs c{};
-            c.X = t.in; c.ldx = t.ld_in; c.Y = t.pre; c.ldy = l.ldw; c.bias = l.bias; c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
-            c.ntaps = l.size;
-            int sh[3]; layer_shifts(l, t.extra_shift, sh);
-            for (int j = 0; j < l.size; ++j) { c.taps[j].W = l.W + (size_t)j * l.cin * l.ldw; c.taps[j].shift = sh[j]; }
-            c.win = RowWin{B, t.L, t.L, nullptr}; c.Lout = t.L; c.ostride = 1; c.ooff = 0;
-            launch_conv_gemm(c, s, 0, false); lc.count();
-            LnArgs n{};
-            n.Y = t.pre; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2; n.X = t.in; n.ldx = t.ld_in;
-            n.out = t.out; n.ldo = l.cout; n.C = l.cout; n.mode = l.kind == K_HC ? 1 : 0; n.act = l.act; n.win = c.win;
-            launch_ln_rows(n, s); lc.count();
-            if (tr.rate > 0.f) { launch_train_dropout(t.out, t.rows * l.cout, drop_args(tr.rate, t.li, seed), s); lc.count(); }
-        }
-    };
-    fwd(tr.first[0], tr.last[0]);
-    fwd(tr.first[1], tr.last[1]);
+    train_fwd(h, lc, tr.first[0], tr.last[0], B, seed);
+    train_fwd(h, lc, tr.first[1], tr.last[1], B, seed);
     const float* KV = tr.layers[tr.last[0]].out;               // (B, N, 2d): K | V
     const float* Q = tr.layers[tr.last[1]].out;                // (B, T, d)
     run_attention(lc, Q, d, KV, 2 * d, KV + d, 2 * d, RowWin{B, T, T, nullptr}, N, nullptr, tr.R.as<float>(), tr.align.as<float>(),
                   nullptr, nullptr, nullptr);
-    fwd(tr.first[2], tr.last[2]);
-    // ---------------- losses ----------------
-    const float* logits = tr.layers[tr.last[2]].out;
-    const long long n_el = (long long)B * T * hp.n_mels;
-    launch_train_loss(logits, mels, tr.gbuf[0].as<float>(), tr.sums.as<double>(), n_el, s); lc.count();
-    // ---------------- backward ----------------
-    auto bwd = [&](int first, int last, float* g_cur, float* g_other) -> float* {
-        for (int i = last; i >= first; --i) {
-            auto& t = tr.layers[i]; const LayerDev& l = *t.l;
-            BlockBwdArgs a{};
-            a.pre = t.pre; a.ldy = l.ldw; a.gout = g_cur; a.X = t.in; a.ldx = t.ld_in;
-            a.g1 = l.g1; a.b1 = l.b1; a.g2 = l.g2; a.b2 = l.b2; a.dy = tr.dy.as<float>(); a.gin = g_other;
-            a.dg1 = t.dg1; a.db1 = t.db1; a.dg2 = t.dg2; a.db2 = t.db2; a.dbias = t.dbias;
-            a.rows = t.rows; a.C = l.cout; a.mode = l.kind == K_HC ? 1 : 0; a.act = l.act; a.drop = drop_args(tr.rate, t.li, seed);
-            launch_train_block_bwd(a, s); lc.count();
-            WgradArgs w{};
-            w.X = t.in; w.ldx = t.ld_in; w.dy = tr.dy.as<float>(); w.ldy = l.ldw; w.dW = t.dW; w.ldw = l.ldw;
-            w.rows = t.rows; w.L = t.L; w.K = l.cin; w.N = l.nconv; w.ntaps = l.size;
-            layer_shifts(l, t.extra_shift, w.shifts);
-            launch_conv_wgrad(w, s); lc.count();
-            if (!t.need_dgrad) continue;
-            launch_transpose_w(l.W, tr.wT.as<float>(), l.size, l.cin, l.nconv, l.ldw, s); lc.count();
-            ConvArgs c{};
-            c.X = tr.dy.as<float>(); c.ldx = l.ldw; c.Y = g_other; c.ldy = l.cin; c.bias = tr.zeros.as<float>();
-            c.K = l.nconv; c.N = l.cin; c.ldw = l.cin; c.ntaps = l.size;
-            for (int j = 0; j < l.size; ++j) { c.taps[j].W = tr.wT.as<float>() + (size_t)j * l.nconv * l.cin; c.taps[j].shift = -w.shifts[j]; }
-            c.win = RowWin{B, t.L, t.L, nullptr}; c.Lout = t.L; c.ostride = 1; c.ooff = 0; c.accumulate = a.mode;
-            launch_conv_gemm(c, s, 0, false); lc.count();
-            std::swap(g_cur, g_other);
-        }
-        return g_cur;
-    };
-    float* gR = bwd(tr.first[2], tr.last[2], tr.gbuf[0].as<float>(), tr.gbuf[1].as<float>());
+    train_fwd(h, lc, tr.first[2], tr.last[2], B, seed);
+    const auto& lastl = tr.layers[tr.last[2]];
+    launch_train_loss(lastl.out, lastl.ld_out, mels, tr.gbuf[0].as<float>(), lastl.ld_out, tr.sums.as<double>(), (long long)B * T, hp.n_mels, s);
+    lc.count();
+    float* gR = train_bwd(h, lc, tr.first[2], tr.last[2], B, seed, tr.gbuf[0].as<float>(), tr.gbuf[1].as<float>());
     AttnBwdArgs ab{};
     ab.gR = gR; ab.Q = Q; ab.ldq = d; ab.K = KV; ab.V = KV + d; ab.ldkv = 2 * d; ab.align = tr.align.as<float>();
     ab.gts = tr.gts.as<float>(); ab.dS = tr.dS.as<float>(); ab.gQ = tr.gbuf[2].as<float>(); ab.gKV = tr.gbuf[3].as<float>();
     ab.B = B; ab.T = T; ab.N = N; ab.d = d; ab.att_scale = 1.0f / ((float)B * (float)N * (float)T);
     launch_attn_bwd(ab, tr.sums.as<double>(), s); lc.count(3);
     float* free_a = (gR == tr.gbuf[0].as<float>()) ? tr.gbuf[1].as<float>() : tr.gbuf[0].as<float>();
-    bwd(tr.first[1], tr.last[1], tr.gbuf[2].as<float>(), free_a);
-    float* gEmb = bwd(tr.first[0], tr.last[0], tr.gbuf[3].as<float>(), free_a);
+    train_bwd(h, lc, tr.first[1], tr.last[1], B, seed, tr.gbuf[2].as<float>(), free_a);
+    float* gEmb = train_bwd(h, lc, tr.first[0], tr.last[0], B, seed, tr.gbuf[3].as<float>(), free_a);
     launch_embed_bwd(L, gEmb, tr.d_table, B * N, hp.e, s); lc.count();
     CUDA_CHECK(cudaGetLastError());
-    if (losses_host) {
-        double sums[4];
-        CUDA_CHECK(cudaMemcpyAsync(sums, tr.sums.p, sizeof(sums), cudaMemcpyDeviceToHost, s));
-        CUDA_CHECK(cudaStreamSynchronize(s));
-        losses_host[1] = (float)(sums[0] / (double)n_el);
-        losses_host[2] = (float)(sums[1] / (double)n_el);
-        losses_host[3] = (float)(sums[2] / ((double)B * N * T));
-        losses_host[0] = losses_host[1] + losses_host[2] + losses_host[3];
-    }
+    train_read_losses(h, losses_host, (double)B * T * hp.n_mels, (double)B * N * T, s);
+}
+
+// SSRN (num = 2): ground-truth mels in, L1 + binary divergence against the linear magnitudes (train.py:100-108)
+void train_forward_backward_ssrn(H* h, const float* mels, const float* mags, int B, uint32_t seed, float* losses_host, cudaStream_t s) {
+    auto& tr = h->tr;
+    REQUIRE(tr.ready && tr.num == 2 && tr.B == B, "dctts_train_step_ssrn: call dctts_train_init_ssrn with this batch size first");
+    Launch lc{h, s};
+    CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
+    CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
+    tr.layers[0].in = mels;
+    const int last = (int)tr.layers.size() - 1;
+    train_fwd(h, lc, 0, last, B, seed);
+    const auto& ll = tr.layers[last];
+    launch_train_loss(ll.out, ll.ld_out, mags, tr.gbuf[0].as<float>(), ll.ld_out, tr.sums.as<double>(), ll.rows, ll.l->cout, s); lc.count();
+    train_bwd(h, lc, 0, last, B, seed, tr.gbuf[0].as<float>(), tr.gbuf[1].as<float>());
+    CUDA_CHECK(cudaGetLastError());
+    train_read_losses(h, losses_host, (double)ll.rows * ll.l->cout, 0.0, s);
 }
 
 void train_apply(H* h, long long global_step, float lr, cudaStream_t s) {
@@ -1552,7 +1635,7 @@ int dctts_get_spectrograms(dctts_handle h, const float* wav, int64_t n_samples, 
 }
 
 int dctts_train_init(dctts_handle h, int32_t B, float dropout_rate) {
-    return guarded(h, [&] { train_init(h, B, dropout_rate); });
+    return guarded(h, [&] { train_init(h, B, dropout_rate, 1, h->hp.max_T); });
 }
 
 int dctts_train_step(dctts_handle h, const int32_t* L, const float* mels, int32_t B, int64_t global_step, uint32_t seed, float lr,
@@ -1576,15 +1659,45 @@ int dctts_train_grads(dctts_handle h, float** grads, int64_t* count) {
     });
 }
 
+int dctts_train_init_ssrn(dctts_handle h, int32_t B, int32_t T, float dropout_rate) {
+    return guarded(h, [&] { train_init(h, B, dropout_rate, 2, T); });
+}
+
+int dctts_train_step_ssrn(dctts_handle h, const float* mels, const float* mags, int32_t B, int64_t global_step, uint32_t seed, float lr,
+                          int32_t apply, float* losses_host, void* stream) {
+    return guarded(h, [&] {
+        REQUIRE(mels && mags && B >= 1 && global_step >= 0, "dctts_train_step_ssrn: bad arguments");
+        cudaStream_t s = S(h, stream);
+        train_forward_backward_ssrn(h, mels, mags, B, seed, losses_host, s);
+        if (apply) train_apply(h, global_step, lr, s);
+    });
+}
+
 int dctts_train_tensor(dctts_handle h, const char* tf_name, int32_t what, float* host_out, int64_t count) {
     return guarded(h, [&] {
         REQUIRE(h->tr.ready && tf_name && host_out && what >= 0 && what <= 3, "dctts_train_tensor: bad arguments");
         auto it = h->tr.tensors.find(tf_name);
-        REQUIRE(it != h->tr.tensors.end(), "dctts_train_tensor: not a Text2Mel variable");
-        REQUIRE(count == it->second.n, "dctts_train_tensor: element count mismatch");
-        const float* src = what == 0 ? it->second.p : what == 1 ? it->second.g : what == 2 ? it->second.m : it->second.v;
+        REQUIRE(it != h->tr.tensors.end(), "dctts_train_tensor: not a variable of the network being trained");
+        const auto& t = it->second;
+        const long long logical = t.layout == 0 ? t.n : (long long)t.d0 * t.d1 * t.d2;
+        REQUIRE(count == logical, "dctts_train_tensor: element count mismatch");
+        const float* src = what == 0 ? t.p : what == 1 ? t.g : what == 2 ? t.m : t.v;
         CUDA_CHECK(cudaDeviceSynchronize());
-        CUDA_CHECK(cudaMemcpy(host_out, src, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+        if (t.layout == 0) {
+            CUDA_CHECK(cudaMemcpy(host_out, src, (size_t)count * sizeof(float), cudaMemcpyDeviceToHost));
+            return;
+        }
+        std::vector<float> tmp((size_t)t.n);
+        CUDA_CHECK(cudaMemcpy(tmp.data(), src, tmp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        if (t.layout == 1) {                                  // [d0][d1][ld] -> [d0][d1][d2]
+            for (long long r = 0; r < (long long)t.d0 * t.d1; ++r)
+                std::copy(tmp.begin() + r * t.ld, tmp.begin() + r * t.ld + t.d2, host_out + r * t.d2);
+        } else {                                              // device [tap][cin][ld] -> TF [1][tap][cout][cin]
+            for (int j = 0; j < t.d0; ++j)
+                for (int co = 0; co < t.d2; ++co)
+                    for (int ci = 0; ci < t.d1; ++ci)
+                        host_out[((size_t)j * t.d2 + co) * t.d1 + ci] = tmp[((size_t)j * t.d1 + ci) * t.ld + co];
+        }
     });
 }
 

@@ -140,7 +140,7 @@ void feat_run(const float* y, int len, float preemph, float* mag, float* mel, co
 struct DropArgs { uint32_t thresh = 0, layer = 0, seed = 0; float scale = 1.f; };   // keep iff mix32(i, layer, seed) >= thresh
 struct BlockBwdArgs {
     const float* pre; int ldy;         // pre-LN conv output (rows, nconv)
-    const float* gout;                 // gradient w.r.t. the block output (rows, C), dense
+    const float* gout; int ldg;        // gradient w.r.t. the block output (rows, C), leading dimension ldg (also of gin)
     const float* X; int ldx;           // block input (highway residual), mode 1
     const float* g1; const float* b1; const float* g2; const float* b2;
     float* dy;                         // out: gradient w.r.t. the conv output (rows, nconv), leading dimension ldy
@@ -165,11 +165,12 @@ struct AttnBwdArgs {
     int B, T, N, d; float att_scale;   // att_scale = 1 / (B N T)
 };
 struct AdamEntry { float* p; float* g; float* m; float* v; long long n; };
-void launch_train_dropout(float* x, long long n, const DropArgs& d, cudaStream_t s);
-void launch_train_loss(const float* logits, const float* mels, float* dlogits, double* sums, long long n, cudaStream_t s);
+void launch_train_dropout(float* x, long long rows, int C, int ld, const DropArgs& d, cudaStream_t s);
+void launch_train_loss(const float* logits, int ldl, const float* target, float* dlogits, int ldg, double* sums, long long rows, int C,
+                       cudaStream_t s);
 void launch_train_block_bwd(const BlockBwdArgs& a, cudaStream_t s);
 void launch_conv_wgrad(WgradArgs a, cudaStream_t s);
-void launch_transpose_w(const float* W, float* WT, int ntaps, int K, int N, int ldw, cudaStream_t s);
+void launch_transpose_w(const float* W, float* WT, int ntaps, int K, int N, int ldw, int Kp, cudaStream_t s);
 void launch_attn_bwd(const AttnBwdArgs& a, double* sums, cudaStream_t s);
 void launch_guided_attention(float* W, int N, int T, cudaStream_t s);
 void launch_embed_bwd(const int* ids, const float* g, float* dtable, int rows, int e, cudaStream_t s);

@@ -30,31 +30,39 @@ __device__ __forceinline__ float keep_mul(uint32_t idx, const DropArgs& d) {
     return mix32(idx, d.layer, d.seed) >= d.thresh ? d.scale : 0.0f;
 }
 
-__global__ void train_dropout_kernel(float* __restrict__ x, long long n, DropArgs d) {
+// x: (rows, C) with leading dimension ld; the mask index is the DENSE element index row * C + c
+__global__ void train_dropout_kernel(float* __restrict__ x, long long n, int C, int ld, DropArgs d) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) x[i] *= keep_mul((uint32_t)i, d);
+    if (i >= n) return;
+    const long long row = i / C;
+    const int c = (int)(i - row * C);
+    x[row * ld + c] *= keep_mul((uint32_t)i, d);
 }
 
-void launch_train_dropout(float* x, long long n, const DropArgs& d, cudaStream_t s) {
+void launch_train_dropout(float* x, long long rows, int C, int ld, const DropArgs& d, cudaStream_t s) {
+    const long long n = rows * C;
     if (d.thresh == 0u || n <= 0) return;
-    train_dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, d);
+    train_dropout_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(x, n, C, ld, d);
 }
 
 // ------------------------------------------------------------------------------------ losses
-// sums[0] += sum |Y - m|, sums[1] += sum BCE(logit, m); dlogits = (sign(Y-m) Y (1-Y) + (Y - m)) / n
-__global__ void train_loss_kernel(const float* __restrict__ logits, const float* __restrict__ mels, float* __restrict__ dlogits,
-                                  double* __restrict__ sums, long long n) {
+// sums[0] += sum |Y - m|, sums[1] += sum BCE(logit, m); dlogits = (sign(Y-m) Y (1-Y) + (Y - m)) / n.
+// logits (rows, C) with leading dimension ldl, targets dense (rows, C), dlogits (rows, C) with leading dimension ldg.
+__global__ void train_loss_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ target, float* __restrict__ dlogits,
+                                  int ldg, double* __restrict__ sums, long long n, int C) {
     __shared__ double red[2][8];
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double l1 = 0.0, bce = 0.0;
     if (i < n) {
-        const float x = logits[i], m = mels[i];
+        const long long row = i / C;
+        const int c = (int)(i - row * C);
+        const float x = logits[row * ldl + c], m = target[i];
         const float y = 1.0f / (1.0f + expf(-x));
         const float d = y - m;
         l1 = fabsf(d);
         bce = fmaxf(x, 0.f) - x * m + log1pf(expf(-fabsf(x)));
         const float sg = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
-        dlogits[i] = (sg * y * (1.0f - y) + d) / (float)n;
+        dlogits[row * ldg + c] = (sg * y * (1.0f - y) + d) / (float)n;
     }
     for (int o = 16; o > 0; o >>= 1) { l1 += __shfl_xor_sync(0xffffffffu, l1, o); bce += __shfl_xor_sync(0xffffffffu, bce, o); }
     const int w = threadIdx.x >> 5;
@@ -67,8 +75,10 @@ __global__ void train_loss_kernel(const float* __restrict__ logits, const float*
     }
 }
 
-void launch_train_loss(const float* logits, const float* mels, float* dlogits, double* sums, long long n, cudaStream_t s) {
-    train_loss_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(logits, mels, dlogits, sums, n);
+void launch_train_loss(const float* logits, int ldl, const float* target, float* dlogits, int ldg, double* sums, long long rows, int C,
+                       cudaStream_t s) {
+    const long long n = rows * C;
+    train_loss_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(logits, ldl, target, dlogits, ldg, sums, n, C);
 }
 
 // ------------------------------------------------------------------------------------ block backward
@@ -125,7 +135,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) train_block_bwd_kernel(const B
         const long long row = ((long long)blockIdx.x * BWD_WARPS + warp) * BWD_ROWS_PER_WARP + rr;
         if (row >= a.rows) break;                                                  // warp-uniform
         const float* y = a.pre + row * a.ldy;
-        const float* go = a.gout + row * C;
+        const float* go = a.gout + row * a.ldg;
         float* dyo = a.dy + row * a.ldy;
         float yh1[MAXV], dz1[MAXV], dy1[MAXV];
         float r1;
@@ -151,7 +161,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) train_block_bwd_kernel(const B
             float r2;
             ln_fwd_half<MAXV>(y + C, C, lane, yh2, r2);
             const float* x = a.X + row * a.ldx;
-            float* gi = a.gin + row * C;
+            float* gi = a.gin + row * a.ldg;
 #pragma unroll
             for (int i = 0; i < MAXV; ++i) {
                 const int c = lane + 32 * i;
@@ -192,7 +202,9 @@ void launch_train_block_bwd(const BlockBwdArgs& a, cudaStream_t s) {
     if (a.C <= 128)      train_block_bwd_kernel<4><<<grid, BWD_WARPS * 32, smem, s>>>(a);
     else if (a.C <= 256) train_block_bwd_kernel<8><<<grid, BWD_WARPS * 32, smem, s>>>(a);
     else if (a.C <= 512) train_block_bwd_kernel<16><<<grid, BWD_WARPS * 32, smem, s>>>(a);
-    else throw std::runtime_error("train_block_bwd: C > 512 is not on the Text2Mel path");
+    else if (a.C <= 1024) train_block_bwd_kernel<32><<<grid, BWD_WARPS * 32, smem, s>>>(a);
+    else if (a.C <= 1056) train_block_bwd_kernel<33><<<grid, BWD_WARPS * 32, smem, s>>>(a);     // F = 1025
+    else throw std::runtime_error("train_block_bwd: C > 1056 is not on the path");
 }
 
 // ------------------------------------------------------------------------------------ weight gradient
@@ -260,12 +272,12 @@ void launch_conv_wgrad(WgradArgs a, cudaStream_t s) {
     conv_wgrad_kernel<<<grid, 256, 0, s>>>(a);
 }
 
-// W[tap][K][ldw] -> WT[tap][N][K]   (N = used columns of W)
-__global__ void transpose_w_kernel(const float* __restrict__ W, float* __restrict__ WT, int K, int N, int ldw) {
+// W[tap][K][ldw] -> WT[tap][N][Kp]   (N rows = columns of W taken, Kp >= K the padded row length; pad columns untouched)
+__global__ void transpose_w_kernel(const float* __restrict__ W, float* __restrict__ WT, int K, int N, int ldw, int Kp) {
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
     const float* w = W + (size_t)tap * K * ldw;
-    float* wt = WT + (size_t)tap * N * K;
+    float* wt = WT + (size_t)tap * N * Kp;
     const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int k = k0 + i, n = n0 + threadIdx.x;
@@ -274,13 +286,13 @@ __global__ void transpose_w_kernel(const float* __restrict__ W, float* __restric
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int n = n0 + i, k = k0 + threadIdx.x;
-        if (n < N && k < K) wt[(size_t)n * K + k] = tile[threadIdx.x][i];
+        if (n < N && k < K) wt[(size_t)n * Kp + k] = tile[threadIdx.x][i];
     }
 }
 
-void launch_transpose_w(const float* W, float* WT, int ntaps, int K, int N, int ldw, cudaStream_t s) {
+void launch_transpose_w(const float* W, float* WT, int ntaps, int K, int N, int ldw, int Kp, cudaStream_t s) {
     dim3 grid((N + 31) / 32, (K + 31) / 32, ntaps);
-    transpose_w_kernel<<<grid, dim3(32, 8), 0, s>>>(W, WT, K, N, ldw);
+    transpose_w_kernel<<<grid, dim3(32, 8), 0, s>>>(W, WT, K, N, ldw, Kp);
 }
 
 // ------------------------------------------------------------------------------------ attention backward

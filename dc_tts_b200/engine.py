@@ -279,6 +279,21 @@ class Engine:
                     "dctts_train_step")
         return {"loss": out[0], "loss_mels": out[1], "loss_bd1": out[2], "loss_att": out[3]}
 
+    def train_init_ssrn(self, B, T=None, dropout_rate=None):
+        """Training workspace for the SSRN trainer (train.py num=2): mels (B, T, n_mels) -> mags (B, 4T, F)."""
+        rate = self.hp.dropout_rate if dropout_rate is None else dropout_rate
+        self._check(self._lib.dctts_train_init_ssrn(self._h, int(B), int(self.hp.max_T if T is None else T), float(rate)),
+                    "dctts_train_init_ssrn")
+
+    def train_step_ssrn(self, mels, mags, global_step=0, seed=0, lr=None, apply=True):
+        """One SSRN optimiser step on ground-truth mels / mags (train.py:69-72,100-108,122-132)."""
+        mels = self._f32(mels); mags = self._f32(mags)
+        out = (C.c_float * 4)()
+        self._check(self._lib.dctts_train_step_ssrn(self._h, _ptr(mels), _ptr(mags), mels.shape[0], int(global_step), int(seed) & 0xffffffff,
+                                                    float(self.hp.lr if lr is None else lr), 1 if apply else 0, out, self._stream()),
+                    "dctts_train_step_ssrn")
+        return {"loss": out[0], "loss_mags": out[1], "loss_bd2": out[2]}
+
     def train_apply(self, global_step, lr=None):
         self._check(self._lib.dctts_train_apply(self._h, int(global_step), float(self.hp.lr if lr is None else lr), self._stream()),
                     "dctts_train_apply")

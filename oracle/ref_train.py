@@ -63,7 +63,12 @@ def learning_rate(global_step, init_lr=None, warmup_steps=4000.0):
 def _chain(P, x, net, layers, counter, seed, rate):
     for l in layers:
         scope = "%s/%s" % (net, l.scope)
-        x = rt.conv1d(P, x, scope, l.rate, l.pad, l.act) if l.kind == "C" else rt.hc(P, x, scope, l.rate, l.pad)
+        if l.kind == "C":
+            x = rt.conv1d(P, x, scope, l.rate, l.pad, l.act)
+        elif l.kind == "HC":
+            x = rt.hc(P, x, scope, l.rate, l.pad)
+        else:
+            x = rt.conv1d_transpose(P, x, scope)
         if rate > 0:
             x = x * torch.from_numpy(dropout_keep(tuple(x.shape), counter[0], seed, rate))
         counter[0] += 1
@@ -119,6 +124,55 @@ def train_step(P, L, mels, state=None, global_step=0, seed=0, rate=None, lr=None
         grads[n] = g
         newstate[n] = (m, v)
     info = {k: float(out[k].detach()) for k in ("loss", "loss_mels", "loss_bd1", "loss_att")}
+    info["grads"] = grads
+    info["lr"] = lr_now
+    return newP, newstate, info
+
+
+# ------------------------------------------------------------------------------------------ SSRN (num = 2)
+def ssrn_names():
+    return [n for n in arch.param_shapes() if n.startswith("SSRN/")]
+
+
+def forward_ssrn(P, mels, mags, seed=0, rate=None):
+    """train.py:69-72 + :100-108 in training mode: SSRN on the GROUND-TRUTH mels, L1 + binary divergence on the
+    linear magnitudes.  Blocks are counted 0..15 for the dropout mask (the num=2 graph holds nothing else)."""
+    rate = hp.dropout_rate if rate is None else rate
+    mels = torch.as_tensor(mels, dtype=torch.float32)
+    mags = torch.as_tensor(mags, dtype=torch.float32)
+    logits = _chain(P, mels, "SSRN", arch.ssrn_layers(), [0], seed, rate)
+    Z = torch.sigmoid(logits)
+    loss_mags = (Z - mags).abs().mean()
+    loss_bd2 = torch.nn.functional.binary_cross_entropy_with_logits(logits, mags)
+    return dict(loss=loss_mags + loss_bd2, loss_mags=loss_mags, loss_bd2=loss_bd2, Z=Z, logits=logits)
+
+
+def _adam(P, names, T, state, global_step, lr, beta1, beta2, eps):
+    lr_now = learning_rate(global_step, lr)
+    t = global_step + 1
+    lr_t = lr_now * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    state = state or {n: (np.zeros(T[n].shape, np.float32), np.zeros(T[n].shape, np.float32)) for n in names}
+    newP, grads, newstate = dict(P), {}, {}
+    for n in names:
+        g = T[n].grad.numpy() if T[n].grad is not None else np.zeros(T[n].shape, np.float32)
+        g = np.clip(g, -1.0, 1.0).astype(np.float32)
+        m, v = state[n]
+        m = (beta1 * m + (1 - beta1) * g).astype(np.float32)
+        v = (beta2 * v + (1 - beta2) * g * g).astype(np.float32)
+        newP[n] = (np.asarray(P[n], np.float32) - np.float32(lr_t) * m / (np.sqrt(v) + np.float32(eps))).astype(np.float32)
+        grads[n] = g
+        newstate[n] = (m, v)
+    return newP, newstate, grads, lr_now
+
+
+def train_step_ssrn(P, mels, mags, state=None, global_step=0, seed=0, rate=None, lr=None, beta1=0.9, beta2=0.999, eps=1e-8):
+    """One SSRN optimiser step (train.py num=2: losses :100-108, optimiser :122-132)."""
+    names = ssrn_names()
+    T = {n: torch.tensor(np.asarray(P[n], np.float32), requires_grad=True) for n in names}
+    out = forward_ssrn(T, mels, mags, seed, rate)
+    out["loss"].backward()
+    newP, newstate, grads, lr_now = _adam(P, names, T, state, global_step, lr, beta1, beta2, eps)
+    info = {k: float(out[k].detach()) for k in ("loss", "loss_mags", "loss_bd2")}
     info["grads"] = grads
     info["lr"] = lr_now
     return newP, newstate, info

@@ -313,6 +313,24 @@ def synthesize(L, steps=None, with_ssrn=True):
     return {"Y": Y, "Z": Z, "p_hist": hist, "max_attentions": out["max_attentions"], "alignments": out["alignments"]}
 
 
+def run_train_graph_ssrn(mels, mags, dropout_hook):
+    """The reference's TRAINING graph for SSRN (train.py Graph(num=2, mode="train")): losses on a fixed batch."""
+    import train as ref_train
+    _State.scope = []
+    _State.layer_counts = {}
+    _State.dropout_hook = dropout_hook
+    _State.dropout_calls = 0
+    mels = _t(np.asarray(mels, np.float32)); mags = _t(np.asarray(mags, np.float32))
+    real = ref_train.get_batch
+    ref_train.get_batch = lambda: (_t(np.zeros((len(mels), 4), np.int32)), mels, mags, None, 1)
+    try:
+        g = ref_train.Graph(num=2, mode="train")
+    finally:
+        ref_train.get_batch = real
+        _State.dropout_hook = None
+    return {k: float(np.asarray(getattr(g, k))) for k in ("loss", "loss_mags", "loss_bd2")}, _State.dropout_calls
+
+
 def run_train_graph(L, mels, dropout_hook):
     """The reference's TRAINING graph for Text2Mel (train.py Graph(num=1, mode="train")): get_batch() is replaced
     by the given fixed-size batch, the optimiser by a stub; returns the three losses and the total."""

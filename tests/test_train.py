@@ -64,6 +64,24 @@ def test_oracle_losses_vs_reference_training_graph():
             assert abs(float(o[k]) - ref[k]) < 2e-6 * max(1.0, abs(ref[k])), (k, float(o[k]), ref[k])
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not present on this machine")
+def test_oracle_ssrn_losses_vs_reference_training_graph():
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tf_shim
+    P = init_params(0, "perturbed")
+    tf_shim.install(tf_shim.Store(P))
+    mels = np.random.default_rng(3).uniform(0, 1, (2, 12, hp.n_mels)).astype(np.float32)
+    mags = np.random.default_rng(4).uniform(0, 1, (2, 48, 1 + hp.n_fft // 2)).astype(np.float32)
+    hook = lambda x, r, i: x * rtr.dropout_keep(x.shape, i, 9, r)
+    ref, ncalls = tf_shim.run_train_graph_ssrn(mels, mags, hook)
+    assert ncalls == 16
+    T = {n: torch.tensor(np.asarray(P[n], np.float32)) for n in rtr.ssrn_names()}
+    with torch.no_grad():
+        o = rtr.forward_ssrn(T, mels, mags, 9)
+    for k in ("loss", "loss_mags", "loss_bd2"):
+        assert abs(float(o[k]) - ref[k]) < 2e-6 * max(1.0, abs(ref[k])), (k, float(o[k]), ref[k])
+
+
 def test_oracle_step_arithmetic():
     P = init_params(0, "perturbed")
     L, mels = _batch(1)
@@ -163,3 +181,29 @@ def test_cuda_train_checkpoint_roundtrip(tmp_path):
     assert torch.equal(ya, yb)
     with pytest.raises(RuntimeError):
         eng.set_tensor_path(1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,rate,seed", [(2, 16, 0.0, 0), (2, 12, 0.05, 9)])
+def test_cuda_ssrn_train_step_vs_oracle(B, T, rate, seed):
+    """The SSRN trainer (train.py num=2): transposed-conv blocks, C = 1024 highway blocks and the F = 1025 wide blocks."""
+    from dc_tts_b200.engine import Engine
+    P = init_params(0, "perturbed")
+    eng = Engine(0)
+    eng.load_params(P)
+    eng.train_init_ssrn(B, T, rate)
+    mels = np.random.default_rng(3).uniform(0, 1, (B, T, hp.n_mels)).astype(np.float32)
+    mags = np.random.default_rng(4).uniform(0, 1, (B, 4 * T, 1 + hp.n_fft // 2)).astype(np.float32)
+    newP, st, info = rtr.train_step_ssrn(P, mels, mags, global_step=3999, seed=seed, rate=rate)
+    out = eng.train_step_ssrn(mels, mags, global_step=3999, seed=seed, apply=False)
+    for k in ("loss", "loss_mags", "loss_bd2"):
+        assert abs(out[k] - info[k]) < 1e-5 * max(1.0, abs(info[k])), (k, out[k], info[k])
+    assert len(info["grads"]) == 80
+    _compare_grads(eng, info["grads"])
+    eng.train_apply(3999)
+    for n in ("SSRN/D_4/conv2d_transpose/kernel", "SSRN/D_7/conv2d_transpose/bias", "SSRN/HC_12/conv1d/kernel", "SSRN/C_13/conv1d/kernel",
+              "SSRN/C_16/conv1d/bias", "SSRN/C_15/normalize/gamma", "SSRN/HC_2/H1/beta"):
+        m, v = st[n]
+        np.testing.assert_allclose(eng.train_tensor(n, "m"), m, rtol=2e-3, atol=1e-9)
+        step = np.abs(newP[n] - P[n]).max()
+        assert np.abs(eng.train_tensor(n, "param") - newP[n]).max() <= 0.05 * step + 2.4e-7, n
