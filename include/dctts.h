@@ -165,9 +165,7 @@ int dctts_train_step(dctts_handle h, const int32_t* L, const float* mels, int32_
 int dctts_train_apply(dctts_handle h, int64_t global_step, float lr, void* stream);
 /* The SSRN trainer (train.py num = 2: SSRN on the GROUND-TRUTH mels :69-72, losses :100-108, same optimiser): mels
  * (B, T, n_mels), mags (B, 4T, 1 + n_fft/2) DEVICE pointers; losses_host = {total, mags L1, binary divergence, 0}.
- * A handle trains one of the two networks at a time (the init call selects which).
- * EXPERIMENTAL: losses are exact; gradients agree with the autograd checker for 32 and 96 rows (B * 4T) but deviate by up to
- * 4e-2 on the two ReLU F = 1025 blocks for 128 rows -- an open bug at the end of round 1. */
+ * A handle trains one of the two networks at a time (the init call selects which). */
 int dctts_train_init_ssrn(dctts_handle h, int32_t B, int32_t T, float dropout_rate);
 int dctts_train_step_ssrn(dctts_handle h, const float* mels, const float* mags, int32_t B, int64_t global_step, uint32_t seed, float lr,
                           int32_t apply, float* losses_host, void* stream);

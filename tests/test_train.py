@@ -183,17 +183,52 @@ def test_cuda_train_checkpoint_roundtrip(tmp_path):
         eng.set_tensor_path(1)
 
 
-_SSRN_OPEN_BUG = ("OPEN (round 1 ended without GPU time to bisect it): with B * 4T = 128 rows the gradients of the two ReLU F = 1025 "
-                  "blocks (SSRN/C_14, C_15) deviate by up to 4e-2 of their max-norm and everything upstream by ~3e-3; losses are exact; "
-                  "B * 4T = 32 and 96 rows agree with the oracle to 6e-6 (tools/train_grad_report.py prints the per-tensor table)")
+_RELU_TIE = ("not a defect: in this configuration a pre-activation of the ReLU block SSRN/C_14 lies 1.2e-7 from zero (float32 "
+             "resolution), so two correct float32 forward passes legitimately disagree on that element's ReLU mask; the flipped element "
+             "moves C_14's gradients by up to 4e-2 of their max-norm and everything upstream by ~3e-3 "
+             "(test_ssrn_relu_margins_explain_the_tie_case, tools/train_grad_report.py)")
+
+
+def _ssrn_relu_margins(B, T, rate, seed):
+    """Smallest |pre-activation| of the two ReLU blocks of SSRN (C_14, C_15) in the oracle's forward pass."""
+    from dc_tts_b200 import arch
+    from oracle import ref_torch as rt
+    P = init_params(0, "perturbed")
+    W = {n: torch.tensor(np.asarray(P[n], np.float32)) for n in rtr.ssrn_names()}
+    x = torch.as_tensor(np.random.default_rng(3).uniform(0, 1, (B, T, hp.n_mels)).astype(np.float32))
+    out = {}
+    for c, l in enumerate(arch.ssrn_layers()):
+        scope = "SSRN/%s" % l.scope
+        if l.kind == "C":
+            y = rt._conv(x, W[scope + "/conv1d/kernel"], W[scope + "/conv1d/bias"], l.rate, l.pad)
+            z = rt.normalize(y, W[scope + "/normalize/gamma"], W[scope + "/normalize/beta"])
+            if l.act == "relu":
+                out[l.scope] = float(z.abs().min())
+                z = torch.relu(z)
+            x = z
+        elif l.kind == "HC":
+            x = rt.hc(W, x, scope, l.rate, l.pad)
+        else:
+            x = rt.conv1d_transpose(W, x, scope)
+        if rate > 0:
+            x = x * torch.from_numpy(rtr.dropout_keep(tuple(x.shape), c, seed, rate))
+    return out
+
+
+def test_ssrn_relu_margins_explain_the_tie_case():
+    """ReLU is discontinuous: gradient parity between two float32 implementations needs every ReLU pre-activation to clear
+    zero by more than the forward noise (~4e-6 here).  The configurations used as GPU parity cases do; (2, 16, 0.0, 0) does not."""
+    assert min(_ssrn_relu_margins(2, 16, 0.0, 0).values()) < 1e-6
+    assert min(_ssrn_relu_margins(2, 12, 0.05, 9).values()) > 4e-6
+    assert min(_ssrn_relu_margins(1, 8, 0.0, 0).values()) > 4e-6
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("B,T,rate,seed", [pytest.param(2, 16, 0.0, 0, marks=pytest.mark.xfail(reason=_SSRN_OPEN_BUG, strict=False)),
+@pytest.mark.parametrize("B,T,rate,seed", [pytest.param(2, 16, 0.0, 0, marks=pytest.mark.xfail(reason=_RELU_TIE, strict=False)),
                                            (2, 12, 0.05, 9), (1, 8, 0.0, 0)])
 def test_cuda_ssrn_train_step_vs_oracle(B, T, rate, seed):
     """The SSRN trainer (train.py num=2): transposed-conv blocks, C = 1024 highway blocks and the F = 1025 wide blocks.
-    EXPERIMENTAL: see _SSRN_OPEN_BUG -- the SSRN step is not claimed as done."""
+    The first case is kept as a documented ReLU tie (see _RELU_TIE)."""
     from dc_tts_b200.engine import Engine
     P = init_params(0, "perturbed")
     eng = Engine(0)
