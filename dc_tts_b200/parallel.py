@@ -5,6 +5,10 @@ Utterances never interact on the synthesis path (every op is per batch row,
 contiguous shards, one per rank, with weights replicated.  The only communication is
 ONE gather of the finished spectrograms; the reference has no counterpart (it is a
 single-process program).  Backend: NCCL over NVLink on GPUs, gloo in the CPU tests.
+
+Training (BASELINE config 5) is plain data parallelism: every rank runs `Engine.train_step(..., apply=False)`
+on its own 32 utterances, the flat gradient arena (`Engine.train_grads()`) is averaged over the ranks
+(`allreduce_mean_`), then every rank applies the identical Adam update (`Engine.train_apply`).
 """
 import torch
 import torch.distributed as dist
@@ -45,3 +49,13 @@ def gather_spectrograms(local, total, dst=0, group=None):
         for w in dist.batch_isend_irecv(ops):
             w.wait()
     return out
+
+
+def allreduce_mean_(flat, group=None):
+    """In-place average of a flat gradient buffer over the ranks (sum all-reduce, then 1/world): the gradient of the mean
+    loss over the global batch when every rank holds the same number of utterances.  Returns `flat`."""
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.mul_(1.0 / world)
+    return flat

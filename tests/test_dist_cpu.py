@@ -56,3 +56,45 @@ def test_gather_two_ranks_gloo(total):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+# ---- data-parallel training (BASELINE config 5): average of the per-rank gradients == gradient of the global batch ----
+def _train_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(4)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dc_tts_b200.hyperparams import Hyperparams as hp
+        from dc_tts_b200.parallel import allreduce_mean_
+        from dc_tts_b200.params import init_params
+        from oracle import ref_train as rtr
+        P = init_params(0, "perturbed")
+        L = synthetic_text(world, 30, seed=2)
+        mels = np.random.default_rng(5).uniform(0, 1, (world, hp.max_T, hp.n_mels)).astype(np.float32)
+        names = rtr.text2mel_names()
+        lo, hi = shard_bounds(world, rank, world)
+        _, _, info = rtr.train_step(P, L[lo:hi], mels[lo:hi], rate=0.0)
+        flat = torch.cat([torch.from_numpy(info["grads"][n]).reshape(-1) for n in names])
+        allreduce_mean_(flat)
+        if rank == 0:
+            _, _, full = rtr.train_step(P, L, mels, rate=0.0)
+            want = torch.cat([torch.from_numpy(full["grads"][n]).reshape(-1) for n in names])
+            scale = float(want.abs().max())
+            q.put((float((flat - want).abs().max()) / scale, flat.numel()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_average_two_ranks_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    err, n = q.get(timeout=5)
+    assert n == 23970288 and err < 1e-5
