@@ -124,3 +124,74 @@ def test_cuda_synthesis_vs_reference_code(engine):
     assert np.array_equal(M.cpu().numpy(), g["max_attentions"])
     _, Z = engine.ssrn(Y, want_logits=False)
     assert np.abs(Z.cpu().numpy()[:, ::8, ::8] - g["Z_sub"]).max() < TOL
+
+
+# ------------------------------------------------------------------------------------------- host-side pieces
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not present on this machine")
+def test_text_adaptor_vs_reference_code(monkeypatch):
+    """data_load.load_data("synthesize") of the reference itself (data_load.py:79-86) on its own harvard_sentences.txt
+    vs the mirror in dc_tts_b200/data_load.py: all 20 sentences, every id."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tf_shim
+    tf_shim.install(tf_shim.Store({}))
+    import data_load as ref_dl
+    import hyperparams as ref_hp
+    monkeypatch.setattr(ref_hp.Hyperparams, "test_data", "/root/reference/harvard_sentences.txt")
+    ref = ref_dl.load_data("synthesize")
+    from dc_tts_b200.data_load import load_data, load_vocab
+    mine = load_data("synthesize", os.path.join(ROOT, "harvard_sentences.txt"))
+    assert ref.shape == (20, hp.max_N) and ref.dtype == np.int32
+    assert np.array_equal(ref, mine)
+    assert ref_dl.load_vocab() == load_vocab()
+    assert np.array_equal(golden("refshim_synth_harvard1.npz")["L"], ref[:1])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not present on this machine")
+def test_training_constants_vs_reference_code():
+    """utils.guided_attention (utils.py:134-140) and the Noam schedule (utils.py:141-145) of the reference itself."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import tf_shim
+    tf_shim.install(tf_shim.Store({}))
+    import utils as ref_utils
+    from oracle import ref_train as rtr
+    np.testing.assert_allclose(ref_utils.guided_attention(), rtr.guided_attention(), rtol=0, atol=1e-7)
+    for gs in (0, 1, 3999, 4000, 123456):
+        assert float(ref_utils.learning_rate_decay(hp.lr, gs)) == pytest.approx(rtr.learning_rate(gs), rel=1e-6)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="/root/reference is not present on this machine")
+def test_vocoder_and_feature_composition_vs_reference_code(monkeypatch):
+    """utils.spectrogram2wav / get_spectrograms / load_spectrograms of the reference itself, with the absent `librosa`
+    replaced by the restated primitives (oracle/ref_vocoder.py, ref_features.py): pins how the reference COMPOSES
+    them (de-normalisation, power, Griffin-Lim loop, lfilter, trim; pre-emphasis, mel, dB, normalisation, reduction) --
+    the primitives themselves stay a restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import types
+    import tf_shim
+    tf_shim.install(tf_shim.Store({}))
+    import utils as ref_utils
+    from oracle import ref_features as rf
+    from oracle import ref_vocoder as rv
+    lib = types.SimpleNamespace(
+        stft=lambda y, n_fft=None, hop_length=None, win_length=None: rv.stft(np.asarray(y, np.float32), n_fft, hop_length, win_length),
+        istft=lambda S, hop_length=None, win_length=None, window="hann": rv.istft(S, hop_length, win_length),
+        effects=types.SimpleNamespace(trim=lambda y: (lambda se: (y[se[0]:se[1]], se))(rv.trim_indices(np.asarray(y)))),
+        filters=types.SimpleNamespace(mel=lambda sr, n_fft, n_mels: rf.mel_basis(sr, n_fft, n_mels)),
+        load=lambda fpath, sr=None: (WAVS[fpath], sr))
+    monkeypatch.setattr(ref_utils, "librosa", lib)
+    import hyperparams as ref_hp
+    monkeypatch.setattr(ref_hp.Hyperparams, "n_iter", 3)
+    monkeypatch.setattr(hp, "n_iter", 3)
+    rng = np.random.default_rng(0)
+    mag = rng.uniform(0.2, 0.8, (40, 1 + hp.n_fft // 2)).astype(np.float32)
+    ref_wav = ref_utils.spectrogram2wav(mag)
+    mine, _, _ = rv.spectrogram2wav(mag, n_iter=3)
+    assert ref_wav.shape == mine.shape and np.abs(ref_wav - mine).max() <= 1e-6 * max(1.0, np.abs(mine).max())
+    t = np.arange(int(hp.sr * 0.8)) / hp.sr
+    y = (0.2 * np.sin(2 * np.pi * 300 * t) + 0.02 * rng.standard_normal(t.size)).astype(np.float32)
+    y[:2000] *= 1e-5
+    WAVS = {"LJ001-0001.wav": y}
+    fname, mel, mg = ref_utils.load_spectrograms("LJ001-0001.wav")
+    mel2, mg2 = rf.load_spectrograms(y)
+    assert fname == "LJ001-0001.wav" and mel.shape == mel2.shape and mg.shape == mg2.shape
+    assert np.abs(mel - mel2).max() < 1e-6 and np.abs(mg - mg2).max() < 1e-6
