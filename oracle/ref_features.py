@@ -2,7 +2,9 @@
 `get_spectrograms` / `load_spectrograms` (/root/reference/utils.py:20-65, 147-162) from a waveform array on
 (file decoding and resampling, `librosa.load`, are outside: LJ Speech is already 22050 Hz PCM).
 
-Third-party pieces restated from librosa 0.6 (absent, un-pinned -- PARITY UNPINNED, see ref_vocoder.py):
+Third-party pieces restated from librosa 0.6 (absent offline; pinned by independent librosa-compatible implementations:
+torch.stft for the STFT, transformers.audio_utils.mel_filter_bank(slaney) for the filterbank -- equal to 1e-16 -- and by
+the reference's own get_spectrograms / load_spectrograms executed with these primitives, tests/test_reference_shim.py):
   effects.trim        ref_vocoder.trim_indices
   core.stft           ref_vocoder.stft
   filters.mel(sr, n_fft, n_mels)   Slaney scale (htk=False), fmin 0, fmax sr/2, area normalisation (norm=1):

@@ -12,8 +12,10 @@ those of librosa 0.5/0.6).  This file restates the published librosa 0.6 algorit
                  squared window where it exceeds tiny(), drop n_fft//2 samples at both ends;
   effects.trim   top_db=60, frame_length=2048, hop_length=512, RMS per centred (reflect-padded)
                  frame, 10*log10 relative to the maximum, first/last frame above -60 dB.
-PARITY UNPINNED: neither librosa nor any vector of it exists offline; the restatement is pinned
-only by self-consistency properties (tests/test_vocoder.py: istft(stft(x)) == x, Parseval).
+PARITY: librosa itself and vectors of it do not exist offline.  The restatement is pinned by (i) torch.stft / torch.istft,
+which implement librosa's conventions by design (agreement 2e-7 relative / 1e-6 absolute, tests/test_vocoder.py), (ii) the
+reference's own utils.spectrogram2wav executed with these primitives plugged in for librosa (tests/test_reference_shim.py:
+the composition), (iii) self-consistency (istft(stft(x)) == x).  `effects.trim` has no independent implementation here.
 dtype: the reference runs in float32 / complex64 (Z is float32, librosa's default dtypes);
 `dtype=np.float64` gives the double-precision variant used to bound float32 noise.
 """

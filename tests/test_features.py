@@ -92,3 +92,12 @@ def test_gpu_load_spectrograms_from_wav_file(engine, tmp_path):
     with pytest.raises(ValueError):
         wavfile.write(path, 16000, pcm)
         utils.load_spectrograms(path)
+
+
+def test_mel_basis_matches_transformers_slaney_filter_bank():
+    """transformers.audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney") documents itself as librosa.filters.mel's
+    equivalent: an independent implementation of what oracle/ref_features.mel_basis restates."""
+    au = pytest.importorskip("transformers.audio_utils")
+    M = au.mel_filter_bank(num_frequency_bins=1 + hp.n_fft // 2, num_mel_filters=hp.n_mels, min_frequency=0.0,
+                           max_frequency=hp.sr / 2, sampling_rate=hp.sr, norm="slaney", mel_scale="slaney")
+    assert np.abs(M.T - rf.mel_basis()).max() < 1e-12

@@ -77,3 +77,20 @@ def test_gpu_vocoder_full_default_iterations(engine):
     n = min(len(wav), len(w))
     # 50 projections amplify float32 rounding differently on the two sides: compare energies, not samples
     assert abs(np.sqrt(np.mean(wav[:n] ** 2)) / np.sqrt(np.mean(w[:n] ** 2)) - 1) < 0.05
+
+
+def test_stft_istft_match_torch_librosa_compatible_implementations():
+    """torch.stft / torch.istft follow librosa's conventions by design (centred reflect padding, window zero-padded to n_fft,
+    window-sum-square normalisation, n_fft/2 trimmed): an independent implementation of what oracle/ref_vocoder.py restates."""
+    import torch
+    from dc_tts_b200.hyperparams import Hyperparams as hp
+    from oracle import ref_vocoder as rv
+    y = np.random.default_rng(0).standard_normal(8000).astype(np.float32)
+    win = torch.hann_window(hp.win_length, periodic=True)
+    S = rv.stft(y)
+    St = torch.stft(torch.from_numpy(y), hp.n_fft, hp.hop_length, hp.win_length, window=win, center=True, pad_mode="reflect",
+                    return_complex=True).numpy()
+    assert S.shape == St.shape and np.abs(S - St).max() < 1e-6 * np.abs(St).max()
+    yi = rv.istft(S)
+    yt = torch.istft(torch.from_numpy(St), hp.n_fft, hp.hop_length, hp.win_length, window=win, center=True).numpy()
+    assert yi.shape == yt.shape and np.abs(yi - yt).max() < 5e-6
