@@ -318,18 +318,22 @@ class Engine:
                                                  out.ctypes.data_as(C.c_void_p), out.size), "dctts_train_tensor(%s)" % name)
         return out
 
-    def save_text2mel_checkpoint(self, prefix, global_step):
-        """What `sv.saver.save(sess, logdir + '/model_gs_...')` writes at train.py:152 for the Text2Mel trainer: every
-        Text2Mel variable, its Adam slots (`<name>/Adam`, `<name>/Adam_1`) and `gs/global_step`, as a TF tensor bundle."""
+    def save_checkpoint(self, prefix, global_step, scope="Text2Mel"):
+        """What `sv.saver.save(sess, logdir + '/model_gs_...')` writes at train.py:152 for the network being trained
+        (`scope` "Text2Mel" or "SSRN"): every variable of the scope, its Adam slots (`<name>/Adam`, `<name>/Adam_1`) and
+        `gs/global_step`, as a TF tensor bundle."""
         from .arch import param_shapes
         from .checkpoint import save_checkpoint
         out = {"gs/global_step": np.array(global_step, np.int32)}
         for name in param_shapes():
-            if name.startswith("Text2Mel/"):
+            if name.startswith(scope + "/"):
                 out[name] = self.train_tensor(name, "param")
                 out[name + "/Adam"] = self.train_tensor(name, "m")
                 out[name + "/Adam_1"] = self.train_tensor(name, "v")
         return save_checkpoint(prefix, out)
+
+    def save_text2mel_checkpoint(self, prefix, global_step):
+        return self.save_checkpoint(prefix, global_step, "Text2Mel")
 
     def synthesize_host(self, L_host, Y_host=None, Z_host=None):
         """synthesize.py:45-57 with host (ideally pinned) tensors in and out."""

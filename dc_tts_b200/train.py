@@ -8,8 +8,9 @@ symbols and `Session.run` evaluates them eagerly on the GPU, so that the referen
 loop (synthesize.py:47-57) runs unmodified in structure.  `Graph.generate` is the fast
 path: the whole loop on the device, replayed from a CUDA graph.
 
-The training branch (losses, optimiser, Supervisor loop: train.py:82-162) is outside the
-hot path and raises NotImplementedError.
+The training branch is not a symbolic graph here: losses, backward pass and optimiser (train.py:82-135) are
+`Engine.train_step` / `train_step_ssrn`, and the loop of train.py:137-160 is `dc_tts_b200/trainer.py: train`;
+`Graph(mode="train")` raises NotImplementedError and says so.
 """
 import numpy as np
 import torch
@@ -38,7 +39,7 @@ _FUSED_OK = {"Y", "max_attentions", "alignments", "global_step"}
 class Graph:
     def __init__(self, num=1, mode="train", engine=None, fused=True):
         if mode != "synthesize":
-            raise NotImplementedError("Graph(mode='train'): the trainer is outside the synthesis hot path")
+            raise NotImplementedError("Graph(mode='train'): use dc_tts_b200.trainer.train (Engine.train_step / train_step_ssrn)")
         self.char2idx, self.idx2char = load_vocab()
         self.engine = engine or get_engine()
         self.fused = fused

@@ -1,0 +1,91 @@
+"""The trainer loop (dc_tts_b200/trainer.py; reference train.py:137-160 + data_load.py:41-56,97-112) with a recording
+stand-in for the engine: batching / padding, step counting, checkpoint cadence and names, termination."""
+import os
+
+import numpy as np
+import pytest
+
+from dc_tts_b200 import trainer
+from dc_tts_b200.hyperparams import Hyperparams as hp
+
+
+class FakeEngine:
+    def __init__(self):
+        self.calls, self.saved, self.init = [], [], None
+
+    def train_init(self, B):
+        self.init = ("t2m", B)
+
+    def train_init_ssrn(self, B, T):
+        self.init = ("ssrn", B, T)
+
+    def train_step(self, L, mels, global_step=0, seed=0):
+        self.calls.append(("t2m", L.shape, mels.shape, global_step, seed))
+        return {"loss": 1.0, "loss_mels": 0.3, "loss_bd1": 0.69, "loss_att": 0.01}
+
+    def train_step_ssrn(self, mels, mags, global_step=0, seed=0):
+        self.calls.append(("ssrn", mels.shape, mags.shape, global_step, seed))
+        return {"loss": 1.0, "loss_mags": 0.3, "loss_bd2": 0.7}
+
+    def save_checkpoint(self, prefix, gs, scope):
+        self.saved.append((prefix, gs, scope))
+
+
+def _dataset(tmp_path, n=7):
+    d = tmp_path / "LJSpeech-1.0"
+    (d / "wavs").mkdir(parents=True)
+    rng = np.random.default_rng(0)
+    lines, lengths = [], []
+    for i in range(n):
+        text = "Sentence number %d, with Ünïcode & digits 123." % i if i != 3 else "x" * 400          # one too long
+        lines.append("LJ%03d|raw|%s" % (i, text))
+        t = 40 + 10 * i if i != 5 else hp.max_T + 8                                                   # one too long in time
+        lengths.append(t)
+    (d / "transcript.csv").write_text("\n".join(lines) + "\n", encoding="utf-8")
+    store = {"LJ%03d.wav" % i: (rng.uniform(0, 1, (t, hp.n_mels)).astype(np.float32),
+                                rng.uniform(0, 1, (4 * t, 1 + hp.n_fft // 2)).astype(np.float32)) for i, t in enumerate(lengths)}
+    loader = lambda fpath: (os.path.basename(fpath),) + store[os.path.basename(fpath)]
+    return str(d), loader, store
+
+
+def test_transcript_parser_and_fixed_size_batches(tmp_path):
+    d, loader, store = _dataset(tmp_path)
+    fpaths, lens, texts = trainer.load_train_data(d)
+    assert len(fpaths) == 7 and fpaths[0].endswith("wavs/LJ000.wav") and lens[3] == 401
+    assert texts[0].dtype == np.int32 and texts[0][-1] == hp.vocab.index("E")
+    assert "".join(hp.vocab[i] for i in texts[1]) == "sentence number with unicode digits .E"   # digits, comma, & -> spaces, squeezed; accents stripped
+    batches = list(trainer.fixed_size_batches(fpaths, texts, B=2, seed=1, loader=loader, epochs=1))
+    assert len(batches) == 2                                       # 7 utterances - 2 skipped = 5 -> two full batches, remainder dropped
+    seen = []
+    for L, mels, mags, names in batches:
+        assert L.shape == (2, hp.max_N) and mels.shape == (2, hp.max_T, hp.n_mels) and mags.shape == (2, 4 * hp.max_T, 1025)
+        for b, name in enumerate(names):
+            mel, mag = store[name]
+            assert np.array_equal(mels[b, :len(mel)], mel) and not mels[b, len(mel):].any()
+            assert np.array_equal(mags[b, :len(mag)], mag) and not mags[b, len(mag):].any()
+            i = int(name[2:5])
+            assert np.array_equal(L[b, :lens[i]], texts[i]) and not L[b, lens[i]:].any()
+        seen += names
+    assert "LJ003.wav" not in seen and "LJ005.wav" not in seen and len(set(seen)) == 4
+
+
+@pytest.mark.parametrize("num", [1, 2])
+def test_loop_cadence_and_termination(tmp_path, num):
+    d, loader, _ = _dataset(tmp_path)
+    fpaths, _, texts = trainer.load_train_data(d)
+    eng = FakeEngine()
+    logdir = str(tmp_path / ("LJ01-%d" % num))
+    gs = trainer.train(num, eng, trainer.fixed_size_batches(fpaths, texts, B=2, seed=0, loader=loader), num_iterations=7,
+                       logdir=logdir, global_step=1996, save_every=1000, log=lambda *_: None)
+    # runs until gs > num_iterations is first checked after a step: starting at 1996 the first step already exceeds 7
+    assert gs == 1997 and len(eng.calls) == 1
+    eng = FakeEngine()
+    gs = trainer.train(num, eng, trainer.fixed_size_batches(fpaths, texts, B=2, seed=0, loader=loader), num_iterations=2003,
+                       logdir=logdir, global_step=1996, save_every=1000, log=lambda *_: None)
+    assert gs == 2004 and [c[3] for c in eng.calls] == list(range(1996, 2004))       # global_step fed BEFORE the increment
+    assert [c[4] for c in eng.calls] == list(range(1996, 2004))                      # per-step dropout seed
+    assert eng.saved == [(os.path.join(logdir, "model_gs_002k"), 2000, "Text2Mel" if num == 1 else "SSRN")]
+    assert eng.init == (("t2m", 2) if num == 1 else ("ssrn", 2, hp.max_T)) and os.path.isdir(logdir)
+    assert eng.calls[0][0] == ("t2m" if num == 1 else "ssrn")
+    with pytest.raises(ValueError):
+        trainer.train(3, eng, [])
