@@ -89,3 +89,13 @@ def test_loop_cadence_and_termination(tmp_path, num):
     assert eng.calls[0][0] == ("t2m" if num == 1 else "ssrn")
     with pytest.raises(ValueError):
         trainer.train(3, eng, [])
+
+
+def test_prepo_writes_what_the_trainer_reads(tmp_path):
+    """prepo.py:15-25 -> data_load.py:105-109: files named after the wav, loadable by the trainer's default loader."""
+    from dc_tts_b200 import prepo
+    d, loader, store = _dataset(tmp_path, n=3)
+    n = prepo.prepo(d, str(tmp_path), load_spectrograms=lambda p: (os.path.basename(p),) + store[os.path.basename(p)])
+    assert n == 3 and sorted(os.listdir(tmp_path / "mels")) == ["LJ000.npy", "LJ001.npy", "LJ002.npy"]
+    fname, mel, mag = trainer._load_spectrograms_npy(os.path.join(d, "wavs", "LJ001.wav"), str(tmp_path / "mels"), str(tmp_path / "mags"))
+    assert fname == "LJ001.wav" and np.array_equal(mel, store[fname][0]) and np.array_equal(mag, store[fname][1])
