@@ -56,6 +56,9 @@ SIGNATURES = {
     "dctts_launch_count": (_i64, [Handle]),
     "dctts_crc32c": (C.c_uint32, [C.c_uint32, _p, _i64]),
     "dctts_set_tensor_path": (C.c_int, [Handle, _i32]),
+    "dctts_set_option": (C.c_int, [Handle, C.c_char_p, _i32]),
+    "dctts_get_option": (C.c_int, [Handle, C.c_char_p, C.POINTER(_i32)]),
+    "dctts_decode_stats": (C.c_int, [Handle, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
     "dctts_malloc": (C.c_int, [Handle, C.POINTER(_p), _i64]),
     "dctts_free": (C.c_int, [Handle, _p]),
     "dctts_memcpy_h2d": (C.c_int, [Handle, _p, _p, _i64, _p]),

@@ -10,6 +10,7 @@
 #include "../../include/dctts.h"
 #include "kernels.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_decode.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -56,6 +57,7 @@ struct LayerDev {
     int act = 0;
     int nconv = 0, ldw = 0;
     float* W = nullptr;      // [size][cin][ldw]
+    std::vector<float> hostW;   // same, kept on the host until the decode stream is packed (AudioEnc / AudioDec only)
     float* bias = nullptr;   // [ldw]
     float *g1 = nullptr, *b1 = nullptr, *g2 = nullptr, *b2 = nullptr;
     // tensor-core path: split-fp16 K-major weight planes [ncta*bn][ntaps*cin_pad], pre-scaled
@@ -156,11 +158,34 @@ struct dctts_handle_s {
     int tensor_path = 1;          // tcgen05 blocks wherever they apply; 0 forces the fp32 CUDA-core kernels
     int64_t launches = 0;
 
+    // kernel-variant switches (dctts_set_option); the defaults are the measured-best configuration
+    struct {
+        int tc_occ2 = 1;          // two tcgen05 CTAs per SM (32-wide slab, 2 stages) on launches that fill the machine
+        int tc_cg2 = 0;           // CTA pairs (cta_group::2): 0 off, 1 wide (N = 512 per pair), 2 narrow (N = 256 per pair)
+        int tc_tile_pair = 0;     // two 128-row tiles per CTA sharing one weight slab
+        int tc_mcast = 1;         // TMA multicast of the activation tile across the cluster
+        int tc_resid_tma = 1;     // hc: residual in / planes out through TMA
+        int tc_debug = 0;         // progress markers + in-kernel cycle stamps (synchronising)
+        int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
+        int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
+    } opt;
+
+    // persistent decode (kernels_decode.cu)
+    struct {
+        bool ok = false;          // stream packed, geometry supported, 16-CTA clusters schedulable
+        DecParams tab{};          // layer / chunk tables (+ parameter pointers); per-call fields filled by text2mel_generate
+        DevBuf wstream, lnp, scr, stats, pfinal;
+        int max_clusters = 0;
+        std::string why;          // why not ok
+        int last_moved_frames = -1, last_moved_utt = -1, last_clusters = 0;
+    } dec;
+
     ~dctts_handle_s() {
         if (ar_exec) cudaGraphExecDestroy(ar_exec);
         for (void* p : param_allocs) cudaFree(p);
         for (DevBuf* b : {&tr.pre, &tr.out, &tr.emb, &tr.R, &tr.align, &tr.dS, &tr.gbuf[0], &tr.gbuf[1], &tr.gbuf[2], &tr.gbuf[3], &tr.dy,
                           &tr.wT, &tr.zeros, &tr.gts, &tr.sums, &tr.ids, &tr.grads, &tr.mom, &tr.vel, &tr.entries}) b->release();
+        dec.wstream.release(); dec.lnp.release(); dec.scr.release(); dec.stats.release(); dec.pfinal.release();
         tickets.release(); scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
         for (auto& b : plane) b.release();
@@ -351,6 +376,7 @@ void commit_layer(H* h, LayerDev& l) {
         h->n_params += (int64_t)k * cin * nconv;
     }
     l.W = upload(h, W);
+    if (l.scope.compare(0, 14, "Text2Mel/Audio") == 0) l.hostW = W;
     pack_tc(h, l, W);
     if (l.kind == K_HC) {
         l.g1 = upload_vec(h, l.scope + "/H1/gamma", l.cout, l.cout);
@@ -361,6 +387,99 @@ void commit_layer(H* h, LayerDev& l) {
         l.g1 = upload_vec(h, l.scope + "/normalize/gamma", l.cout, l.cout);
         l.b1 = upload_vec(h, l.scope + "/normalize/beta", l.cout, l.cout);
     }
+}
+
+std::vector<int> audiodec_rows(const std::vector<LayerDev>& net, int T);
+
+// ---------------------------------------------------------------------------- persistent decode tables
+// Layer / chunk tables and the per-rank weight streams of the cluster decode kernel (kernels_decode.cu).
+// Stream of rank r = for every block of AudioEnc then AudioDec, for every tap, for every chunk of <= 4096 floats:
+// the block's weight columns owned by rank r ([k/4][column][4]).  hc blocks: columns [0, cs) are the gate
+// channels r*cs.., [cs, 2cs) the info channels of the same index (modules.py:188-193); conv blocks: cs columns
+// (+ zero columns up to a multiple of 4).
+void pack_decode(H* h) {
+    auto& D = h->dec;
+    D.ok = false;
+    const dctts_hparams& hp = h->hp;
+    const int d = hp.d;
+    if (d != 256) { D.why = "persistent decode needs d = 256"; return; }
+    if (hp.n_mels % DEC_NC || hp.n_mels > 128 || hp.attention_win_size > 4 || hp.attention_win_size < 1) { D.why = "persistent decode: unsupported n_mels / window"; return; }
+    std::vector<LayerDev*> nets;
+    for (auto& l : h->audioenc) nets.push_back(&l);
+    for (auto& l : h->audiodec) nets.push_back(&l);
+    if ((int)nets.size() > DEC_MAXL) { D.why = "persistent decode: too many blocks"; return; }
+    DecParams& P = D.tab;
+    memset(&P, 0, sizeof(P));
+    P.nl = (int)nets.size(); P.n_enc = (int)h->audioenc.size();
+    std::vector<int> prow = audiodec_rows(h->audiodec, hp.max_T);
+    int nch = 0, off = 0;
+    for (int li = 0; li < P.nl; ++li) {
+        const LayerDev& l = *nets[li];
+        DecLayer& L = P.L[li];
+        if (l.kind == K_D || !l.causal || (l.cin % 4) || (l.kind == K_HC && (l.cin != d || l.cout != d)) || l.cout % DEC_NC ||
+            (li != 0 && l.cin % 128)) { D.why = "persistent decode: unsupported block " + l.scope; return; }
+        L.kind = l.kind == K_HC ? 1 : 0; L.cin = l.cin; L.cout = l.cout; L.ntaps = l.size; L.rate = l.rate; L.act = l.act;
+        L.cs = l.cout / DEC_NC; L.ns = L.kind ? 2 * L.cs : (L.cs <= 8 ? 8 : roundup(L.cs, 4));
+        if (L.ns != 8 && L.ns != 16 && L.ns != 32) { D.why = "persistent decode: unsupported slice width"; return; }
+        L.prow = li >= P.n_enc ? prow[li - P.n_enc] : 1;
+        if (L.prow > 1 && (L.cout != 256 || (L.ns != 32 && L.ns != 16) || L.prow > 85)) { D.why = "persistent decode: unsupported receptive field"; return; }
+        L.ldin = l.cin;
+        const int cinp = roundup(l.cin, 128);                     // AudioEnc C_1: 80 -> 128 zero rows
+        const int krows_max = DEC_SLOT_F / L.ns;                  // k rows per chunk
+        L.ch0 = nch;
+        for (int tap = 0; tap < l.size; ++tap)
+            for (int ci0 = 0; ci0 < cinp; ci0 += krows_max) {
+                if (nch >= DEC_MAXCH) { D.why = "persistent decode: too many weight chunks"; return; }
+                const int kr = std::min(krows_max, cinp - ci0);
+                DecChunk& c = P.C[nch++];
+                c.off = off; c.nfl4 = (short)(kr * L.ns / 4); c.tap = (short)tap; c.ci0 = (short)ci0; c.krows = (short)kr;
+                if (kr % (4 * (DEC_THREADS / L.ns)) || kr % 16) { D.why = "persistent decode: chunk rows not divisible"; return; }
+                off += kr * L.ns;
+            }
+        L.nch = nch - L.ch0;
+    }
+    if (P.L[P.nl - 1].prow != 1 || P.L[P.n_enc].ntaps != 1) { D.why = "persistent decode: unexpected AudioDec shape"; return; }
+    P.nch = nch; P.stream_len = off;
+    // streams
+    std::vector<float> st((size_t)DEC_NC * off, 0.f);
+    for (int r = 0; r < DEC_NC; ++r)
+        for (int li = 0; li < P.nl; ++li) {
+            const LayerDev& l = *nets[li]; const DecLayer& L = P.L[li];
+            REQUIRE(!l.hostW.empty(), "persistent decode: host weights missing");
+            for (int c = L.ch0; c < L.ch0 + L.nch; ++c) {
+                const DecChunk& ch = P.C[c];
+                float* dst = st.data() + (size_t)r * off + ch.off;
+                for (int k = 0; k < ch.krows; ++k) {
+                    const int ci = ch.ci0 + k;
+                    if (ci >= l.cin) continue;
+                    const float* wrow = l.hostW.data() + ((size_t)ch.tap * l.cin + ci) * l.ldw;
+                    for (int n = 0; n < L.ns; ++n) {
+                        int col;
+                        if (L.kind) col = n < L.cs ? r * L.cs + n : l.cout + r * L.cs + (n - L.cs);
+                        else { if (n >= L.cs) continue; col = r * L.cs + n; }
+                        dst[((size_t)(k / 4) * L.ns + n) * 4 + (k % 4)] = wrow[col];
+                    }
+                }
+            }
+        }
+    D.wstream.ensure(st.size() * sizeof(float));
+    CUDA_CHECK(cudaMemcpy(D.wstream.p, st.data(), st.size() * sizeof(float), cudaMemcpyHostToDevice));
+    // LayerNorm parameters [layer][gamma1 | beta1 | gamma2 | beta2][256]
+    D.lnp.ensure((size_t)P.nl * 1024 * sizeof(float));
+    CUDA_CHECK(cudaMemset(D.lnp.p, 0, D.lnp.bytes));
+    for (int li = 0; li < P.nl; ++li) {
+        const LayerDev& l = *nets[li];
+        float* base = D.lnp.as<float>() + (size_t)li * 1024;
+        const float* src[4] = {l.g1, l.b1, l.kind == K_HC ? l.g2 : nullptr, l.kind == K_HC ? l.b2 : nullptr};
+        for (int q = 0; q < 4; ++q)
+            if (src[q]) CUDA_CHECK(cudaMemcpy(base + q * 256, src[q], (size_t)l.cout * sizeof(float), cudaMemcpyDeviceToDevice));
+        P.lnp[li] = base; P.bias[li] = l.bias;
+    }
+    P.wstream = D.wstream.as<float>();
+    for (auto* lp : nets) { lp->hostW.clear(); lp->hostW.shrink_to_fit(); }
+    D.max_clusters = decode_max_active_clusters();
+    if (D.max_clusters < 1) { D.why = "persistent decode: a 16-CTA cluster with " + std::to_string(decode_smem_bytes()) + " B of shared memory cannot be scheduled"; return; }
+    D.ok = true; D.why.clear();
 }
 
 void commit_params(H* h) {
@@ -385,6 +504,7 @@ void commit_params(H* h) {
         }
         throw std::runtime_error("staged variable count does not match the path's variable set");
     }
+    pack_decode(h);
     h->staged.clear();
     h->committed = true;
 }
@@ -421,6 +541,9 @@ void ensure_ws(H* h, int B) {
         h->arpl[i].ensure(bytes);
         CUDA_CHECK(cudaMemset(h->arpl[i].p, 0, h->arpl[i].bytes));
     }
+    h->dec.scr.ensure((size_t)roundup(B, DEC_GMAX) * 85 * 512 * sizeof(float));
+    h->dec.stats.ensure((size_t)2 * B * sizeof(int));
+    h->dec.pfinal.ensure((size_t)B * sizeof(int));
     h->ws_B = B;
 }
 
@@ -456,22 +579,6 @@ void run_block(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
                int extra_shift = 0) {
     H* h = lc.h;
     REQUIRE(l.kind != K_D, "run_block: transposed conv must use run_deconv");
-    const int Mrows = win.B * win.R;
-    if (h->tensor_path == 2 && Mrows <= 256 && rows_block_supported(l.kind == K_HC ? 1 : 0, l.cin, l.cout, l.size)) {
-        // mode 2 (experiment): the whole block in ONE 8-CTA cluster launch, no pre-LN round trip.  Measured
-        // slower than split-K GEMM + LN kernel (B=1: 336 vs 243 us per decode step): an SM pulls only
-        // ~50 GB/s from L2, so concentrating a block's 1.5 MB of weights on 8 SMs costs more than the
-        // second kernel boundary saves; the split-K form spreads them over ~100 SMs.
-        RowsBlockArgs r{};
-        r.W = l.W; r.bias = l.bias; r.g1 = l.g1; r.b1 = l.b1; r.g2 = l.g2; r.b2 = l.b2;
-        r.X = X; r.ldx = ldx; r.out = out; r.ldo = ldo; r.out2 = out2; r.ldo2 = ldo2; r.ldw = l.ldw;
-        r.kind = l.kind == K_HC ? 1 : 0; r.K = l.cin; r.C = l.cout; r.ntaps = l.size; r.act = act;
-        const int tot_ = (l.size - 1) * rate, left_ = causal ? tot_ : tot_ / 2;
-        for (int j = 0; j < l.size; ++j) r.shifts[j] = j * rate - left_ + extra_shift;
-        r.win = win;
-        launch_rows_block(r, lc.s); lc.count();
-        return;
-    }
     ConvArgs c{};
     c.X = X; c.ldx = ldx; c.Y = h->scratch.as<float>(); c.ldy = l.ldw; c.bias = l.bias;
     c.K = l.cin; c.N = l.nconv; c.ldw = l.ldw;
@@ -487,12 +594,11 @@ void run_block(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     n.Y = c.Y; n.ldy = l.ldw; n.g1 = l.g1; n.b1 = l.b1; n.g2 = l.g2; n.b2 = l.b2;
     n.X = X; n.ldx = ldx; n.out = out; n.ldo = ldo; n.out2 = out2; n.ldo2 = ldo2;
     n.C = l.cout; n.mode = (l.kind == K_HC) ? 1 : 0; n.act = act; n.win = win;
-    // DCTTS_FUSED_LN=1 (experiment): GEMM and LN epilogue in one launch, the last CTAs of each 16-row block
+    // option fused_ln (experiment): GEMM and LN epilogue in one launch, the last CTAs of each 16-row block
     // waiting on an arrival counter.  Parity-green but SLOWER than two graph nodes (B=1: 220 vs 187 us per
     // decode step, B=32: 339 vs 303): a kernel boundary inside a CUDA graph costs less than the
     // ticket / spin / L2 round trips that replace it.
-    static const bool fuse_ln = getenv("DCTTS_FUSED_LN") != nullptr;
-    if (fuse_ln && h->tickets.p && conv_gemm_ln_fusable(c, n)) {
+    if (h->opt.fused_ln && h->tickets.p && conv_gemm_ln_fusable(c, n)) {
         launch_conv_gemm_ln(c, n, h->tickets.as<int>(), lc.s, h->scratch.bytes); lc.count();
         return;
     }
@@ -572,13 +678,14 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     // each stages half of the slice's weight slab; the accumulator is 512 columns (256 gate + 256 info).
     // Two CTAs per SM (default for launches that fill the machine): 32-wide slab, two pipeline stages -> ~105 KB of
     // shared memory and 256 TMEM columns per CTA, so one tile's epilogue runs under the other tile's main loop
-    // (SSRN at B=32: 5.61 -> 4.66 ms).  DCTTS_TC_NO_OCC2=1 turns it off; DCTTS_TC_CG2=1 selects CTA pairs instead
+    // (SSRN at B=32: 5.61 -> 4.66 ms).  Option tc_occ2 = 0 turns it off; tc_cg2 = 1 selects CTA pairs instead
     // (cta_group::2 needs all 512 TMEM columns, so the two cannot be combined).
-    static const bool occ2_mode = getenv("DCTTS_TC_NO_OCC2") == nullptr;
-    // DCTTS_TC_CG2: 1 = wide pairs (N = 512 per pair, all of TMEM, one CTA per SM), 2 = narrow pairs (N = 256 per pair,
+    H* h = lc.h;
+    const bool occ2_mode = h->opt.tc_occ2 != 0;
+    // option tc_cg2: 1 = wide pairs (N = 512 per pair, all of TMEM, one CTA per SM), 2 = narrow pairs (N = 256 per pair,
     // 256 TMEM columns per CTA, so two CTAs per SM still overlap epilogue and main loop; the cluster doubles to
     // 2 x slices CTAs, 16 for the C = 1024 blocks)
-    static const int cg2_mode = getenv("DCTTS_TC_CG2") ? atoi(getenv("DCTTS_TC_CG2")) : 0;
+    const int cg2_mode = h->opt.tc_cg2;
     const bool pairable = p.mode != 0 && p.half == 128 && p.bn == 256 && !win.jptr && TT == 128 && TB == 1;
     // Only when the paired grid still fills the machine: pairs halve the CTA count (B=1 SSRN: 1.09 vs 0.74 ms).
     const bool wide_pairs = cg2_mode == 1 && pairable && (p.ncta % 2) == 0 && tiles * p.ncta >= 4 * 148;
@@ -586,9 +693,9 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     const int cg = (wide_pairs || narrow_pairs) ? 2 : 1;
     if (wide_pairs) { a.bn = 512; a.half = 256; }
     const int cluster = narrow_pairs ? 2 * p.ncta : p.ncta;
-    // DCTTS_TC_PAIR=1: two 128-row tiles per CTA sharing one weight slab (a third fewer bytes per MMA).
+    // option tc_tile_pair: two 128-row tiles per CTA sharing one weight slab (a third fewer bytes per MMA).
     // Measured no gain (SSRN/HC_11: 1.27 vs 1.26 ms), like TMA multicast and a deeper pipeline.
-    static const bool pair = getenv("DCTTS_TC_PAIR") != nullptr;
+    const bool pair = h->opt.tc_tile_pair != 0;
     const int mt = (cg == 1 && pair && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 4 * 148) ? 2 : 1;
     const bool occ2 = occ2_mode && cg == 1 && mt == 1 && !win.jptr && TT == 128 && TB == 1 && tiles * p.ncta >= 148;
     const int bk = (mt == 2 || occ2 || narrow_pairs) ? 32 : (cg == 2 ? 64 : tc_bk());
@@ -604,14 +711,14 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     a.X = X; a.out = out; a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.sig_f32 = sig_f32; a.ld_sig = ld_sig; a.sig = sig;
     // the A tile is identical in all CTAs of the cluster: fetch it once (TMA multicast) when the
     // tile is 128 consecutive time rows, each CTA contributing 128/ncta of them
-    static const bool no_mcast = getenv("DCTTS_TC_NO_MCAST") != nullptr;
+    const bool no_mcast = h->opt.tc_mcast == 0;
     a.mcast = (!no_mcast && cg == 1 && p.ncta > 1 && TT == 128 && TB == 1) ? 1 : 0;
     const int box_rows = a.mcast ? TT / p.ncta : TT;
     CUtensorMap mAh, mAl;
     tc_make_act_map(&mAh, X.hi, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
     tc_make_act_map(&mAl, X.lo, l.cin, X.ld, win.L, win.B, box_rows, TB, bk);
-    // DCTTS_TC_DEBUG=1: progress markers in host-mapped memory, dumped after a synchronising launch
-    static const bool debug = getenv("DCTTS_TC_DEBUG") != nullptr;
+    // option tc_debug: progress markers in host-mapped memory, dumped after a synchronising launch
+    const bool debug = h->opt.tc_debug != 0;
     static int* dbg_host = nullptr;
     if (debug) {
         if (!dbg_host) CUDA_CHECK(cudaHostAlloc(&dbg_host, 16 * 64 * sizeof(int), cudaHostAllocMapped));
@@ -625,7 +732,7 @@ void run_block_tc(Launch& lc, const LayerDev& l, int rate, bool causal, int act,
     else if (bk != tc_bk()) { tc_make_w_map(&mWh, p.Whi, p.Ktot, p.nrows, p.bn, bk); tc_make_w_map(&mWl, p.Wlo, p.Ktot, p.nrows, p.bn, bk); }
     // hc on full sequences: the residual tile comes in by TMA and the output planes leave by TMA (staged in the
     // same drained pipeline stage), instead of row-scattered 32-byte loads / stores from the epilogue threads
-    static const bool no_rtma = getenv("DCTTS_TC_NO_RESID_TMA") != nullptr;
+    const bool no_rtma = h->opt.tc_resid_tma == 0;
     CUtensorMap io[4];
     a.resid_tma = 0;
     a.out_tma = 0;
@@ -834,21 +941,50 @@ void build_ar_graph(H* h, int B) {
     h->ar_B = B;
 }
 
+// The whole AR loop as one persistent launch (kernels_decode.cu).  Returns false when this handle / device cannot run it.
+bool decode_cluster(H* h, int B, int steps, cudaStream_t s) {
+    auto& D = h->dec;
+    if (!D.ok || h->opt.decode_mode != 1) return false;
+    const dctts_hparams& hp = h->hp;
+    IntBufs ib = ints(h);
+    DecParams P = D.tab;
+    for (int li = 0; li < P.nl; ++li) {
+        const bool enc = li < P.n_enc;
+        P.out_hist[li] = enc ? h->ae_out[li].as<float>() : h->ad_out[li - P.n_enc].as<float>();
+        P.in_hist[li] = li == 0 ? nullptr : (li == P.n_enc ? h->rbuf.as<float>() : P.out_hist[li - 1]);
+    }
+    P.kv = h->kv.as<float>(); P.ybuf = h->ybuf.as<float>(); P.rbuf = h->rbuf.as<float>(); P.pre_scr = D.scr.as<float>();
+    P.p_hist = ib.p_hist; P.p_final = D.pfinal.as<int>(); P.stats = D.stats.as<int>();
+    P.B = B; P.G = std::min(DEC_GMAX, (B + 7) / 8); P.T = hp.max_T; P.N = hp.max_N; P.d = hp.d; P.n_mels = hp.n_mels;
+    P.win_size = hp.attention_win_size; P.steps = steps;
+    const int n_clusters = (B + P.G - 1) / P.G;
+    cudaError_t e = launch_decode_cluster(P, n_clusters, s);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("decode_cluster_kernel launch failed: ") + cudaGetErrorString(e));
+    h->launches += 1;
+    D.last_clusters = n_clusters; D.last_moved_frames = -1;
+    return true;
+}
+
 void text2mel_generate(H* h, const int* L, int B, int steps, float* Y, int* prev_hist,
                        long long* maxatt, float* align, cudaStream_t s) {
     const dctts_hparams& hp = h->hp;
     const int T = hp.max_T, N = hp.max_N, d = hp.d;
     if (steps <= 0 || steps > T) steps = T;
     ensure_ws(h, B);
-    build_ar_graph(h, B);
+    const bool cluster = h->dec.ok && h->opt.decode_mode == 1;
+    if (!cluster) build_ar_graph(h, B);
     IntBufs ib = ints(h);
     Launch lc{h, s};
     run_textenc(lc, L, B, h->kv.as<float>());
     CUDA_CHECK(cudaMemsetAsync(h->ybuf.p, 0, (size_t)B * T * hp.n_mels * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(h->ibuf.p, 0, (size_t)(4 + 3 * h->ws_B + (size_t)h->ws_B * T) * sizeof(int), s));
-    for (int j = 0; j < steps; ++j) {
-        CUDA_CHECK(cudaGraphLaunch(h->ar_exec, s));
-        h->launches += h->ar_nodes;
+    if (cluster) {
+        decode_cluster(h, B, steps, s);
+    } else {
+        for (int j = 0; j < steps; ++j) {
+            CUDA_CHECK(cudaGraphLaunch(h->ar_exec, s));
+            h->launches += h->ar_nodes;
+        }
     }
     if (Y) CUDA_CHECK(cudaMemcpyAsync(Y, h->ybuf.p, (size_t)B * T * hp.n_mels * sizeof(float),
                                       cudaMemcpyDeviceToDevice, s));
@@ -986,6 +1122,7 @@ void train_init(H* h, int B, float rate, int num, int T_in) {
     CUDA_CHECK(cudaDeviceSynchronize());
     if (h->ar_exec) { cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0; }
     h->tensor_path = 0;            // the optimiser updates the fp32 weights only: this handle stops using the packed fp16 planes
+    h->dec.ok = false; h->dec.why = "this handle has been trained: the packed decode stream is stale";
     tr.ready = false;
     const dctts_hparams& hp = h->hp;
     const int N = hp.max_N, T = T_in, d = hp.d;
@@ -1293,7 +1430,6 @@ int dctts_create(const dctts_hparams* hp, int device, dctts_handle* out) {
         if (prop.major != 10) throw std::runtime_error("dctts_create: this library is built for sm_100a (B200) only");
         if (hp->d > 256 || hp->d % 8 || hp->e % 4 || hp->max_N > 192 || hp->r != 4)
             throw std::runtime_error("dctts_create: unsupported hyper-parameters");
-        if (getenv("DCTTS_PDL")) pdl_enabled() = true;
         std::unique_ptr<dctts_handle_s> h(new dctts_handle_s());
         h->hp = *hp; h->device = device; h->F = 1 + hp->n_fft / 2;
         CUDA_CHECK(cudaSetDevice(device));
@@ -1709,18 +1845,20 @@ int64_t dctts_launch_count(dctts_handle h) { return h ? h->launches : -1; }
 
 // CRC-32C (polynomial 0x1EDC6F41, reflected 0x82F63B78), slicing-by-8 on the host.
 uint32_t dctts_crc32c(uint32_t crc, const void* data, int64_t n) {
-    static uint32_t T[8][256];
-    static bool init = false;
-    if (!init) {
-        for (uint32_t i = 0; i < 256; ++i) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
-            T[0][i] = c;
+    struct Table {
+        uint32_t T[8][256];
+        Table() {
+            for (uint32_t i = 0; i < 256; ++i) {
+                uint32_t c = i;
+                for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : (c >> 1);
+                T[0][i] = c;
+            }
+            for (uint32_t i = 0; i < 256; ++i)
+                for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xffu];
         }
-        for (uint32_t i = 0; i < 256; ++i)
-            for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xffu];
-        init = true;
-    }
+    };
+    static const Table tab;                 // C++11: initialised once, thread-safe
+    const auto& T = tab.T;
     const uint8_t* p = static_cast<const uint8_t*>(data);
     uint32_t c = ~crc;
     while (n > 0 && (reinterpret_cast<uintptr_t>(p) & 7u)) { c = (c >> 8) ^ T[0][(c ^ *p++) & 0xffu]; --n; }
@@ -1738,7 +1876,7 @@ uint32_t dctts_crc32c(uint32_t crc, const void* data, int64_t n) {
 
 int dctts_set_tensor_path(dctts_handle h, int32_t mode) {
     return guarded(h, [&] {
-        REQUIRE(mode >= 0 && mode <= 2, "dctts_set_tensor_path: mode must be 0, 1 or 2");
+        REQUIRE(mode == 0 || mode == 1, "dctts_set_tensor_path: mode must be 0 or 1");
         REQUIRE(!(h->tr.ready && mode == 1), "dctts_set_tensor_path: this handle has been trained -- its packed fp16 weight planes "
                 "are stale; load the trained variables (dctts_train_tensor) into a new handle for the tcgen05 kernel set");
         if (mode != h->tensor_path && h->ar_exec) {      // the captured AR step depends on the mode
@@ -1746,6 +1884,68 @@ int dctts_set_tensor_path(dctts_handle h, int32_t mode) {
             cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0;
         }
         h->tensor_path = mode;
+    });
+}
+
+
+// Kernel-variant switches: every value selects a parity-tested code path (tests/test_gpu_variants.py); the defaults are the
+// measured-best configuration.  Replaces the environment variables of round 1, which froze at first use.
+static int* option_slot(dctts_handle h, const char* name) {
+    const std::string n = name ? name : "";
+    if (n == "tc_occ2") return &h->opt.tc_occ2;
+    if (n == "tc_cg2") return &h->opt.tc_cg2;
+    if (n == "tc_tile_pair") return &h->opt.tc_tile_pair;
+    if (n == "tc_mcast") return &h->opt.tc_mcast;
+    if (n == "tc_resid_tma") return &h->opt.tc_resid_tma;
+    if (n == "tc_debug") return &h->opt.tc_debug;
+    if (n == "fused_ln") return &h->opt.fused_ln;
+    if (n == "decode_mode") return &h->opt.decode_mode;
+    return nullptr;
+}
+
+int dctts_set_option(dctts_handle h, const char* name, int32_t value) {
+    return guarded(h, [&] {
+        if (name && std::string(name) == "pdl") { pdl_enabled() = value != 0; return; }     // process-wide launch attribute
+        int* slot = option_slot(h, name);
+        REQUIRE(slot, "dctts_set_option: unknown option");
+        REQUIRE(value >= 0 && value <= 2, "dctts_set_option: value out of range");
+        if (std::string(name) == "decode_mode" && value == 1 && !h->dec.ok && h->committed)
+            throw std::runtime_error("dctts_set_option: persistent decode unavailable: " + h->dec.why);
+        if (*slot != value && h->ar_exec) {                  // the captured AR step bakes the variant in
+            CUDA_CHECK(cudaDeviceSynchronize());
+            cudaGraphExecDestroy(h->ar_exec); h->ar_exec = nullptr; h->ar_B = 0;
+        }
+        *slot = value;
+    });
+}
+
+int dctts_get_option(dctts_handle h, const char* name, int32_t* value) {
+    return guarded(h, [&] {
+        REQUIRE(value, "dctts_get_option: null output");
+        if (name && std::string(name) == "pdl") { *value = pdl_enabled() ? 1 : 0; return; }
+        if (name && std::string(name) == "decode_available") { *value = h->dec.ok ? 1 : 0; return; }
+        int* slot = option_slot(h, name);
+        REQUIRE(slot, "dctts_get_option: unknown option");
+        *value = *slot;
+    });
+}
+
+// Of the last dctts_text2mel_generate on the persistent decode path: frames in which at least one utterance of a cluster
+// moved its attention window (summed over clusters), utterance-frames whose receptive field was recomputed, clusters used.
+int dctts_decode_stats(dctts_handle h, int32_t* moved_frames, int32_t* moved_utterance_frames, int32_t* clusters) {
+    return guarded(h, [&] {
+        auto& D = h->dec;
+        REQUIRE(D.last_clusters > 0, "dctts_decode_stats: no persistent decode has run on this handle");
+        if (D.last_moved_frames < 0) {
+            std::vector<int> st(2 * (size_t)D.last_clusters);
+            CUDA_CHECK(cudaDeviceSynchronize());
+            CUDA_CHECK(cudaMemcpy(st.data(), D.stats.p, st.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            D.last_moved_frames = 0; D.last_moved_utt = 0;
+            for (int c = 0; c < D.last_clusters; ++c) { D.last_moved_frames += st[2 * c]; D.last_moved_utt += st[2 * c + 1]; }
+        }
+        if (moved_frames) *moved_frames = D.last_moved_frames;
+        if (moved_utterance_frames) *moved_utterance_frames = D.last_moved_utt;
+        if (clusters) *clusters = D.last_clusters;
     });
 }
 

@@ -96,21 +96,6 @@ struct AttnArgs {
     RowWin win;                    // rows = query rows (L = T)
 };
 
-// One block on a few rows in one launch (kernels_rows.cu): 8-CTA cluster, GEMM + LN fused.
-struct RowsBlockArgs {
-    const float* W; const float* bias;      // [ntaps][K][ldw], [ldw]
-    const float* g1; const float* b1; const float* g2; const float* b2;
-    const float* X;                         // input rows (B, L, K); also the highway residual
-    float* out; float* out2;                // output rows (B, L, C); optional sigmoid copy
-    int ldw, ldx, ldo, ldo2;
-    int kind;                               // 0 conv1d, 1 hc
-    int K, C, ntaps, act;
-    int shifts[3];
-    RowWin win;
-};
-bool rows_block_supported(int kind, int K, int C, int ntaps);
-void launch_rows_block(const RowsBlockArgs& a, cudaStream_t s);
-
 // Griffin-Lim vocoder (kernels_vocoder.cu; reference utils.py:67-114)
 struct VocoderArgs {
     const float* mag;          // (B, T, F) normalised linear magnitudes in [0, 1]

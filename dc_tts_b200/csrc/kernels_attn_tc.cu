@@ -280,7 +280,10 @@ int attn_tc_padded_keys() { return AT_NP; }
 
 void launch_attention_tc(const Planes& Q, const Planes& K, const Planes& Vt, const AttnTcArgs& a, int B, cudaStream_t s) {
     if (a.d != AT_D || a.N > AT_NP) throw std::runtime_error("attention_tc: unsupported d / N");
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};      // per device (the attribute is per device, not per process)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& attr_set = attr_set_dev[dev & 63];
     const size_t smem = AT_SMEM_MAIN + 128 + 1024;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

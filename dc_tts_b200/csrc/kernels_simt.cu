@@ -12,7 +12,7 @@
 
 namespace dctts {
 
-bool& pdl_enabled() { static bool on = false; return on; }   // opt-in (DCTTS_PDL=1): measured no gain inside CUDA graphs
+bool& pdl_enabled() { static bool on = false; return on; }   // opt-in (dctts_set_option "pdl"): measured no gain inside CUDA graphs
 
 __device__ __forceinline__ int win_t_end(const RowWin& w) {
     return w.jptr ? __ldg(w.jptr) : (w.L - 1);

@@ -604,8 +604,7 @@ void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int 
 int tc_bk() {
     // measured (SSRN/HC_11, B=32): BK=64 / 2 stages 1.24 ms, BK=32 / 4 stages 1.32 ms -- the kernel is bound by
     // bytes delivered per SM, not by pipeline depth, so the wider slab (half as many TMA rows) wins
-    static const int bk = (getenv("DCTTS_TC_BK") && atoi(getenv("DCTTS_TC_BK")) == 32) ? 32 : 64;
-    return bk;
+    return 64;
 }
 
 int tc_stages_for(int bn, int bk, int mt) {      // bn = weight rows staged per CTA
@@ -617,7 +616,12 @@ int tc_stages_for(int bn, int bk, int mt) {      // bn = weight rows staged per 
 void launch_conv_ln_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& w_hi,
                        const CUtensorMap& w_lo, const CUtensorMap* io, const TcArgs& a, int ncta, int ctas_y, int bk, int mt, int cg,
                        cudaStream_t s) {
-    static bool attr_set = false;
+    // the attributes are per device: cache them per device, not per process (a second Engine on another GPU
+    // of the same process must raise its own limits)
+    static bool attr_set_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& attr_set = attr_set_dev[dev & 63];
     const int max_smem = 227 * 1024;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv_ln_tc_kernel<64, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);

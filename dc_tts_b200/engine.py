@@ -106,6 +106,21 @@ class Engine:
     def set_tensor_path(self, mode):
         self._check(self._lib.dctts_set_tensor_path(self._h, int(mode)), "dctts_set_tensor_path")
 
+    def set_option(self, name, value):
+        """Kernel-variant switch (include/dctts.h: dctts_set_option), e.g. ("decode_mode", 0) for the graph-per-frame loop."""
+        self._check(self._lib.dctts_set_option(self._h, name.encode(), int(value)), "dctts_set_option(%s)" % name)
+
+    def get_option(self, name):
+        v = C.c_int32(0)
+        self._check(self._lib.dctts_get_option(self._h, name.encode(), C.byref(v)), "dctts_get_option(%s)" % name)
+        return int(v.value)
+
+    def decode_stats(self):
+        """(frames with a receptive-field recompute summed over clusters, utterance-frames recomputed, clusters)."""
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.dctts_decode_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "dctts_decode_stats")
+        return int(a.value), int(b.value), int(c.value)
+
     def reserve(self, batch):
         self._check(self._lib.dctts_reserve(self._h, int(batch)), "dctts_reserve")
 

@@ -184,10 +184,21 @@ int64_t dctts_launch_count(dctts_handle h);
 uint32_t dctts_crc32c(uint32_t crc, const void* data, int64_t n);
 /* Selects the kernel set: 0 = one fp32 CUDA-core GEMM + one LN kernel per block (baseline),
  * 1 = default: tcgen05 split-fp16 (3-MMA, fp32-grade) fused blocks where they apply (whole
- * networks, full-sequence attention, and the wide AudioDec rows of the decode step when B >= 8),
- * split-K fp32 kernels for the few-row decode blocks, 2 = experiment: fp32 CUDA-core blocks with
- * the fused few-row block kernel (8-CTA cluster, GEMM + LN in one launch; measured slower). */
+ * networks, full-sequence attention, and the wide AudioDec rows of the graph decode step when B >= 8). */
 int dctts_set_tensor_path(dctts_handle h, int32_t mode);
+
+/* Kernel-variant switches (every value is a parity-tested code path; defaults = measured best):
+ *   "decode_mode"  1 = the whole AR loop (synthesize.py:45-54) as ONE persistent cluster kernel (default),
+ *                  0 = one captured CUDA graph per mel frame (round-1 path)
+ *   "tc_occ2" 0/1, "tc_cg2" 0/1/2, "tc_tile_pair" 0/1, "tc_mcast" 0/1, "tc_resid_tma" 0/1: tcgen05 block kernel variants
+ *   "fused_ln" 0/1: graph decode, GEMM + LN in one launch;  "tc_debug" 0/1;  "pdl" 0/1 (process-wide)
+ * dctts_get_option also answers "decode_available" (1 when this handle / device can run the persistent decode). */
+int dctts_set_option(dctts_handle h, const char* name, int32_t value);
+int dctts_get_option(dctts_handle h, const char* name, int32_t* value);
+/* Of the last dctts_text2mel_generate on the persistent decode path: frames in which a cluster had to recompute the
+ * AudioDec receptive field because an attention window moved (summed over clusters), utterance-frames recomputed,
+ * clusters launched.  Synchronises the device. */
+int dctts_decode_stats(dctts_handle h, int32_t* moved_frames, int32_t* moved_utterance_frames, int32_t* clusters);
 /* Measurement aid for bench.py's roofline leg: runs the block `scope` on a synthetic
  * (B,L,Cin) input `warmup`+`iters` times and returns the mean device time of each of its
  * kernels (CUDA events on `stream` around every launch), ms_per_kernel[0..*n_kernels), <= 8. */

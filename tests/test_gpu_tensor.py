@@ -111,9 +111,11 @@ def test_tensor_path_close_to_fp32_path(engine):
     assert (Z0 - Z1).abs().max().item() < 1e-4
 
 
-def test_generate_tensor_pyramid_vs_oracle(tc, params):
-    """B >= 8 moves the 85..59-row AudioDec pyramid of every AR step onto tcgen05 (windowed
+@pytest.mark.parametrize("decode_mode", [0, 1], ids=["graph", "cluster"])
+def test_generate_tensor_pyramid_vs_oracle(tc, params, decode_mode):
+    """graph decode: B >= 8 moves the 85..59-row AudioDec pyramid of every AR step onto tcgen05 (windowed
     128-row tiles ending at row j); free-running 40 steps against the oracle's literal schedule."""
+    tc.set_option("decode_mode", decode_mode)
     L = np.concatenate([synthetic_text(1, 40 + 15 * i, seed=60 + i) for i in range(8)])
     steps = 40
     r = rt.synthesize(params, L, steps=steps, literal=False, record=True)
@@ -127,4 +129,5 @@ def test_generate_tensor_pyramid_vs_oracle(tc, params):
     tc.set_tensor_path(0)
     Y0, P0, _, _ = tc.text2mel_generate(L, steps=steps)
     tc.set_tensor_path(1)
+    tc.set_option("decode_mode", 1)
     assert torch.equal(P0[ok], P[ok]) and (Y0[ok] - Y[ok]).abs().max().item() < 1e-4

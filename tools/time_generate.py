@@ -1,22 +1,48 @@
-"""Time Text2Mel generation (TextEnc + 210 CUDA-graph steps) for a list of batch sizes.
-   python tools/time_generate.py 1 32"""
-import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import torch
-from dc_tts_b200.engine import Engine
-from dc_tts_b200.params import init_params, synthetic_text
+"""Time Text2Mel generation (TextEnc + 210 frames) for a list of batch sizes, persistent cluster decode
+(decode_mode 1) next to the graph-per-frame loop (decode_mode 0), and compare their outputs.
+   python tools/time_generate.py 1 32 [--steps N] [--modes 1,0]"""
+import argparse
+import os
+import sys
+import time
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+from dc_tts_b200.engine import Engine  # noqa: E402
+from dc_tts_b200.params import init_params, synthetic_text  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("batches", type=int, nargs="*", default=[1, 32])
+ap.add_argument("--steps", type=int, default=210)
+ap.add_argument("--modes", default="1,0")
+ap.add_argument("--iters", type=int, default=5)
+a = ap.parse_args()
 e = Engine(0)
 e.load_params(init_params(0, "perturbed"))
-for B in [int(x) for x in sys.argv[1:]] or [1, 32]:
+print("decode_available", e.get_option("decode_available"), flush=True)
+for B in a.batches:
     L = synthetic_text(B, 100, seed=0)
-    for _ in range(2):
-        e.text2mel_generate(L)
-    torch.cuda.synchronize()
-    n = 5
-    t0 = time.perf_counter()
-    for _ in range(n):
-        Y = e.text2mel_generate(L)[0]
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / n
-    print("generate B=%d: %.2f ms (%.1f us/step)  checksum %.6f" % (B, dt * 1e3, dt * 1e6 / 210, float(Y.double().sum())))
+    outs = {}
+    for mode in [int(m) for m in a.modes.split(",")]:
+        e.set_option("decode_mode", mode)
+        for _ in range(2):
+            e.text2mel_generate(L, steps=a.steps)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.iters):
+            Y, P, _, _ = e.text2mel_generate(L, steps=a.steps)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / a.iters
+        extra = ""
+        if mode == 1:
+            fr, ut, cl = e.decode_stats()
+            extra = "  clusters %d, cluster-frames with a recompute %d, utterance-frames recomputed %d" % (cl, fr, ut)
+        print("generate B=%d mode=%d: %.2f ms (%.1f us/frame)  checksum %.6f%s"
+              % (B, mode, dt * 1e3, dt * 1e6 / a.steps, float(Y.double().sum()), extra), flush=True)
+        outs[mode] = (Y, P)
+    if len(outs) == 2:
+        (Y1, P1), (Y0, P0) = outs[1], outs[0]
+        same = (P0 == P1).all(dim=1)
+        print("   windows equal for %d/%d utterances; max|dY| over those %.3e"
+              % (int(same.sum()), B, float((Y0[same] - Y1[same]).abs().max()) if same.any() else float("nan")), flush=True)
+e.set_option("decode_mode", 1)
