@@ -167,6 +167,7 @@ struct dctts_handle_s {
         int tc_resid_tma = 1;     // hc: residual in / planes out through TMA
         int tc_debug = 0;         // progress markers + in-kernel cycle stamps (synchronising)
         int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
+        int decode_prof = 0;      // persistent decode: record SM-clock lap timers of cluster 0 / rank 0 (dctts_decode_profile)
         int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
     } opt;
 
@@ -174,7 +175,7 @@ struct dctts_handle_s {
     struct {
         bool ok = false;          // stream packed, geometry supported, 16-CTA clusters schedulable
         DecParams tab{};          // layer / chunk tables (+ parameter pointers); per-call fields filled by text2mel_generate
-        DevBuf wstream, lnp, scr, stats, pfinal;
+        DevBuf wstream, lnp, scr, stats, pfinal, prof;
         int max_clusters = 0;
         std::string why;          // why not ok
         int last_moved_frames = -1, last_moved_utt = -1, last_clusters = 0;
@@ -185,7 +186,7 @@ struct dctts_handle_s {
         for (void* p : param_allocs) cudaFree(p);
         for (DevBuf* b : {&tr.pre, &tr.out, &tr.emb, &tr.R, &tr.align, &tr.dS, &tr.gbuf[0], &tr.gbuf[1], &tr.gbuf[2], &tr.gbuf[3], &tr.dy,
                           &tr.wT, &tr.zeros, &tr.gts, &tr.sums, &tr.ids, &tr.grads, &tr.mom, &tr.vel, &tr.entries}) b->release();
-        dec.wstream.release(); dec.lnp.release(); dec.scr.release(); dec.stats.release(); dec.pfinal.release();
+        dec.prof.release(); dec.wstream.release(); dec.lnp.release(); dec.scr.release(); dec.stats.release(); dec.pfinal.release();
         tickets.release(); scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
         for (auto& b : plane) b.release();
@@ -955,6 +956,8 @@ bool decode_cluster(H* h, int B, int steps, cudaStream_t s) {
     }
     P.kv = h->kv.as<float>(); P.ybuf = h->ybuf.as<float>(); P.rbuf = h->rbuf.as<float>(); P.pre_scr = D.scr.as<float>();
     P.p_hist = ib.p_hist; P.p_final = D.pfinal.as<int>(); P.stats = D.stats.as<int>();
+    P.prof = nullptr;
+    if (h->opt.decode_prof) { D.prof.ensure(16 * sizeof(long long)); CUDA_CHECK(cudaMemsetAsync(D.prof.p, 0, 16 * sizeof(long long), s)); P.prof = D.prof.as<long long>(); }
     P.B = B; P.G = std::min(DEC_GMAX, (B + 7) / 8); P.T = hp.max_T; P.N = hp.max_N; P.d = hp.d; P.n_mels = hp.n_mels;
     P.win_size = hp.attention_win_size; P.steps = steps;
     const int n_clusters = (B + P.G - 1) / P.G;
@@ -1900,6 +1903,7 @@ static int* option_slot(dctts_handle h, const char* name) {
     if (n == "tc_debug") return &h->opt.tc_debug;
     if (n == "fused_ln") return &h->opt.fused_ln;
     if (n == "decode_mode") return &h->opt.decode_mode;
+    if (n == "decode_prof") return &h->opt.decode_prof;
     return nullptr;
 }
 
@@ -1946,6 +1950,20 @@ int dctts_decode_stats(dctts_handle h, int32_t* moved_frames, int32_t* moved_utt
         if (moved_frames) *moved_frames = D.last_moved_frames;
         if (moved_utterance_frames) *moved_utterance_frames = D.last_moved_utt;
         if (clusters) *clusters = D.last_clusters;
+    });
+}
+
+// SM-clock lap timers of the last persistent decode run with option decode_prof = 1 (cluster 0, CTA rank 0, thread 0):
+// cycles[0..13] = block start / stream wait / GEMV / slot release / gather / cluster barrier / LayerNorm / mix / attention /
+// recompute attention / recompute GEMM / recompute LayerNorm / recompute barriers / frame bookkeeping.
+int dctts_decode_profile(dctts_handle h, int64_t* cycles, int32_t n) {
+    return guarded(h, [&] {
+        REQUIRE(cycles && n >= 1 && n <= 16, "dctts_decode_profile: bad arguments");
+        REQUIRE(h->dec.prof.p, "dctts_decode_profile: no profiled decode has run (set option decode_prof)");
+        CUDA_CHECK(cudaDeviceSynchronize());
+        long long v[16];
+        CUDA_CHECK(cudaMemcpy(v, h->dec.prof.p, sizeof(v), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) cycles[i] = v[i];
     });
 }
 

@@ -52,7 +52,13 @@ struct Smem {
     float wrk[WRK_F];
     unsigned long long full[DEC_NSLOT];
     int p_cur[GMAX], p_prev[GMAX], p_next[GMAX], moved[GMAX];
+    long long prof[16], prof_last;
 };
+
+// lap timer (option decode_prof): thread 0 attributes the cycles since the previous lap to bucket i
+#define LAP(i) do { if (P.prof && threadIdx.x == 0) { const long long now_ = clock64(); S.prof[i] += now_ - S.prof_last; S.prof_last = now_; } } while (0)
+enum { LP_START = 0, LP_WAIT = 1, LP_GEMV = 2, LP_RELEASE = 3, LP_GATHER = 4, LP_CBAR = 5, LP_LN = 6, LP_MIX = 7, LP_ATT = 8,
+       LP_PYR_ATT = 9, LP_PYR_GEMM = 10, LP_PYR_LN = 11, LP_PYR_BAR = 12, LP_FRAME = 13 };
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -201,6 +207,7 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
         cp_async_wait<1>();                 // everything but the group just committed: this block's taps and parameters
     }
     __syncthreads();
+    LAP(LP_START);
 
     float acc[GMAX];
 #pragma unroll
@@ -208,11 +215,14 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
     for (int c = l.ch0; c < l.ch0 + l.nch; ++c) {
         const DecChunk& ch = P.C[c];
         const float* w = stream_acquire(S, st);
+        LAP(LP_WAIT);
         const float* x = (ch.tap == l.ntaps - 1) ? &S.xcur[cb][0][ch.ci0] : &S.xtap[li & 1][0][ch.tap * 256 + ch.ci0];
         if (l.ns == 32) gemv_chunk<32>(w, x, ch.krows, G, acc);
         else if (l.ns == 16) gemv_chunk<16>(w, x, ch.krows, G, acc);
         else gemv_chunk<8>(w, x, ch.krows, G, acc);
+        LAP(LP_GEMV);
         stream_release(P, S, st);
+        LAP(LP_RELEASE);
     }
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
@@ -235,7 +245,9 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
             }
         }
     }
+    LAP(LP_GATHER);
     cluster_sync_all();
+    LAP(LP_CBAR);
     // LayerNorm of whole rows, redundantly in every CTA: warp -> (utterance, half)
     const int nh = l.kind + 1, C = l.cout;
     float* nrm = S.wrk;                                   // [g][half][256]
@@ -258,6 +270,7 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
         for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < C) nrm[(g * 2 + hf) * 256 + c] = v[i] * inv * gam[c] + bet[c]; }
     }
     __syncthreads();
+    LAP(LP_LN);
     const bool last = (li + 1 == P.nl);
     float* oh = P.out_hist[li];
     for (int i = tid; i < G * C; i += NT) {
@@ -281,6 +294,7 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
     if (last) {                                                     // AudioEnc C_1 reads K = 128 padded channels
         for (int i = tid; i < G * (128 - C); i += NT) S.xcur[cb ^ 1][i / (128 - C)][C + i % (128 - C)] = 0.f;
     }
+    LAP(LP_MIX);
     return cb ^ 1;
 }
 
@@ -501,6 +515,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
     }
     for (int i = tid; i < 2 * GMAX * XLD; i += NT) { (&S.xcur[0][0][0])[i] = 0.f; (&S.xtap[0][0][0])[i] = 0.f; (&S.pre[0][0][0])[i] = 0.f; }
     if (tid < GMAX) { S.p_cur[tid] = 0; S.p_prev[tid] = 0; S.p_next[tid] = 0; S.moved[tid] = 0; }
+    if (tid < 16) S.prof[tid] = 0;
     __syncthreads();
     if (tid == 0) for (int s = 0; s < DEC_NSLOT; ++s) stream_issue(P, S, st, s);
     prefetch_params(P, S, 0, rank);
@@ -509,6 +524,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
 
     int cb = 0;
     int n_moved_frames = 0, n_moved_utt = 0;
+    if (tid == 0) S.prof_last = clock64();
     for (int j = 0; j < P.steps; ++j) {
         bool any_moved = false;
         if (tid < GMAX) S.moved[tid] = (tid < G && j > 0 && S.p_cur[tid] != S.p_prev[tid]) ? 1 : 0;
@@ -533,6 +549,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
         }
         cb ^= 1;
         __syncthreads();
+        LAP(LP_ATT);
 
         int li = P.n_enc;
         if (any_moved) {
@@ -556,6 +573,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
                 *reinterpret_cast<float4*>(rr + P.d + lane * 8 + 4) = q1;
             }
             cluster_sync_all();
+            LAP(LP_PYR_ATT);
             for (; li < P.nl && P.L[li].prow > 1; ++li) {
                 const int nl_next = li + 1;               // AudioDec never ends on a recomputed block
                 prefetch_params(P, S, nl_next, rank);
@@ -565,9 +583,13 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
                 const RowList rl = make_rows(S, G, j, P.L[li].prow);
                 if (P.L[li].ns == 32) pyr_gemm<4>(P, S, st, li, j, b0, rl, rank, scr);
                 else pyr_gemm<2>(P, S, st, li, j, b0, rl, rank, scr);
+                LAP(LP_PYR_GEMM);
                 cluster_sync_all();
+                LAP(LP_PYR_BAR);
                 pyr_ln(P, S, li, j, b0, rl, rank, scr);
+                LAP(LP_PYR_LN);
                 cluster_sync_all();
+                LAP(LP_PYR_BAR);
             }
             cb = layer_row(P, S, st, li, j, b0, G, rank, cb, true);
             ++li;
@@ -577,9 +599,11 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
         __syncthreads();
         if (tid < GMAX) { S.p_prev[tid] = S.p_cur[tid]; S.p_cur[tid] = S.p_next[tid]; }
         __syncthreads();
+        LAP(LP_FRAME);
     }
     if (rank == 0 && tid < G) P.p_final[b0 + tid] = S.p_cur[tid];
     if (rank == 0 && tid == 0 && P.stats) { P.stats[2 * cluster] = n_moved_frames; P.stats[2 * cluster + 1] = n_moved_utt; }
+    if (P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
     cp_async_wait<0>();
     cluster_sync_all();                                   // no CTA exits while a peer may still write into its shared memory
 }

@@ -46,6 +46,7 @@ struct DecParams {
     int* p_hist;                       // (B, T) window used at every step
     int* p_final;                      // (B) window after the last step
     int* stats;                        // [clusters][2]: frames with a window move, utterance-frames recomputed
+    long long* prof;                   // optional [16] SM-clock lap timers of cluster 0 / rank 0 (option decode_prof), else nullptr
     int nl, n_enc, nch, stream_len;
     int B, G, T, N, d, n_mels, win_size, steps;
 };

@@ -121,6 +121,14 @@ class Engine:
         self._check(self._lib.dctts_decode_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "dctts_decode_stats")
         return int(a.value), int(b.value), int(c.value)
 
+    def decode_profile(self):
+        """Lap timers (SM cycles) of the last persistent decode run with option decode_prof = 1; see include/dctts.h."""
+        v = (C.c_int64 * 14)()
+        self._check(self._lib.dctts_decode_profile(self._h, v, 14), "dctts_decode_profile")
+        names = ["start", "stream_wait", "gemv", "release", "gather", "cluster_barrier", "layernorm", "mix", "attention",
+                 "re_attention", "re_gemm", "re_layernorm", "re_barriers", "frame"]
+        return dict(zip(names, [int(x) for x in v]))
+
     def reserve(self, batch):
         self._check(self._lib.dctts_reserve(self._h, int(batch)), "dctts_reserve")
 
@@ -211,10 +219,15 @@ class Engine:
         self._check(self._lib.dctts_audiodec(self._h, _ptr(R), B, T, _ptr(logits), _ptr(Y), self._stream()), "dctts_audiodec")
         return logits, Y
 
-    def ssrn(self, Y, want_logits=True):
+    def ssrn(self, Y, want_logits=True, out=None):
+        """`out`: optional preallocated contiguous (B, 4T, F) float32 CUDA tensor (e.g. a slice of a gather buffer)."""
         Y = self._f32(Y)
         B, T, _ = Y.shape
-        Z = self._empty(B, T * self.hp.r, self.F)
+        if out is not None:
+            if tuple(out.shape) != (B, T * self.hp.r, self.F) or out.dtype != torch.float32 or not out.is_contiguous() \
+                    or out.device != self.device:
+                raise DcttsError("ssrn: `out` must be a contiguous float32 (B, 4T, F) tensor on this engine's device")
+        Z = out if out is not None else self._empty(B, T * self.hp.r, self.F)
         logits = self._empty(B, T * self.hp.r, self.F) if want_logits else None
         self._check(self._lib.dctts_ssrn(self._h, _ptr(Y), B, T, _ptr(logits), _ptr(Z), self._stream()), "dctts_ssrn")
         return logits, Z

@@ -51,6 +51,103 @@ def gather_spectrograms(local, total, dst=0, group=None):
     return out
 
 
+class OverlappedGather:
+    """The same single gather, hidden under the SSRN: SSRN runs in utterance chunks and every finished
+    chunk leaves at once on a side stream into a receive buffer that is allocated ONCE, so only the last chunk's transfer
+    is exposed.  Round 1 gathered after the whole SSRN, allocating the receive tensor every step: a fixed ~2.4 ms at every
+    N > 1 (SCALE_r01: 0.964).  Rows keep global order and are bit-identical to the per-rank results (no arithmetic here).
+
+        og = OverlappedGather(total, shape_tail, dtype, device, chunks=4)
+        for step:  og.begin(); for c in og.chunks(): z = produce(c.lo, c.hi); og.send(c, z);  Z = og.finish()
+    """
+
+    class Chunk:
+        __slots__ = ("index", "lo", "hi")
+
+        def __init__(self, index, lo, hi):
+            self.index, self.lo, self.hi = index, lo, hi
+
+    def __init__(self, total, shape_tail, dtype, device, chunks=4, dst=0, group=None):
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.total, self.dst, self.group, self.device = total, dst, group, device
+        self.lo, self.hi = shard_bounds(total, self.rank, self.world)
+        n = self.hi - self.lo
+        self.nchunks = max(1, min(chunks, n))
+        self.cuda = torch.device(device).type == "cuda"
+        self.side = torch.cuda.Stream(device=device) if self.cuda else None
+        self.out = torch.empty((total,) + tuple(shape_tail), dtype=dtype, device=device) if self.rank == dst else None
+        self._pending = []
+
+    def _bounds(self, rank, c, nchunks):
+        lo, hi = shard_bounds(self.total, rank, self.world)
+        n = hi - lo
+        return lo + (n * c) // nchunks, lo + (n * (c + 1)) // nchunks
+
+    def chunks(self):
+        """This rank's chunks as LOCAL row ranges [lo, hi) of its shard."""
+        n = self.hi - self.lo
+        return [self.Chunk(c, (n * c) // self.nchunks, (n * (c + 1)) // self.nchunks) for c in range(self.nchunks)]
+
+    def begin(self):
+        """Destination: post the receives of every chunk of every other rank (they complete as the chunks arrive)."""
+        self._pending = []
+        if self.world == 1 or self.rank != self.dst:
+            return
+        ctx = torch.cuda.stream(self.side) if self.cuda else _Null()
+        if self.cuda:
+            self.side.wait_stream(torch.cuda.current_stream(self.device))      # the buffer's previous consumer is done
+        with ctx:
+            for g in range(self.world):
+                if g == self.dst:
+                    continue
+                glo, ghi = shard_bounds(self.total, g, self.world)
+                nch = max(1, min(self.nchunks, ghi - glo))
+                for c in range(nch):
+                    a, b = self._bounds(g, c, nch)
+                    if b > a:
+                        self._pending.append(dist.irecv(self.out[a:b], src=g, group=self.group, tag=c))
+
+    def send(self, chunk, z):
+        """Hand over the finished local rows [chunk.lo, chunk.hi) (a tensor of exactly those rows)."""
+        a, b = self.lo + chunk.lo, self.lo + chunk.hi
+        if b <= a:
+            return
+        if self.world == 1 or self.rank == self.dst:
+            if self.out is not None and z.data_ptr() != self.out[a:b].data_ptr():
+                self.out[a:b].copy_(z)
+            return
+        if self.cuda:
+            self.side.wait_stream(torch.cuda.current_stream(self.device))      # chunk is complete on the compute stream
+            with torch.cuda.stream(self.side):
+                z.record_stream(self.side)
+                self._pending.append(dist.isend(z.contiguous(), dst=self.dst, group=self.group, tag=chunk.index))
+        else:
+            self._pending.append(dist.isend(z.contiguous(), dst=self.dst, group=self.group, tag=chunk.index))
+
+    def local_view(self, chunk):
+        """Destination rank: the slice of the receive buffer its own chunk belongs in (produce straight into it)."""
+        if self.out is None:
+            return None
+        return self.out[self.lo + chunk.lo:self.lo + chunk.hi]
+
+    def finish(self):
+        for w in self._pending:
+            w.wait()
+        self._pending = []
+        if self.cuda and self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        return self.out
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def allreduce_mean_(flat, group=None):
     """In-place average of a flat gradient buffer over the ranks (sum all-reduce, then 1/world): the gradient of the mean
     loss over the global batch when every rank holds the same number of utterances.  Returns `flat`."""

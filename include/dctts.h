@@ -191,7 +191,7 @@ int dctts_set_tensor_path(dctts_handle h, int32_t mode);
  *   "decode_mode"  1 = the whole AR loop (synthesize.py:45-54) as ONE persistent cluster kernel (default),
  *                  0 = one captured CUDA graph per mel frame (round-1 path)
  *   "tc_occ2" 0/1, "tc_cg2" 0/1/2, "tc_tile_pair" 0/1, "tc_mcast" 0/1, "tc_resid_tma" 0/1: tcgen05 block kernel variants
- *   "fused_ln" 0/1: graph decode, GEMM + LN in one launch;  "tc_debug" 0/1;  "pdl" 0/1 (process-wide)
+ *   "fused_ln" 0/1: graph decode, GEMM + LN in one launch;  "tc_debug" 0/1;  "decode_prof" 0/1;  "pdl" 0/1 (process-wide)
  * dctts_get_option also answers "decode_available" (1 when this handle / device can run the persistent decode). */
 int dctts_set_option(dctts_handle h, const char* name, int32_t value);
 int dctts_get_option(dctts_handle h, const char* name, int32_t* value);
@@ -199,6 +199,10 @@ int dctts_get_option(dctts_handle h, const char* name, int32_t* value);
  * AudioDec receptive field because an attention window moved (summed over clusters), utterance-frames recomputed,
  * clusters launched.  Synchronises the device. */
 int dctts_decode_stats(dctts_handle h, int32_t* moved_frames, int32_t* moved_utterance_frames, int32_t* clusters);
+/* SM-clock lap timers (cycles) of the last persistent decode run with option "decode_prof" = 1: cluster 0, CTA rank 0.
+ * Buckets: 0 block start, 1 weight-stream wait, 2 GEMV, 3 slot release, 4 all-gather, 5 cluster barrier, 6 LayerNorm, 7 mix,
+ * 8 attention, 9 recompute attention, 10 recompute GEMM, 11 recompute LayerNorm, 12 recompute barriers, 13 frame bookkeeping. */
+int dctts_decode_profile(dctts_handle h, int64_t* cycles, int32_t n);
 /* Measurement aid for bench.py's roofline leg: runs the block `scope` on a synthetic
  * (B,L,Cin) input `warmup`+`iters` times and returns the mean device time of each of its
  * kernels (CUDA events on `stream` around every launch), ms_per_kernel[0..*n_kernels), <= 8. */

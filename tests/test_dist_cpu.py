@@ -98,3 +98,45 @@ def test_data_parallel_gradient_average_two_ranks_gloo():
         assert p.exitcode == 0
     err, n = q.get(timeout=5)
     assert n == 23970288 and err < 1e-5
+
+
+# ---- overlapped chunked gather: same result as the plain gather, ragged shards included ----
+def _og_worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from dc_tts_b200.parallel import OverlappedGather
+        og = OverlappedGather(total, (3, 5), torch.float32, "cpu", chunks=4)
+        lo, hi = shard_bounds(total, rank, world)
+        for step in range(2):                                   # the receive buffer is reused across steps
+            og.begin()
+            for c in og.chunks():
+                rows = torch.arange(lo + c.lo, lo + c.hi, dtype=torch.float32)[:, None, None].expand(-1, 3, 5) + 100.0 * step
+                view = og.local_view(c)
+                if view is not None:
+                    view.copy_(rows); og.send(c, view)
+                else:
+                    og.send(c, rows.contiguous())
+            out = og.finish()
+            if rank == 0:
+                want = torch.arange(total, dtype=torch.float32)[:, None, None].expand(-1, 3, 5) + 100.0 * step
+                q.put(bool(torch.equal(out, want)))
+            else:
+                assert out is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [16, 7, 2])
+def test_overlapped_gather_two_ranks_gloo(total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 300 + total
+    procs = [ctx.Process(target=_og_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True and q.get(timeout=5) is True

@@ -16,6 +16,7 @@ ap.add_argument("batches", type=int, nargs="*", default=[1, 32])
 ap.add_argument("--steps", type=int, default=210)
 ap.add_argument("--modes", default="1,0")
 ap.add_argument("--iters", type=int, default=5)
+ap.add_argument("--prof", action="store_true", help="print the in-kernel lap timers of the persistent decode")
 a = ap.parse_args()
 e = Engine(0)
 e.load_params(init_params(0, "perturbed"))
@@ -40,6 +41,14 @@ for B in a.batches:
         print("generate B=%d mode=%d: %.2f ms (%.1f us/frame)  checksum %.6f%s"
               % (B, mode, dt * 1e3, dt * 1e6 / a.steps, float(Y.double().sum()), extra), flush=True)
         outs[mode] = (Y, P)
+        if mode == 1 and a.prof:
+            e.set_option("decode_prof", 1)
+            e.text2mel_generate(L, steps=a.steps)
+            pr = e.decode_profile()
+            e.set_option("decode_prof", 0)
+            tot = float(sum(pr.values())) or 1.0
+            print("   lap timers (cluster 0, rank 0; %% of %.1f Mcycles): " % (tot / 1e6)
+                  + ", ".join("%s %.1f" % (k, 100.0 * v / tot) for k, v in pr.items()), flush=True)
     if len(outs) == 2:
         (Y1, P1), (Y0, P0) = outs[1], outs[0]
         same = (P0 == P1).all(dim=1)
