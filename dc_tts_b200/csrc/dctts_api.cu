@@ -426,39 +426,49 @@ void pack_decode(H* h) {
         if (L.prow > 1 && (L.cout != 256 || (L.ns != 32 && L.ns != 16) || L.prow > 85)) { D.why = "persistent decode: unsupported receptive field"; return; }
         L.ldin = l.cin;
         const int cinp = roundup(l.cin, 128);                     // AudioEnc C_1: 80 -> 128 zero rows
-        const int krows_max = DEC_SLOT_F / L.ns;                  // k rows per chunk
+        if (l.size > 1 && cinp != 256) { D.why = "persistent decode: multi-tap blocks must have 256 input channels"; return; }
+        const int K = l.size * cinp;
+        L.krows = std::min(K, DEC_SLOT_F / L.ns);                 // k rows per chunk
+        const int kr8 = L.krows / 8, sg = 32 / L.ns;
+        if (K % L.krows || L.krows % 8 || kr8 * L.ns > DEC_REG_F || kr8 % (8 * sg) || (L.prow > 1 && kr8 % 16)) {
+            D.why = "persistent decode: chunk geometry"; return;
+        }
+        if (L.prow > 1 && (L.prow - 1) + (l.size - 1) * l.rate > 96) { D.why = "persistent decode: receptive field too tall"; return; }
         L.ch0 = nch;
-        for (int tap = 0; tap < l.size; ++tap)
-            for (int ci0 = 0; ci0 < cinp; ci0 += krows_max) {
-                if (nch >= DEC_MAXCH) { D.why = "persistent decode: too many weight chunks"; return; }
-                const int kr = std::min(krows_max, cinp - ci0);
-                DecChunk& c = P.C[nch++];
-                c.off = off; c.nfl4 = (short)(kr * L.ns / 4); c.tap = (short)tap; c.ci0 = (short)ci0; c.krows = (short)kr;
-                if (kr % (4 * (DEC_THREADS / L.ns)) || kr % 16) { D.why = "persistent decode: chunk rows not divisible"; return; }
-                off += kr * L.ns;
-            }
+        for (int k0 = 0; k0 < K; k0 += L.krows) {
+            if (nch >= DEC_MAXCH) { D.why = "persistent decode: too many weight chunks"; return; }
+            DecChunk& c = P.C[nch++];
+            c.off = off; c.nfl4 = (short)(L.krows * L.ns / 4); c.k0 = (short)k0; c.krows = (short)L.krows; c.layer = (short)li;
+            off += L.krows * L.ns;
+        }
         L.nch = nch - L.ch0;
+        if (li == P.n_enc - 1) P.nch_enc = nch;
+        if (L.prow > 1) { if (P.pyr_ch1 == 0) P.pyr_ch0 = L.ch0; P.pyr_ch1 = nch; }
     }
-    if (P.L[P.nl - 1].prow != 1 || P.L[P.n_enc].ntaps != 1) { D.why = "persistent decode: unexpected AudioDec shape"; return; }
+    if (P.L[P.nl - 1].prow != 1 || P.L[P.n_enc].ntaps != 1 || P.nch_enc <= DEC_NSLOT) { D.why = "persistent decode: unexpected AudioDec shape"; return; }
+    for (int li = P.n_enc; li < P.nl; ++li)                        // the receptive-field blocks must be a prefix of AudioDec
+        if (P.L[li].prow > 1 && li > P.n_enc && P.L[li - 1].prow <= 1) { D.why = "persistent decode: receptive-field blocks not contiguous"; return; }
     P.nch = nch; P.stream_len = off;
-    // streams
+    // streams: chunk = 8 warp regions, region w = rows [w*kr8, (w+1)*kr8) as [k/4][column][4]
     std::vector<float> st((size_t)DEC_NC * off, 0.f);
     for (int r = 0; r < DEC_NC; ++r)
         for (int li = 0; li < P.nl; ++li) {
             const LayerDev& l = *nets[li]; const DecLayer& L = P.L[li];
             REQUIRE(!l.hostW.empty(), "persistent decode: host weights missing");
+            const int cinp = roundup(l.cin, 128), kr8 = L.krows / 8;
             for (int c = L.ch0; c < L.ch0 + L.nch; ++c) {
                 const DecChunk& ch = P.C[c];
                 float* dst = st.data() + (size_t)r * off + ch.off;
-                for (int k = 0; k < ch.krows; ++k) {
-                    const int ci = ch.ci0 + k;
+                for (int kc = 0; kc < ch.krows; ++kc) {
+                    const int k = ch.k0 + kc, tap = k / cinp, ci = k % cinp;
                     if (ci >= l.cin) continue;
-                    const float* wrow = l.hostW.data() + ((size_t)ch.tap * l.cin + ci) * l.ldw;
+                    const int w = kc / kr8, kk = kc % kr8;
+                    const float* wrow = l.hostW.data() + ((size_t)tap * l.cin + ci) * l.ldw;
                     for (int n = 0; n < L.ns; ++n) {
                         int col;
                         if (L.kind) col = n < L.cs ? r * L.cs + n : l.cout + r * L.cs + (n - L.cs);
                         else { if (n >= L.cs) continue; col = r * L.cs + n; }
-                        dst[((size_t)(k / 4) * L.ns + n) * 4 + (k % 4)] = wrow[col];
+                        dst[(size_t)w * kr8 * L.ns + ((size_t)(kk / 4) * L.ns + n) * 4 + (kk % 4)] = wrow[col];
                     }
                 }
             }
@@ -1837,6 +1847,36 @@ int dctts_train_tensor(dctts_handle h, const char* tf_name, int32_t what, float*
                     for (int ci = 0; ci < t.d1; ++ci)
                         host_out[((size_t)j * t.d2 + co) * t.d1 + ci] = tmp[((size_t)j * t.d1 + ci) * t.ld + co];
         }
+    });
+}
+
+// Inverse of dctts_train_tensor: upload a variable (what = 0), its Adam first (2) or second (3) moment from the TF layout --
+// what Supervisor's restore does for a resumed run (train.py:144; ADVICE r1: training could not resume).
+int dctts_train_set_tensor(dctts_handle h, const char* tf_name, int32_t what, const float* host_in, int64_t count) {
+    return guarded(h, [&] {
+        REQUIRE(h->tr.ready && tf_name && host_in && (what == 0 || what == 2 || what == 3), "dctts_train_set_tensor: bad arguments");
+        auto it = h->tr.tensors.find(tf_name);
+        REQUIRE(it != h->tr.tensors.end(), "dctts_train_set_tensor: not a variable of the network being trained");
+        const auto& t = it->second;
+        const long long logical = t.layout == 0 ? t.n : (long long)t.d0 * t.d1 * t.d2;
+        REQUIRE(count == logical, "dctts_train_set_tensor: element count mismatch");
+        float* dst = what == 0 ? t.p : what == 2 ? t.m : t.v;
+        CUDA_CHECK(cudaDeviceSynchronize());
+        if (t.layout == 0) {
+            CUDA_CHECK(cudaMemcpy(dst, host_in, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+            return;
+        }
+        std::vector<float> tmp((size_t)t.n, 0.f);
+        if (t.layout == 1) {                                  // [d0][d1][d2] -> [d0][d1][ld]
+            for (long long r = 0; r < (long long)t.d0 * t.d1; ++r)
+                std::copy(host_in + r * t.d2, host_in + (r + 1) * t.d2, tmp.begin() + r * t.ld);
+        } else {                                              // TF [1][tap][cout][cin] -> device [tap][cin][ld]
+            for (int j = 0; j < t.d0; ++j)
+                for (int co = 0; co < t.d2; ++co)
+                    for (int ci = 0; ci < t.d1; ++ci)
+                        tmp[((size_t)j * t.d1 + ci) * t.ld + co] = host_in[((size_t)j * t.d2 + co) * t.d1 + ci];
+        }
+        CUDA_CHECK(cudaMemcpy(dst, tmp.data(), tmp.size() * sizeof(float), cudaMemcpyHostToDevice));
     });
 }
 

@@ -4,28 +4,35 @@
 // Why: a decode step is 24 dependent conv blocks on one row per utterance; as 46 graph nodes it was
 // bound by kernel boundaries and by split-K round trips through L2 (round 1: ~300 us per step, 1.5 %
 // of any roofline).  Utterances never interact (networks.py:140-153 is batched per row), so a group
-// of G <= 4 utterances can be decoded by one thread-block CLUSTER with no grid-level synchronisation:
+// of G <= 4 utterances is decoded by one thread-block CLUSTER with no grid-level synchronisation:
 //
 //   * 16 CTAs per cluster; CTA r owns 1/16 of every block's output channels (for `hc` the same 16
 //     channels of the gate and of the info half, so the highway mix is local).
-//   * its weight slices for all 24 blocks form one contiguous 1.7 MB stream (packed at commit time,
-//     [k/4][column][4] so that one LDS.128 yields four k of one column); the stream is identical for
-//     every frame and is pulled from L2 by TMA bulk copies (cp.async.bulk + mbarrier) into a
-//     9 x 16 KB shared-memory ring, always ~128 KB ahead of the math.
-//   * per block: GEMV of the slice on fp32 FMA (exact fp32, as the reference), the pre-LN slice is
-//     written into every peer's shared memory (DSMEM all-gather, 512 B per peer), ONE cluster
-//     barrier, then every CTA normalises the whole rows redundantly (LayerNorm, gate, mix): the next
-//     block's input sits in local shared memory.  Dilated taps come from the per-layer history in
-//     HBM/L2, prefetched one block ahead with cp.async; each CTA appends its slice of the new row.
+//   * its weight slices for all 24 blocks form one contiguous 1.7 MB stream (packed at commit time).
+//     The stream is the same for every frame and is pulled from L2 by TMA bulk copies
+//     (cp.async.bulk + mbarrier) into a 3 x 48 KB shared-memory ring.  Every WARP owns the k rows it
+//     multiplies: it waits on its own mbarrier, and refills its own 6 KB region the moment it has read
+//     it -- the chunk loop has no block-wide synchronisation at all.
+//   * per block: GEMV of the slice on fp32 FMA (exact fp32 arithmetic, as the reference), one block
+//     barrier for the cross-warp reduction, the pre-LN slice goes to every peer with ONE bulk copy
+//     per peer through distributed shared memory, completing on the peer's mbarrier (no hardware
+//     cluster barrier on this path); every CTA then normalises the whole rows redundantly (one warp
+//     per utterance: both LayerNorms, gate, highway mix in registers), so the next block's input is in
+//     local shared memory.  Dilated taps come from the per-layer history in HBM/L2, prefetched one
+//     block ahead with cp.async; each CTA appends its channel slice of the new row.
 //   * Quirk Q1: the reference recomputes R under the CURRENT window every step.  While
 //     the window of an utterance does not move, the cached rows are exactly what a recompute would
-//     give, so only row j is evaluated (1 row per block).  When it moves, the 85-row receptive field
-//     of AudioDec is recomputed (85/83/77/59/5/3 rows for C_1, HC_2..HC_6) by a register-tiled fp32
-//     GEMM over the same weight stream, pre-LN rows through an L2 scratch, LayerNorm one warp per row.
+//     give.  When it moves, a PRE-PASS refreshes the rows t < j of its AudioDec receptive field
+//     (84/82/76/58/4/2 rows of C_1, HC_2..HC_6) under the new window -- attention one warp per row, a
+//     register-tiled fp32 GEMM per utterance (3 rows x 4 columns per thread, the input rows staged ONCE
+//     per 16-channel slab for all three taps through a 3-stage cp.async pipeline), pre-LN rows through
+//     an L2 scratch, LayerNorm one warp per row over the whole cluster -- and the ordinary one-row pass
+//     then runs for every utterance.  The pre-pass consumes the same weight chunks a second time: the
+//     stream is "virtual" (frame, segment, chunk) and both the consumer and the refill cursor walk it.
 //
-// All waits are bounded (mbarrier waits trap after ~2 s).  Cluster barriers are executed by all
-// threads of all CTAs in uniform control flow: every branch that contains one depends only on values
-// that are computed identically in every CTA (the attention windows).
+// All waits are bounded (mbarrier waits trap after ~2 s).  Hardware cluster barriers (pre-pass, frame
+// end) are executed by all threads of all CTAs in uniform control flow: every branch that contains
+// one depends only on the attention windows, which every CTA computes identically.
 #include "kernels_decode.cuh"
 #include "tc_ptx.cuh"
 
@@ -37,21 +44,24 @@ using namespace ptx;
 namespace {
 
 constexpr int NC = DEC_NC, GMAX = DEC_GMAX, NT = DEC_THREADS, NWARP = NT / 32;
-constexpr int XLD = 512;                       // row pitch of the shared activation buffers
-constexpr int ALD = 132;                       // row pitch of the transposed A sub-tile (128 rows + 4)
-constexpr int WRK_F = 2 * 16 * ALD;            // max(A staging 2 x 16 x 132, normalised rows GMAX x 2 x 256)
-static_assert(WRK_F >= GMAX * 2 * 256, "work buffer too small for the normalised rows");
+constexpr int XLD = 768;                       // row pitch of the input vectors: [tap0 | tap1 | current]
+constexpr int PLD = GMAX * 32 + 16;            // pitch between the ranks' slices in `pre` (16 floats of bank skew)
+constexpr int SROWS = 96, SLD = 20;            // pre-pass A slab: <= 96 source rows x 16 channels (+4 pad)
+constexpr int WRK_F = 3 * SROWS * SLD;         // three slab stages; also 4 x 768 floats of few-row inputs
+static_assert(WRK_F >= 4 * 768, "work buffer too small for the few-row inputs");
 
 struct Smem {
-    float ring[DEC_NSLOT * DEC_SLOT_F];
-    float prm[2][DEC_PRM_F];
-    float xtap[2][GMAX][XLD];
-    float xcur[2][GMAX][XLD];
-    float pre[2][GMAX][XLD];
+    float ring[DEC_NSLOT][NWARP][DEC_REG_F];
+    float xin[2][GMAX][XLD];
+    float pre[2][NC][PLD];
+    float outv[2][GMAX * 32];
     float red[GMAX][NT];
+    float prm[2][DEC_PRM_F];
     float wrk[WRK_F];
-    unsigned long long full[DEC_NSLOT];
+    unsigned long long fullw[DEC_NSLOT][NWARP];
+    unsigned long long gbar[2];
     int p_cur[GMAX], p_prev[GMAX], p_next[GMAX], moved[GMAX];
+    int fmoved[2];
     long long prof[16], prof_last;
 };
 
@@ -78,86 +88,111 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
-    asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+// local shared memory -> a peer CTA's shared memory, completing on the PEER's mbarrier
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, const void* src, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_cluster), "r"(smem_u32(src)), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() { cluster_arrive(); cluster_wait(); }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint64_t* bar64(unsigned long long* p) { return reinterpret_cast<uint64_t*>(p); }
 
-// ---- the weight stream ---------------------------------------------------------------------------
+// ---- the virtual weight stream ---------------------------------------------------------------------
+// frame f = AudioEnc chunks, [the AudioDec chunks of the receptive-field blocks, if a window moved in f], AudioDec chunks
+struct Cur { int f, seg, c; };
+__device__ __forceinline__ void cur_next(const DecParams& P, const Smem& S, Cur& u) {
+    u.c++;
+    const int end = (u.seg == 0) ? P.nch_enc : (u.seg == 1 ? P.pyr_ch1 : P.nch);
+    if (u.c < end) return;
+    if (u.seg == 0) {
+        if (S.fmoved[u.f & 1]) { u.seg = 1; u.c = P.pyr_ch0; } else { u.seg = 2; u.c = P.nch_enc; }
+    } else if (u.seg == 1) { u.seg = 2; u.c = P.nch_enc; }
+    else { u.f++; u.seg = 0; u.c = 0; }
+}
 struct Stream {
-    const float* base;          // this rank's stream
-    long long pos;              // next chunk to consume (global index over all frames)
-    long long total;            // frames * chunks per frame
+    const float* base;          // this rank's packed stream
+    Cur cons, prod;             // chunk being consumed / chunk that will be loaded into the slot it frees
+    unsigned pos;               // number of chunks consumed so far
 };
+// one lane of warp `warp`: load the warp's rows of chunk `u` into its region of `slot`
+__device__ __forceinline__ void stream_issue(const DecParams& P, Smem& S, const Stream& st, const Cur& u, int slot, int warp) {
+    if (u.f >= P.steps) return;
+    const DecChunk& ch = P.C[u.c];
+    const uint32_t bytes = (uint32_t)ch.nfl4 * 2u;                   // nfl * 4 bytes / 8 warps
+    mbar_expect_tx(bar64(&S.fullw[slot][warp]), bytes);
+    bulk_g2s(&S.ring[slot][warp][0], st.base + ch.off + warp * (ch.nfl4 >> 1), bytes, &S.fullw[slot][warp]);
+}
+__device__ __forceinline__ void stream_advance(const DecParams& P, const Smem& S, Stream& st) {
+    cur_next(P, S, st.cons); cur_next(P, S, st.prod); st.pos++;
+}
+// the calling warp has read its region of the current chunk: refill it with its rows of the chunk 3 ahead
+__device__ __forceinline__ void warp_release(const DecParams& P, Smem& S, Stream& st, int warp, int lane) {
+    __syncwarp();
+    if (lane == 0) {
+        fence_proxy_async_smem();                                     // generic reads before the async-proxy overwrite
+        stream_issue(P, S, st, st.prod, (int)(st.pos % DEC_NSLOT), warp);
+    }
+    stream_advance(P, S, st);
+}
 
-__device__ __forceinline__ void stream_issue(const DecParams& P, Smem& S, const Stream& st, long long idx) {
-    if (idx >= st.total) return;
-    const int c = (int)(idx % P.nch), slot = (int)(idx % DEC_NSLOT);
-    const uint32_t bytes = (uint32_t)P.C[c].nfl4 * 16u;
-    mbar_expect_tx(reinterpret_cast<uint64_t*>(&S.full[slot]), bytes);
-    bulk_g2s(S.ring + slot * DEC_SLOT_F, st.base + P.C[c].off, bytes, &S.full[slot]);
-}
-__device__ __forceinline__ const float* stream_acquire(Smem& S, const Stream& st) {
-    const int slot = (int)(st.pos % DEC_NSLOT);
-    mbar_wait(reinterpret_cast<uint64_t*>(&S.full[slot]), (uint32_t)((st.pos / DEC_NSLOT) & 1));
-    return S.ring + slot * DEC_SLOT_F;
-}
-// all threads are done with the chunk at st.pos: refill its slot with the chunk DEC_NSLOT ahead
-__device__ __forceinline__ void stream_release(const DecParams& P, Smem& S, Stream& st) {
-    __syncthreads();
-    if (threadIdx.x == 0) stream_issue(P, S, st, st.pos + DEC_NSLOT);
-    st.pos++;
-}
-
-// ---- prefetch of the next block's parameters (and dilated taps) -----------------------------------
+// ---- prefetch of the next block's parameters and dilated taps -------------------------------------------
 __device__ __forceinline__ void prefetch_params(const DecParams& P, Smem& S, int li, int rank) {
     const DecLayer& l = P.L[li];
     float* dst = S.prm[li & 1];
     const int tid = threadIdx.x;
     cp_async16(dst + tid * 4, P.lnp[li] + tid * 4, true);                        // 1024 floats
-    if (tid < l.ns / 4) {                                                         // bias slice, stream column order
-        // hc: columns [0,cs) gate of channels rank*cs.., [cs,2cs) info; conv: [0,cs) (+ zero padding handled by the reader)
+    if (tid < l.ns / 4 && (l.cs & 3) == 0) {                                      // bias slice in stream column order
         const int n = tid * 4;
         const float* src = (l.kind == 1 && n >= l.cs) ? P.bias[li] + l.cout + rank * l.cs + (n - l.cs) : P.bias[li] + rank * l.cs + n;
-        // slices are 16-byte aligned only when cs % 4 == 0; otherwise (n_mels / 16 = 5) the reader loads bias from global
-        if ((l.cs & 3) == 0) cp_async16(dst + 1024 + n, src, true);
+        cp_async16(dst + 1024 + n, src, true);
     }
 }
-// taps (all but the last) of block li at frame j for the G utterances: rows j - (ntaps-1-tap)*rate of the input history
-__device__ __forceinline__ void prefetch_taps(const DecParams& P, Smem& S, int li, int j, int b0, int G) {
+// taps (all but the last) of block li at frame j: rows j - (ntaps-1-tap)*rate of its input history -> xin[buf][g][tap*256..]
+__device__ __forceinline__ void prefetch_taps(const DecParams& P, Smem& S, int li, int j, int b0, int G, int buf) {
     const DecLayer& l = P.L[li];
     const int ntap_ld = l.ntaps - 1;
     if (ntap_ld <= 0 || !P.in_hist[li]) return;
-    const int per_row = l.cin / 4;                                                // float4 per row
+    const int per_row = l.cin / 4;
     const int total = G * ntap_ld * per_row;
     for (int i = threadIdx.x; i < total; i += NT) {
         const int c4 = i % per_row, rt = i / per_row, tap = rt % ntap_ld, g = rt / ntap_ld;
         const int t = j - (l.ntaps - 1 - tap) * l.rate;
         const float* src = P.in_hist[li] + ((size_t)(b0 + g) * P.T + (t < 0 ? 0 : t)) * l.ldin + c4 * 4;
-        cp_async16(&S.xtap[li & 1][g][tap * 256 + c4 * 4], src, t >= 0);
+        cp_async16(&S.xin[buf][g][tap * 256 + c4 * 4], src, t >= 0);
     }
 }
 
-// ---- GEMV of one weight chunk: acc[g] += sum_k x[g][k] * W[k][n] -----------------------------------
+// ---- GEMV of the calling warp's k rows of one chunk: acc[g] += sum_k x[g][k] * W[k][n] ----------------------
+// wreg: the warp's region ([k/4][column][4]); x: row 0 of the input vectors at the warp's first k; NS columns per CTA
 template <int NS>
-__device__ __forceinline__ void gemv_chunk(const float* __restrict__ w, const float* __restrict__ x, int krows, int G,
-                                           float (&acc)[GMAX]) {
-    constexpr int NG = NT / NS;
-    const int n = threadIdx.x % NS, kq = threadIdx.x / NS;
-    const int kper = krows / NG, kb = kq * kper;
+__device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const float* __restrict__ x, int xld, int kr8, int G,
+                                          float (&acc)[GMAX]) {
+    constexpr int SG = 32 / NS;                                      // k sub-groups inside the warp
+    const int lane = threadIdx.x & 31, n = lane % NS, sg = lane / NS;
+    const int kper = kr8 / SG;                                       // multiple of 8
+    const float* w = wreg + ((size_t)(sg * kper / 4) * NS + n) * 4;
+    const float* xs = x + sg * kper;
 #pragma unroll 2
-    for (int k = kb; k < kb + kper; k += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(w + ((size_t)(k >> 2) * NS + n) * 4);
+    for (int k = 0; k < kper; k += 8) {
+        const float4 w0 = *reinterpret_cast<const float4*>(w + (size_t)(k >> 2) * NS * 4);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + (size_t)((k >> 2) + 1) * NS * 4);
 #pragma unroll
         for (int g = 0; g < GMAX; ++g) {
             if (g < G) {
-                const float4 xv = *reinterpret_cast<const float4*>(x + g * XLD + k);
-                acc[g] = fmaf(xv.x, wv.x, acc[g]); acc[g] = fmaf(xv.y, wv.y, acc[g]);
-                acc[g] = fmaf(xv.z, wv.z, acc[g]); acc[g] = fmaf(xv.w, wv.w, acc[g]);
+                const float4 x0 = *reinterpret_cast<const float4*>(xs + g * xld + k);
+                const float4 x1 = *reinterpret_cast<const float4*>(xs + g * xld + k + 4);
+                float a = acc[g];
+                a = fmaf(x0.x, w0.x, a); a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
+                a = fmaf(x1.x, w1.x, a); a = fmaf(x1.y, w1.y, a); a = fmaf(x1.z, w1.z, a); a = fmaf(x1.w, w1.w, a);
+                acc[g] = a;
             }
         }
     }
+}
+__device__ __forceinline__ void gemv_dispatch(int ns, const float* wreg, const float* x, int xld, int kr8, int G, float (&acc)[GMAX]) {
+    if (ns == 32) gemv_warp<32>(wreg, x, xld, kr8, G, acc);
+    else if (ns == 16) gemv_warp<16>(wreg, x, xld, kr8, G, acc);
+    else gemv_warp<8>(wreg, x, xld, kr8, G, acc);
 }
 
 // global column of stream column n of rank r (hc: gate | info halves of the 2*cout pre-LN row)
@@ -165,296 +200,328 @@ __device__ __forceinline__ int pre_col(const DecLayer& l, int rank, int n) {
     if (l.kind == 1) return n < l.cs ? rank * l.cs + n : 256 + rank * l.cs + (n - l.cs);
     return rank * l.cs + n;
 }
-__device__ __forceinline__ float bias_of(const DecParams& P, const Smem& S, int li, int rank, int n) {
+__device__ __forceinline__ float bias_smem_or_global(const DecParams& P, const float* prm, int li, int rank, int n) {
     const DecLayer& l = P.L[li];
-    if ((l.cs & 3) == 0) return S.prm[li & 1][1024 + n];
+    if (prm && (l.cs & 3) == 0) return prm[1024 + n];
+    if (l.kind == 1) return __ldg(P.bias[li] + (n < l.cs ? rank * l.cs + n : l.cout + rank * l.cs + (n - l.cs)));
     if (n >= l.cs) return 0.f;
     return __ldg(P.bias[li] + rank * l.cs + n);
 }
 
-// ---- one block on ONE row per utterance -------------------------------------------------------------
-// in: S.xcur[cb] = the block's input at frame j (all G utterances), S.xtap[li&1] = its dilated taps (prefetched),
-// S.prm[li&1] = its parameters.  out: S.xcur[cb^1] = the block's output row; this CTA's channel slice appended
-// to the output history.  Returns the new cb.
-__device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j, int b0, int G, int rank, int cb, bool direct_in) {
+// LayerNorm of one row held as v[i] (channel lane + 32 i), pivoted single pass (pivot = channel 0): the sum and the
+// sum of squares of (v - pivot) reduce together; a constant row gives exactly 0 (eps = 1e-12, quirk Q4)
+__device__ __forceinline__ void ln_row(float (&v)[8], int C, int lane, const float* gam, const float* bet) {
+    const float pivot = __shfl_sync(0xffffffffu, v[0], 0);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; v[i] = (c < C) ? v[i] - pivot : 0.f; s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+    const float fC = (float)C;
+    const float md = s1 / fC;
+    const float var = fmaxf(s2 / fC - md * md, 0.f);
+    const float inv = 1.0f / sqrtf(var + 1e-12f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < C) v[i] = (v[i] - md) * inv * gam[c] + bet[c]; }
+}
+
+// ---- one block on ONE row per utterance -------------------------------------------------------------------
+// in: S.xin[cb][g] = [taps | current row] of the block's input, S.prm[li&1] = its parameters (both prefetched).
+// out: S.xin[cb^1][g][next_off ..] = the block's output row; this CTA's channel slice appended to the output history.
+__device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j, int b0, int G, int rank, int cb, unsigned& lcount) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nl_next = (li + 1 == P.nl) ? 0 : li + 1;
-    // prefetch for the following block (its taps are rows of earlier frames, already in the history)
-    {
-        const bool next_frame = (li + 1 == P.nl);
-        const int jn = next_frame ? j + 1 : j;
-        if (!next_frame || j + 1 < P.steps) {
-            prefetch_params(P, S, nl_next, rank);
-            prefetch_taps(P, S, nl_next, jn, b0, G);
-        }
-        cp_async_commit();
+    const bool last = (li + 1 == P.nl);
+    const int nl_next = last ? 0 : li + 1;
+    const int pb = (int)(lcount & 1u);
+    const uint32_t gpar = (lcount >> 1) & 1u;
+    const uint32_t gbytes = (uint32_t)(G * l.ns * 4);
+
+    cp_async_wait<0>();                     // this block's taps and parameters (issued one block ago)
+    __syncthreads();                        // ... and every warp has finished the previous block
+    if (tid == 0) mbar_expect_tx(bar64(&S.gbar[pb]), NC * gbytes);
+    // prefetch for the following block: its taps are rows of earlier frames, already in the history
+    if (!last || j + 1 < P.steps) {
+        prefetch_params(P, S, nl_next, rank);
+        // the following block's input vector lives in xin[cb^1]; the attention writes the whole AudioDec C_1 input itself
+        if (nl_next != P.n_enc) prefetch_taps(P, S, nl_next, last ? j + 1 : j, b0, G, cb ^ 1);
     }
-    if (direct_in) {
-        // first single-row block after a recompute: its input rows (taps AND the current row) were just rewritten in the
-        // history by the whole cluster (a cluster barrier precedes this call)
-        const int per_row = l.cin / 4, total = G * l.ntaps * per_row;
-        for (int i = tid; i < total; i += NT) {
-            const int c4 = i % per_row, rt = i / per_row, tap = rt % l.ntaps, g = rt / l.ntaps;
-            const int t = j - (l.ntaps - 1 - tap) * l.rate;
-            const float* src = P.in_hist[li] + ((size_t)(b0 + g) * P.T + (t < 0 ? 0 : t)) * l.ldin + c4 * 4;
-            float* dst = (tap == l.ntaps - 1) ? &S.xcur[cb][g][c4 * 4] : &S.xtap[li & 1][g][tap * 256 + c4 * 4];
-            cp_async16(dst, src, t >= 0);
-        }
-        cp_async_commit();
-        cp_async_wait<0>();
-    } else {
-        cp_async_wait<1>();                 // everything but the group just committed: this block's taps and parameters
-    }
-    __syncthreads();
+    cp_async_commit();
     LAP(LP_START);
 
     float acc[GMAX];
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
-    for (int c = l.ch0; c < l.ch0 + l.nch; ++c) {
-        const DecChunk& ch = P.C[c];
-        const float* w = stream_acquire(S, st);
+    for (int c = 0; c < l.nch; ++c) {
+        const DecChunk& ch = P.C[st.cons.c];
+        const int slot = (int)(st.pos % DEC_NSLOT);
+        mbar_wait(bar64(&S.fullw[slot][warp]), (st.pos / DEC_NSLOT) & 1u);
         LAP(LP_WAIT);
-        const float* x = (ch.tap == l.ntaps - 1) ? &S.xcur[cb][0][ch.ci0] : &S.xtap[li & 1][0][ch.tap * 256 + ch.ci0];
-        if (l.ns == 32) gemv_chunk<32>(w, x, ch.krows, G, acc);
-        else if (l.ns == 16) gemv_chunk<16>(w, x, ch.krows, G, acc);
-        else gemv_chunk<8>(w, x, ch.krows, G, acc);
+        const int kr8 = ch.krows >> 3;
+        gemv_dispatch(l.ns, &S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], XLD, kr8, G, acc);
         LAP(LP_GEMV);
-        stream_release(P, S, st);
+        warp_release(P, S, st, warp, lane);
         LAP(LP_RELEASE);
     }
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
     __syncthreads();
-    // final sums of the slice, written into every CTA's `pre` (all-gather through distributed shared memory)
-    const int pb = li & 1;
-    {
-        const int nvals = G * l.ns;                       // <= 128
-        const int idx = tid % 128, half = tid / 128;      // two thread halves serve 8 peers each
-        if (idx < nvals) {
-            const int g = idx / l.ns, n = idx % l.ns;
-            const int ng = NT / l.ns;
-            float s = bias_of(P, S, li, rank, n);
-            for (int q = 0; q < ng; ++q) s += S.red[g][q * l.ns + n];
-            const bool real = (l.kind == 1) ? true : (n < l.cs);
-            if (real) {
-                const uint32_t local = smem_u32(&S.pre[pb][g][pre_col(l, rank, n)]);
+    // warp 0: final sums of the slice -> staging -> one bulk copy per peer (all-gather through distributed shared memory)
+    if (warp == 0) {
+        const int nvals = G * l.ns, ng = NT / l.ns;
+        float* ov = S.outv[pb];
 #pragma unroll
-                for (int p = 0; p < 8; ++p) st_cluster_f32(mapa(local, (uint32_t)(half * 8 + p)), s);
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i;
+            if (idx < nvals) {
+                const int g = idx / l.ns, n = idx % l.ns;
+                float s = bias_smem_or_global(P, S.prm[li & 1], li, rank, n);
+                for (int q = 0; q < ng; ++q) s += S.red[g][q * l.ns + n];
+                ov[idx] = s;
             }
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane < NC)
+            bulk_s2peer(mapa(smem_u32(&S.pre[pb][rank][0]), (uint32_t)lane), ov, gbytes, mapa(smem_u32(&S.gbar[pb]), (uint32_t)lane));
     }
     LAP(LP_GATHER);
-    cluster_sync_all();
+    mbar_wait(bar64(&S.gbar[pb]), gpar);
     LAP(LP_CBAR);
-    // LayerNorm of whole rows, redundantly in every CTA: warp -> (utterance, half)
-    const int nh = l.kind + 1, C = l.cout;
-    float* nrm = S.wrk;                                   // [g][half][256]
-    const float* prm = S.prm[li & 1];
-    for (int pr = warp; pr < G * nh; pr += NWARP) {
-        const int g = pr / nh, hf = pr % nh;
-        const float* y = &S.pre[pb][g][hf * 256];
-        float v[8];
-        float s = 0.f;
+    // one warp per utterance: both LayerNorms, gate, highway mix in registers (redundantly in every CTA)
+    if (warp < G) {
+        const int g = warp, C = l.cout, cs = l.cs;
+        const float* prm = S.prm[li & 1];
+        const float* pr = &S.pre[pb][0][g * l.ns];
+        float v1[8], v2[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; v[i] = (c < C) ? y[c] : 0.f; s += v[i]; }
-        const float fC = (float)C;
-        const float mean = warp_sum(s) / fC;
-        float qd = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; v[i] = (c < C) ? v[i] - mean : 0.f; qd = fmaf(v[i], v[i], qd); }
-        const float inv = 1.0f / sqrtf(warp_sum(qd) / fC + 1e-12f);
-        const float* gam = prm + hf * 512; const float* bet = gam + 256;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < C) nrm[(g * 2 + hf) * 256 + c] = v[i] * inv * gam[c] + bet[c]; }
-    }
-    __syncthreads();
-    LAP(LP_LN);
-    const bool last = (li + 1 == P.nl);
-    float* oh = P.out_hist[li];
-    for (int i = tid; i < G * C; i += NT) {
-        const int g = i / C, c = i % C;
-        float o;
-        if (l.kind == 1) {
-            const float h1 = sigmoid_acc(nrm[(g * 2) * 256 + c]);
-            o = h1 * nrm[(g * 2 + 1) * 256 + c] + (1.0f - h1) * S.xcur[cb][g][c];
-        } else {
-            o = nrm[(g * 2) * 256 + c];
-            if (l.act == 1) o = fmaxf(o, 0.f);
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane + 32 * i;
+            const int rk = (cs == 16) ? (c >> 4) : c / cs, wi = (cs == 16) ? (c & 15) : c % cs;
+            v1[i] = (c < C) ? pr[rk * PLD + wi] : 0.f;
+            v2[i] = (c < C && l.kind == 1) ? pr[rk * PLD + cs + wi] : 0.f;
         }
+        ln_row(v1, C, lane, prm, prm + 256);
+        if (l.kind == 1) ln_row(v2, C, lane, prm + 512, prm + 768);
+        LAP(LP_LN);
+        const int cur_off = (l.ntaps - 1) * 256;
+        const int next_off = (last || li + 1 == P.n_enc) ? 0 : (P.L[li + 1].ntaps - 1) * 256;
         const size_t row = (size_t)(b0 + g) * P.T + j;
-        if (c / l.cs == rank && oh) oh[row * C + c] = o;           // this CTA's slice of the history row
-        if (last) {                                                 // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
-            o = sigmoid_acc(o);
-            if (rank == 0) P.ybuf[row * C + c] = o;
+        float* oh = P.out_hist[li];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) {
+                float o;
+                if (l.kind == 1) {
+                    const float h1 = sigmoid_acc(v1[i]);
+                    o = h1 * v2[i] + (1.0f - h1) * S.xin[cb][g][cur_off + c];
+                } else {
+                    o = v1[i];
+                    if (l.act == 1) o = fmaxf(o, 0.f);
+                }
+                const int rk = (cs == 16) ? (c >> 4) : c / cs;
+                if (rk == rank && oh) oh[row * C + c] = o;           // this CTA's slice of the history row
+                if (last) {                                           // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
+                    o = sigmoid_acc(o);
+                    if (rank == 0) P.ybuf[row * C + c] = o;
+                }
+                S.xin[cb ^ 1][g][next_off + c] = o;
+            }
         }
-        S.xcur[cb ^ 1][g][c] = o;
-    }
-    if (last) {                                                     // AudioEnc C_1 reads K = 128 padded channels
-        for (int i = tid; i < G * (128 - C); i += NT) S.xcur[cb ^ 1][i / (128 - C)][C + i % (128 - C)] = 0.f;
+        if (last) for (int c = C + lane; c < 128; c += 32) S.xin[cb ^ 1][g][c] = 0.f;   // AudioEnc C_1 reads K = 128 padded channels
+    } else {
+        LAP(LP_LN);
     }
     LAP(LP_MIX);
+    lcount++;
     return cb ^ 1;
 }
 
-// ---- attention of ONE query row under the 3-key window (networks.py:140-153) -------------------------
+// ---- attention of ONE query row under the 3-key window (networks.py:140-153) -------------------------------
 // lane holds q[lane*8 .. +8); returns ctx[8] in the same layout and the argmax key (first index among equal maxima)
 __device__ __forceinline__ int attend_row(const DecParams& P, const float (&qv)[8], int b, int p, int lane, float (&ctx)[8]) {
     const int d = P.d;
     const int n_lo = min(max(p, 0), P.N - 1), n_hi = min(n_lo + P.win_size, P.N);
     const float scale = rsqrtf((float)d);
-    float sc[4];
-    for (int n = n_lo; n < n_hi; ++n) {
-        const float* k = P.kv + ((size_t)b * P.N + n) * (2 * d) + lane * 8;
-        const float4 k0 = ldcg4(k), k1 = ldcg4(k + 4);
-        float s = 0.f;
-        s = fmaf(qv[0], k0.x, s); s = fmaf(qv[1], k0.y, s); s = fmaf(qv[2], k0.z, s); s = fmaf(qv[3], k0.w, s);
-        s = fmaf(qv[4], k1.x, s); s = fmaf(qv[5], k1.y, s); s = fmaf(qv[6], k1.z, s); s = fmaf(qv[7], k1.w, s);
-        sc[n - n_lo] = warp_sum(s) * scale;
+    float sc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n_lo + i;
+        if (n < n_hi) {
+            const float* k = P.kv + ((size_t)b * P.N + n) * (2 * d) + lane * 8;
+            const float4 k0 = ldcg4(k), k1 = ldcg4(k + 4);
+            float s = 0.f;
+            s = fmaf(qv[0], k0.x, s); s = fmaf(qv[1], k0.y, s); s = fmaf(qv[2], k0.z, s); s = fmaf(qv[3], k0.w, s);
+            s = fmaf(qv[4], k1.x, s); s = fmaf(qv[5], k1.y, s); s = fmaf(qv[6], k1.z, s); s = fmaf(qv[7], k1.w, s);
+            sc[i] = warp_sum(s) * scale;
+        }
     }
     const int cnt = n_hi - n_lo;
     float mx = -INFINITY;
-    for (int i = 0; i < cnt; ++i) mx = fmaxf(mx, sc[i]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < cnt) mx = fmaxf(mx, sc[i]);
     float sum = 0.f;
-    for (int i = 0; i < cnt; ++i) { sc[i] = expf(sc[i] - mx); sum += sc[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < cnt) { sc[i] = expf(sc[i] - mx); sum += sc[i]; }
     float best = -1.f; int besti = 0;
-    for (int i = 0; i < cnt; ++i) { sc[i] = sc[i] / sum; if (sc[i] > best) { best = sc[i]; besti = i; } }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (i < cnt) { sc[i] = sc[i] / sum; if (sc[i] > best) { best = sc[i]; besti = i; } }
 #pragma unroll
     for (int i = 0; i < 8; ++i) ctx[i] = 0.f;
-    for (int n = n_lo; n < n_hi; ++n) {
-        const float* v = P.kv + ((size_t)b * P.N + n) * (2 * d) + d + lane * 8;
-        const float4 v0 = ldcg4(v), v1 = ldcg4(v + 4);
-        const float p_ = sc[n - n_lo];
-        ctx[0] = fmaf(p_, v0.x, ctx[0]); ctx[1] = fmaf(p_, v0.y, ctx[1]); ctx[2] = fmaf(p_, v0.z, ctx[2]); ctx[3] = fmaf(p_, v0.w, ctx[3]);
-        ctx[4] = fmaf(p_, v1.x, ctx[4]); ctx[5] = fmaf(p_, v1.y, ctx[5]); ctx[6] = fmaf(p_, v1.z, ctx[6]); ctx[7] = fmaf(p_, v1.w, ctx[7]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n_lo + i;
+        if (n < n_hi) {
+            const float* v = P.kv + ((size_t)b * P.N + n) * (2 * d) + d + lane * 8;
+            const float4 v0 = ldcg4(v), v1 = ldcg4(v + 4);
+            const float p_ = sc[i];
+            ctx[0] = fmaf(p_, v0.x, ctx[0]); ctx[1] = fmaf(p_, v0.y, ctx[1]); ctx[2] = fmaf(p_, v0.z, ctx[2]); ctx[3] = fmaf(p_, v0.w, ctx[3]);
+            ctx[4] = fmaf(p_, v1.x, ctx[4]); ctx[5] = fmaf(p_, v1.y, ctx[5]); ctx[6] = fmaf(p_, v1.z, ctx[6]); ctx[7] = fmaf(p_, v1.w, ctx[7]);
+        }
     }
     return n_lo + besti;
 }
 
-// ---- recompute path: rows of the AudioDec receptive field ---------------------------------------------
-struct RowList { int cnt[GMAX], off[GMAX + 1], M; };
-__device__ __forceinline__ RowList make_rows(const Smem& S, int G, int j, int prow) {
-    RowList r; r.off[0] = 0;
+// ---- pre-pass: refresh the receptive field (rows t < j) of the utterances whose window moved -------------------
+struct PreRows { int t_lo[GMAX], n[GMAX], off[GMAX + 1]; };        // per utterance: first row, row count (rows t_lo .. j-1), scratch offset
+__device__ __forceinline__ PreRows pre_rows(const Smem& S, int G, int j, int prow) {
+    PreRows r; r.off[0] = 0;
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) {
-        r.cnt[g] = (g < G) ? (S.moved[g] ? min(prow, j + 1) : 1) : 0;
-        r.off[g + 1] = r.off[g] + r.cnt[g];
+        const bool mv = g < G && S.moved[g];
+        r.t_lo[g] = max(0, j - (prow - 1));
+        r.n[g] = mv ? j - r.t_lo[g] : 0;
+        r.off[g + 1] = r.off[g] + r.n[g];
     }
-    r.M = r.off[GMAX];
     return r;
 }
-__device__ __forceinline__ void row_of(const RowList& r, int m, int j, int& g, int& t) {
+__device__ __forceinline__ void pre_row_of(const PreRows& r, int m, int& g, int& t) {
     g = 0;
 #pragma unroll
     for (int i = 1; i < GMAX; ++i) if (m >= r.off[i]) g = i;
-    t = j - r.cnt[g] + 1 + (m - r.off[g]);
+    t = r.t_lo[g] + (m - r.off[g]);
+}
+// address of W[k][n] (k = row within the layer's K) inside the ring; the layer's chunks occupy consecutive slots from pos0
+__device__ __forceinline__ const float* w_quad(const Smem& S, const DecLayer& l, unsigned pos0, int k, int ns, int n) {
+    const int c = k / l.krows, kc = k - c * l.krows, kr8 = l.krows >> 3;
+    const int reg = kc / kr8, wi = kc - reg * kr8;                   // wi is a multiple of 4 for the callers
+    return &S.ring[(pos0 + c) % DEC_NSLOT][reg][((wi >> 2) * ns + n) * 4];
 }
 
-// register-tiled fp32 GEMM of the row list against this CTA's weight slice; 128 rows x NS columns per pass,
-// thread tile 4 rows x TN columns {q, q+8, ..}; A sub-tiles (128 rows x 16 k) transposed through shared memory
+// register-tiled fp32 GEMM of ONE utterance: rows {rg, rg+32, rg+64} x TN columns {q, q+8, ..} per thread; the source rows
+// of a 16-channel slab are staged once (cp.async, 3 stages) and used for every tap
 template <int TN>
-__device__ void pyr_gemm(const DecParams& P, Smem& S, Stream& st, int li, int j, int b0, const RowList& rl, int rank, float* scr) {
+__device__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
     constexpr int NS = 8 * TN;
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, q = tid & 7, rg = tid >> 3;
-    const int nrb = (rl.M + 127) / 128;                   // <= 3
-    float acc[3][4][TN];
+    const int halo = (l.ntaps - 1) * l.rate, n_src = n_out + halo;    // source rows t_lo - halo .. j-1  (<= 96)
+    const int nslab = l.cin / 16;
+    const float* in = P.in_hist[li];
+    float acc[3][TN];
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
+    for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < TN; ++c) acc[i][c] = 0.f;
+    float* As = S.wrk;
+    auto stage = [&](int ks) {
+        float* dst = As + (ks % 3) * SROWS * SLD;
+        for (int i = tid; i < n_src * 4; i += NT) {
+            const int s = i >> 2, c4 = i & 3;
+            const int t = t_lo - halo + s;
+            cp_async16(dst + s * SLD + c4 * 4, in + ((size_t)b * P.T + (t < 0 ? 0 : t)) * l.ldin + ks * 16 + c4 * 4, t >= 0);
+        }
+        cp_async_commit();
+    };
+    stage(0);
+    if (nslab > 1) stage(1); else cp_async_commit();
+    for (int ks = 0; ks < nslab; ++ks) {
+        cp_async_wait<1>();                                           // slab ks has landed (at most the newest group is pending)
+        __syncthreads();                                              // ... for every thread, and slab ks-1 is fully consumed
+        if (ks + 2 < nslab) stage(ks + 2); else cp_async_commit();
+        const float* A = As + (ks % 3) * SROWS * SLD;
+        for (int tap = 0; tap < l.ntaps; ++tap) {
+            const int soff = tap * l.rate;                            // slot of output row m under this tap = m + tap*rate
 #pragma unroll
-            for (int c = 0; c < TN; ++c) acc[a][i][c] = 0.f;
-    float* As = S.wrk;                                    // [2][16][ALD]
-    const int lr = tid & 127, lk = tid >> 7;              // loader role: row, k-quad {lk, lk+2}
-    for (int c = l.ch0; c < l.ch0 + l.nch; ++c) {
-        const DecChunk& ch = P.C[c];
-        const float* w = stream_acquire(S, st);
-        const int shift = -(l.ntaps - 1 - ch.tap) * l.rate;
-        const int nks = ch.krows / 16;
+            for (int k4 = 0; k4 < 4; ++k4) {
+                float4 w4[TN];
 #pragma unroll
-        for (int rb = 0; rb < 3; ++rb) {
-            if (rb < nrb) {
-                const int m = rb * 128 + lr;
-                const float* src = nullptr;
-                if (m < rl.M) {
-                    int g, t; row_of(rl, m, j, g, t);
-                    const int ts = t + shift;
-                    if (ts >= 0) src = P.in_hist[li] + ((size_t)(b0 + g) * P.T + ts) * l.ldin + ch.ci0;
-                }
-                float4 ra[2];
-                auto gload = [&](int ks) {
+                for (int cc = 0; cc < TN; ++cc)
+                    w4[cc] = *reinterpret_cast<const float4*>(w_quad(S, l, pos0, tap * l.cin + ks * 16 + k4 * 4, NS, q + 8 * cc));
 #pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        ra[i] = src ? ldcg4(src + ks * 16 + (lk + 2 * i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                };
-                auto sstore = [&](int buf) {
+                for (int i = 0; i < 3; ++i) {
+                    const int m = rg + 32 * i;
+                    if (m < n_out) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(A + (m + soff) * SLD + k4 * 4);
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        float* a0 = As + (buf * 16 + (lk + 2 * i) * 4) * ALD + lr;
-                        a0[0] = ra[i].x; a0[ALD] = ra[i].y; a0[2 * ALD] = ra[i].z; a0[3 * ALD] = ra[i].w;
-                    }
-                };
-                gload(0);
-                __syncthreads();                          // previous users of As are done
-                sstore(0);
-                __syncthreads();
-                for (int ks = 0; ks < nks; ++ks) {
-                    const int buf = ks & 1;
-                    if (ks + 1 < nks) gload(ks + 1);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {
-                        float4 w4[TN];
-#pragma unroll
-                        for (int cc = 0; cc < TN; ++cc)
-                            w4[cc] = *reinterpret_cast<const float4*>(w + ((size_t)(ks * 4 + k4) * NS + q + 8 * cc) * 4);
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk) {
-                            const float4 a4 = *reinterpret_cast<const float4*>(As + (buf * 16 + k4 * 4 + kk) * ALD + rg * 4);
-#pragma unroll
-                            for (int cc = 0; cc < TN; ++cc) {
-                                const float ww = kk == 0 ? w4[cc].x : (kk == 1 ? w4[cc].y : (kk == 2 ? w4[cc].z : w4[cc].w));
-                                acc[rb][0][cc] = fmaf(a4.x, ww, acc[rb][0][cc]);
-                                acc[rb][1][cc] = fmaf(a4.y, ww, acc[rb][1][cc]);
-                                acc[rb][2][cc] = fmaf(a4.z, ww, acc[rb][2][cc]);
-                                acc[rb][3][cc] = fmaf(a4.w, ww, acc[rb][3][cc]);
-                            }
+                        for (int cc = 0; cc < TN; ++cc) {
+                            float a = acc[i][cc];
+                            a = fmaf(a4.x, w4[cc].x, a); a = fmaf(a4.y, w4[cc].y, a);
+                            a = fmaf(a4.z, w4[cc].z, a); a = fmaf(a4.w, w4[cc].w, a);
+                            acc[i][cc] = a;
                         }
                     }
-                    if (ks + 1 < nks) { sstore(buf ^ 1); __syncthreads(); }
                 }
             }
         }
-        stream_release(P, S, st);
     }
-    // pre-LN slice (+ bias) -> scratch rows [m][512]
+    cp_async_wait<0>();
+    __syncthreads();                                                  // the slab buffers are free for the next utterance
 #pragma unroll
-    for (int rb = 0; rb < 3; ++rb) {
-        if (rb < nrb) {
+    for (int cc = 0; cc < TN; ++cc) {
+        const int n = q + 8 * cc;
+        const float bs = bias_smem_or_global(P, nullptr, li, rank, n);
+        const int col = pre_col(l, rank, n);
 #pragma unroll
-            for (int cc = 0; cc < TN; ++cc) {
-                const int n = q + 8 * cc;
-                const float bs = bias_of(P, S, li, rank, n);
-                const int col = pre_col(l, rank, n);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int m = rb * 128 + rg * 4 + i;
-                    if (m < rl.M) scr[(size_t)m * 512 + col] = acc[rb][i][cc] + bs;
-                }
-            }
+        for (int i = 0; i < 3; ++i) {
+            const int m = rg + 32 * i;
+            if (m < n_out) scr_rows[(size_t)m * 512 + col] = acc[i][cc] + bs;
         }
     }
 }
 
-// LayerNorm / gate / highway mix of the recomputed rows: one warp per row over the whole cluster
-__device__ void pyr_ln(const DecParams& P, Smem& S, int li, int j, int b0, const RowList& rl, int rank, const float* scr) {
+// <= 4 rows of one utterance: the GEMV path with the rows in the role of the utterances
+__device__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
+    const DecLayer& l = P.L[li];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    float* xs = S.wrk;                                                // [m][tap*cin + c], pitch 768
+    const int per_row = l.cin / 4, K = l.ntaps * l.cin;
+    for (int i = tid; i < n_out * l.ntaps * per_row; i += NT) {
+        const int c4 = i % per_row, rt = i / per_row, tap = rt % l.ntaps, m = rt / l.ntaps;
+        const int t = t_lo + m - (l.ntaps - 1 - tap) * l.rate;
+        cp_async16(xs + m * 768 + tap * l.cin + c4 * 4, P.in_hist[li] + ((size_t)b * P.T + (t < 0 ? 0 : t)) * l.ldin + c4 * 4, t >= 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    float acc[GMAX];
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+    const int kr8 = l.krows >> 3;
+    for (int c = 0; c * l.krows < K; ++c)
+        gemv_dispatch(l.ns, &S.ring[(pos0 + c) % DEC_NSLOT][warp][0], xs + c * l.krows + warp * kr8, 768, kr8, n_out, acc);
+#pragma unroll
+    for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
+    __syncthreads();
+    for (int idx = tid; idx < n_out * l.ns; idx += NT) {
+        const int m = idx / l.ns, n = idx % l.ns, ng = NT / l.ns;
+        if (l.kind == 0 && n >= l.cs) continue;
+        float s = bias_smem_or_global(P, nullptr, li, rank, n);
+        for (int qq = 0; qq < ng; ++qq) s += S.red[m][qq * l.ns + n];
+        scr_rows[(size_t)m * 512 + pre_col(l, rank, n)] = s;
+    }
+    __syncthreads();                                                  // red / xs are free for the next utterance
+}
+
+// LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
+__device__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRows& rl, int rank, const float* scr) {
     const DecLayer& l = P.L[li];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* prm = S.prm[li & 1];
+    const float* prm = &S.red[0][0];
     const float fC = 256.f;
-    for (int m = rank * NWARP + warp; m < rl.M; m += NC * NWARP) {
-        int g, t; row_of(rl, m, j, g, t);
+    for (int m = rank * NWARP + warp; m < rl.off[GMAX]; m += NC * NWARP) {
+        int g, t; pre_row_of(rl, m, g, t);
         const float* y = scr + (size_t)m * 512;
         const size_t row = (size_t)(b0 + g) * P.T + t;
         float z[2][8];
@@ -505,35 +572,47 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
     const int G = min(P.G, P.B - b0);
     float* scr = P.pre_scr + (size_t)cluster * P.G * 85 * 512;
 
-    Stream st;
-    st.base = P.wstream + (size_t)rank * P.stream_len;
-    st.pos = 0; st.total = (long long)P.steps * P.nch;
-
     if (tid == 0) {
-        for (int s = 0; s < DEC_NSLOT; ++s) mbar_init(reinterpret_cast<uint64_t*>(&S.full[s]), 1);
+        for (int s = 0; s < DEC_NSLOT; ++s)
+            for (int w = 0; w < NWARP; ++w) mbar_init(bar64(&S.fullw[s][w]), 1);
+        mbar_init(bar64(&S.gbar[0]), 1); mbar_init(bar64(&S.gbar[1]), 1);
         fence_mbar_init();
     }
-    for (int i = tid; i < 2 * GMAX * XLD; i += NT) { (&S.xcur[0][0][0])[i] = 0.f; (&S.xtap[0][0][0])[i] = 0.f; (&S.pre[0][0][0])[i] = 0.f; }
+    for (int i = tid; i < 2 * GMAX * XLD; i += NT) (&S.xin[0][0][0])[i] = 0.f;
+    for (int i = tid; i < 2 * NC * PLD; i += NT) (&S.pre[0][0][0])[i] = 0.f;
     if (tid < GMAX) { S.p_cur[tid] = 0; S.p_prev[tid] = 0; S.p_next[tid] = 0; S.moved[tid] = 0; }
+    if (tid < 2) S.fmoved[tid] = 0;
     if (tid < 16) S.prof[tid] = 0;
     __syncthreads();
-    if (tid == 0) for (int s = 0; s < DEC_NSLOT; ++s) stream_issue(P, S, st, s);
+
+    Stream st;
+    st.base = P.wstream + (size_t)rank * P.stream_len;
+    st.cons = Cur{0, 0, 0}; st.prod = Cur{0, 0, 0}; st.pos = 0;
+    for (int s = 0; s < DEC_NSLOT; ++s) {                // the first chunks are AudioEnc chunks of frame 0 (nch_enc > DEC_NSLOT)
+        if (lane == 0) stream_issue(P, S, st, st.prod, s, warp);
+        cur_next(P, S, st.prod);
+    }
     prefetch_params(P, S, 0, rank);
     cp_async_commit();
-    cluster_sync_all();                                   // every CTA of the cluster is running: DSMEM is addressable
+    cluster_sync_all();                                   // every CTA of the cluster is running: DSMEM and its barriers exist
 
     int cb = 0;
+    unsigned lcount = 0;
     int n_moved_frames = 0, n_moved_utt = 0;
     if (tid == 0) S.prof_last = clock64();
     for (int j = 0; j < P.steps; ++j) {
-        bool any_moved = false;
         if (tid < GMAX) S.moved[tid] = (tid < G && j > 0 && S.p_cur[tid] != S.p_prev[tid]) ? 1 : 0;
+        if (tid == 0) {
+            int any = 0;
+            for (int g = 0; g < G; ++g) any |= (j > 0 && S.p_cur[g] != S.p_prev[g]) ? 1 : 0;
+            S.fmoved[j & 1] = any;
+        }
         __syncthreads();
-        for (int g = 0; g < G; ++g) any_moved |= (S.moved[g] != 0);
+        const bool any_moved = S.fmoved[j & 1] != 0;
         if (rank == 0 && tid < G) P.p_hist[(size_t)(b0 + tid) * P.T + j] = S.p_cur[tid];
 
-        // AudioEnc (networks.py:81-124): input Y[j-1] (train.py:51), already in xcur[cb]
-        for (int li = 0; li < P.n_enc; ++li) cb = layer_row(P, S, st, li, j, b0, G, rank, cb, false);
+        // AudioEnc (networks.py:81-124): input Y[j-1] (train.py:51), already in xin[cb]
+        for (int li = 0; li < P.n_enc; ++li) cb = layer_row(P, S, st, li, j, b0, G, rank, cb, lcount);
 
         // Attention of row j under the current window, redundantly in every CTA: R[j] = [A.V ; Q] (networks.py:140-153)
         __syncthreads();
@@ -541,26 +620,23 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
             const int g = warp;
             float qv[8], ctx[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) qv[i] = S.xcur[cb][g][lane * 8 + i];
+            for (int i = 0; i < 8; ++i) qv[i] = S.xin[cb][g][lane * 8 + i];
             const int amax = attend_row(P, qv, b0 + g, S.p_cur[g], lane, ctx);
             if (lane == 0) S.p_next[g] = amax;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { S.xcur[cb ^ 1][g][lane * 8 + i] = ctx[i]; S.xcur[cb ^ 1][g][P.d + lane * 8 + i] = qv[i]; }
+            for (int i = 0; i < 8; ++i) { S.xin[cb ^ 1][g][lane * 8 + i] = ctx[i]; S.xin[cb ^ 1][g][P.d + lane * 8 + i] = qv[i]; }
         }
         cb ^= 1;
-        __syncthreads();
         LAP(LP_ATT);
 
-        int li = P.n_enc;
         if (any_moved) {
-            // ---- recompute the receptive field of the moved utterances under the new window ----
+            // ---- pre-pass: rows t < j of the moved utterances under the new window (uniform branch: see the file header) ----
             n_moved_frames++;
             for (int g = 0; g < G; ++g) n_moved_utt += S.moved[g];
-            cluster_sync_all();                           // Q[j] slices of all CTAs are in the history
-            const RowList ra = make_rows(S, G, j, P.L[P.n_enc].prow);
+            const PreRows ra = pre_rows(S, G, j, P.L[P.n_enc].prow);
             const float* Qh = P.out_hist[P.n_enc - 1];
-            for (int m = rank * NWARP + warp; m < ra.M; m += NC * NWARP) {
-                int g, t; row_of(ra, m, j, g, t);
+            for (int m = rank * NWARP + warp; m < ra.off[GMAX]; m += NC * NWARP) {
+                int g, t; pre_row_of(ra, m, g, t);
                 const size_t row = (size_t)(b0 + g) * P.T + t;
                 float qv[8], ctx[8];
                 const float4 q0 = ldcg4(Qh + row * P.d + lane * 8), q1 = ldcg4(Qh + row * P.d + lane * 8 + 4);
@@ -574,31 +650,44 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
             }
             cluster_sync_all();
             LAP(LP_PYR_ATT);
-            for (; li < P.nl && P.L[li].prow > 1; ++li) {
-                const int nl_next = li + 1;               // AudioDec never ends on a recomputed block
-                prefetch_params(P, S, nl_next, rank);
-                cp_async_commit();
-                cp_async_wait<1>();
-                __syncthreads();
-                const RowList rl = make_rows(S, G, j, P.L[li].prow);
-                if (P.L[li].ns == 32) pyr_gemm<4>(P, S, st, li, j, b0, rl, rank, scr);
-                else pyr_gemm<2>(P, S, st, li, j, b0, rl, rank, scr);
+            for (int li = P.n_enc; li < P.nl && P.L[li].prow > 1; ++li) {
+                const DecLayer& l = P.L[li];
+                // every warp waits for ALL regions of the block's chunks (lane w watches region w)
+                for (int c = 0; c < l.nch; ++c) {
+                    const unsigned pp = st.pos + c;
+                    if (lane < NWARP) mbar_wait(bar64(&S.fullw[pp % DEC_NSLOT][lane]), (pp / DEC_NSLOT) & 1u);
+                }
+                __syncwarp();
+                const PreRows rl = pre_rows(S, G, j, l.prow);
+                for (int g = 0; g < G; ++g) {
+                    if (rl.n[g] <= 0) continue;
+                    float* rows = scr + (size_t)rl.off[g] * 512;
+                    if (rl.n[g] <= GMAX) pyr_small_utt(P, S, li, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                    else if (l.ns == 32) pyr_gemm_utt<4>(P, S, li, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                    else pyr_gemm_utt<2>(P, S, li, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                }
+                __syncthreads();                          // every warp is done with every region of these chunks
+                for (int c = 0; c < l.nch; ++c) {
+                    if (lane == 0) { fence_proxy_async_smem(); stream_issue(P, S, st, st.prod, (int)(st.pos % DEC_NSLOT), warp); }
+                    stream_advance(P, S, st);
+                }
+                for (int i = tid; i < 256; i += NT)       // this block's LayerNorm parameters for pyr_ln
+                    *reinterpret_cast<float4*>(&S.red[0][0] + i * 4) = __ldg(reinterpret_cast<const float4*>(P.lnp[li]) + i);
                 LAP(LP_PYR_GEMM);
                 cluster_sync_all();
                 LAP(LP_PYR_BAR);
-                pyr_ln(P, S, li, j, b0, rl, rank, scr);
+                pyr_ln(P, S, li, b0, rl, rank, scr);
                 LAP(LP_PYR_LN);
                 cluster_sync_all();
                 LAP(LP_PYR_BAR);
             }
-            cb = layer_row(P, S, st, li, j, b0, G, rank, cb, true);
-            ++li;
         }
-        for (; li < P.nl; ++li) cb = layer_row(P, S, st, li, j, b0, G, rank, cb, false);
+        // AudioDec (networks.py:166-212), one row per utterance
+        for (int li = P.n_enc; li < P.nl; ++li) cb = layer_row(P, S, st, li, j, b0, G, rank, cb, lcount);
 
         __syncthreads();
         if (tid < GMAX) { S.p_prev[tid] = S.p_cur[tid]; S.p_cur[tid] = S.p_next[tid]; }
-        __syncthreads();
+        cluster_sync_all();                               // this frame's history rows are visible to the whole cluster
         LAP(LP_FRAME);
     }
     if (rank == 0 && tid < G) P.p_final[b0 + tid] = S.p_cur[tid];

@@ -11,10 +11,11 @@ namespace dctts {
 constexpr int DEC_NC = 16;          // CTAs per cluster (non-portable cluster size)
 constexpr int DEC_GMAX = 4;         // utterances per cluster
 constexpr int DEC_THREADS = 256;
-constexpr int DEC_SLOT_F = 4096;    // floats per ring slot (16 KB)
-constexpr int DEC_NSLOT = 9;
+constexpr int DEC_NSLOT = 3;        // ring slots
+constexpr int DEC_REG_F = 1536;     // floats per warp region of a slot (6 KB): every warp streams and frees its own k-rows
+constexpr int DEC_SLOT_F = 8 * DEC_REG_F;   // 48 KB per slot
 constexpr int DEC_MAXL = 24;        // 13 AudioEnc + 11 AudioDec blocks
-constexpr int DEC_MAXCH = 112;      // weight chunks per frame
+constexpr int DEC_MAXCH = 48;       // weight chunks per frame
 constexpr int DEC_PRM_F = 1024 + 64;   // per-layer parameter block: gamma1 | beta1 | gamma2 | beta2 (256 each) | bias slice
 
 struct DecLayer {
@@ -26,10 +27,11 @@ struct DecLayer {
     int ns;          // weight-slice columns per CTA (multiple of 4)
     int cs;          // channels owned per CTA (per LN half)
     int ch0, nch;    // chunk range of this layer within a frame
+    int krows;       // k rows per chunk of this layer
     int prow;        // AudioDec receptive-field rows to recompute when the attention window moved (1 otherwise)
     int ldin;        // leading dimension of the input history
 };
-struct DecChunk { int off; short nfl4; short tap; short ci0; short krows; };   // off: float offset in a rank's stream; nfl4: floats / 4
+struct DecChunk { int off; short nfl4; short k0; short krows; short layer; };   // off: float offset in a rank's stream; nfl4: floats / 4; k0: first k row (tap*cin + ci)
 
 struct DecParams {
     DecLayer L[DEC_MAXL];
@@ -47,7 +49,7 @@ struct DecParams {
     int* p_final;                      // (B) window after the last step
     int* stats;                        // [clusters][2]: frames with a window move, utterance-frames recomputed
     long long* prof;                   // optional [16] SM-clock lap timers of cluster 0 / rank 0 (option decode_prof), else nullptr
-    int nl, n_enc, nch, stream_len;
+    int nl, n_enc, nch, nch_enc, pyr_ch0, pyr_ch1, stream_len;   // pyr_ch0..pyr_ch1: chunks of the AudioDec blocks with prow > 1
     int B, G, T, N, d, n_mels, win_size, steps;
 };
 static_assert(sizeof(DecParams) <= 4000, "DecParams must fit the kernel parameter space");

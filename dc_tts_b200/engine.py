@@ -346,13 +346,54 @@ class Engine:
                                                  out.ctypes.data_as(C.c_void_p), out.size), "dctts_train_tensor(%s)" % name)
         return out
 
+    def train_set_tensor(self, name, array, what="param"):
+        """Upload a variable / Adam m / Adam v of the network being trained from the TF layout (resume)."""
+        from .arch import param_shapes
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        if tuple(a.shape) != tuple(param_shapes()[name]):
+            raise DcttsError("train_set_tensor(%s): shape %s, expected %s" % (name, a.shape, param_shapes()[name]))
+        self._check(self._lib.dctts_train_set_tensor(self._h, name.encode(), {"param": 0, "m": 2, "v": 3}[what],
+                                                     a.ctypes.data_as(C.c_void_p), a.size), "dctts_train_set_tensor(%s)" % name)
+
+    def restore_training(self, logdir, scope="Text2Mel"):
+        """What tf.train.Supervisor does when `logdir` already holds a checkpoint (train.py:144): every variable of the
+        network being trained, its Adam slots (`<name>/Adam`, `<name>/Adam_1`) and `gs/global_step` come back from the
+        latest bundle, so a restarted run continues the Noam schedule and the Adam state instead of overwriting
+        model_gs_001k from scratch.  Call after train_init / train_init_ssrn.  Returns the restored global step, or None
+        when the directory holds no checkpoint."""
+        from .arch import param_shapes
+        from .checkpoint import latest_checkpoint, list_variables, load_checkpoint
+        path = latest_checkpoint(logdir)
+        if path is None:
+            return None
+        avail = {n for n, _, _ in list_variables(path)}
+        names = [n for n in param_shapes() if n.startswith(scope + "/")]
+        missing = [n for n in names if n not in avail]
+        if missing:
+            raise DcttsError("restore_training: %s lacks %s" % (path, ", ".join(missing[:3])))
+        for n in names:
+            want = [n] + [n + sfx for sfx in ("/Adam", "/Adam_1") if n + sfx in avail]
+            t = load_checkpoint(path, want)
+            self.train_set_tensor(n, t[n], "param")
+            if n + "/Adam" in t:
+                self.train_set_tensor(n, t[n + "/Adam"], "m")
+            if n + "/Adam_1" in t:
+                self.train_set_tensor(n, t[n + "/Adam_1"], "v")
+        gs = 0
+        if "gs/global_step" in avail:
+            gs = int(load_checkpoint(path, ["gs/global_step"])["gs/global_step"])
+        return gs
+
     def save_checkpoint(self, prefix, global_step, scope="Text2Mel"):
         """What `sv.saver.save(sess, logdir + '/model_gs_...')` writes at train.py:152 for the network being trained
-        (`scope` "Text2Mel" or "SSRN"): every variable of the scope, its Adam slots (`<name>/Adam`, `<name>/Adam_1`) and
-        `gs/global_step`, as a TF tensor bundle."""
+        (`scope` "Text2Mel" or "SSRN"): every variable of the scope, its Adam slots (`<name>/Adam`, `<name>/Adam_1`),
+        the optimiser's `beta1_power` / `beta2_power` (TF's Adam keeps beta^t as variables; a TF train-graph
+        Saver.restore expects them) and `gs/global_step`, as a TF tensor bundle."""
         from .arch import param_shapes
         from .checkpoint import save_checkpoint
-        out = {"gs/global_step": np.array(global_step, np.int32)}
+        out = {"gs/global_step": np.array(global_step, np.int32),
+               "beta1_power": np.array(0.9 ** (global_step + 1), np.float32),      # after t applies TF holds beta^(t+1)
+               "beta2_power": np.array(0.999 ** (global_step + 1), np.float32)}
         for name in param_shapes():
             if name.startswith(scope + "/"):
                 out[name] = self.train_tensor(name, "param")

@@ -20,7 +20,11 @@ from .params import init_params
 from .train import Graph, Session
 
 
-def synthesize(params=None, sentences=None, fast=True, write=True, seed=0, vocoder=True):
+def synthesize(params=None, sentences=None, fast=True, write=True, seed=0, vocoder=True, allow_random_init=False):
+    """`params`: a name -> array dict to use instead of the checkpoints.  Without it the latest checkpoints of
+    hp.logdir-1 (Text2Mel) and hp.logdir-2 (SSRN) are restored, and a missing one RAISES like the reference's
+    `saver.restore(sess, None)` does (synthesize.py:33,39) -- seeded random weights are used only when the caller asks
+    for them (`allow_random_init=True`, benchmarks and smoke tests) or has already loaded parameters into the engine."""
     # Load data
     L = load_data("synthesize", sentences)
 
@@ -32,12 +36,22 @@ def synthesize(params=None, sentences=None, fast=True, write=True, seed=0, vocod
         # Restore parameters (synthesize.py:31-41)
         if params is not None:
             g.engine.load_params(params)
-        elif latest_checkpoint(hp.logdir + "-1") and latest_checkpoint(hp.logdir + "-2"):
-            g.engine.restore(hp.logdir + "-1", hp.logdir + "-2")
-        elif not g.engine.params_loaded:
-            g.engine.load_params(init_params(seed))
-        print("Text2Mel Restored!")
-        print("SSRN Restored!")
+            print("Parameters loaded from the caller's dictionary")
+        elif g.engine.params_loaded:
+            print("Using the parameters already committed to the engine")
+        else:
+            ck1, ck2 = latest_checkpoint(hp.logdir + "-1"), latest_checkpoint(hp.logdir + "-2")
+            if ck1 and ck2:
+                g.engine.restore(hp.logdir + "-1", hp.logdir + "-2")
+                print("Text2Mel Restored!")
+                print("SSRN Restored!")
+            elif allow_random_init:
+                g.engine.load_params(init_params(seed))
+                print("WARNING: no checkpoint -- seeded random weights (allow_random_init=True); the output is noise")
+            else:
+                missing = [d for d, c in ((hp.logdir + "-1", ck1), (hp.logdir + "-2", ck2)) if not c]
+                raise FileNotFoundError("no checkpoint under %s (reference: Saver.restore(sess, None) fails); pass params=..., "
+                                        "or allow_random_init=True for seeded random weights" % " and ".join(missing))
 
         if fast:
             # the whole loop on the device (CUDA-graph replay), identical results

@@ -171,6 +171,8 @@ int dctts_train_step_ssrn(dctts_handle h, const float* mels, const float* mags, 
                           int32_t apply, float* losses_host, void* stream);
 int dctts_train_grads(dctts_handle h, float** grads, int64_t* count);
 int dctts_train_tensor(dctts_handle h, const char* tf_name, int32_t what, float* host_out, int64_t count);
+/* Inverse of dctts_train_tensor for what = 0 (variable), 2 (Adam m), 3 (Adam v): restores a training state (resume). */
+int dctts_train_set_tensor(dctts_handle h, const char* tf_name, int32_t what, const float* host_in, int64_t count);
 
 /* ---- utilities ----------------------------------------------------------------- */
 /* Pre-size the workspace (otherwise grown lazily on first use) for batches up to B. */

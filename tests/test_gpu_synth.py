@@ -153,3 +153,21 @@ def test_synthesize_script(engine, tmp_path, monkeypatch):
     sr, wav = read_wav(tmp_path / "samples" / "1.wav")
     assert sr == hp.sr and wav.dtype == np.float32 and 0 < len(wav) <= hp.hop_length * (hp.max_T * hp.r - 1)
     assert np.isfinite(wav).all()
+
+
+def test_synthesize_without_checkpoint_raises(engine, tmp_path, monkeypatch):
+    """a missing logdir-1 / logdir-2 checkpoint must fail like the reference's Saver.restore(sess, None)
+    (synthesize.py:33,39), never fall back silently to random weights."""
+    from dc_tts_b200 import synthesize as syn
+    from dc_tts_b200.engine import Engine, set_engine
+    monkeypatch.chdir(tmp_path)
+    fresh = Engine(0)                                   # no parameters committed
+    set_engine(fresh)
+    try:
+        with pytest.raises(FileNotFoundError):
+            syn.synthesize(sentences=os.path.join(ROOT, "harvard_sentences.txt"), write=False)
+        Y, Z = syn.synthesize(sentences=os.path.join(ROOT, "harvard_sentences.txt"), write=False, allow_random_init=True, seed=3)
+        assert Y.shape[0] == 20 and np.isfinite(Z).all()
+    finally:
+        set_engine(engine)
+        fresh.close()

@@ -249,3 +249,47 @@ def test_cuda_ssrn_train_step_vs_oracle(B, T, rate, seed):
         np.testing.assert_allclose(eng.train_tensor(n, "m"), m, rtol=2e-3, atol=1e-9)
         step = np.abs(newP[n] - P[n]).max()
         assert np.abs(eng.train_tensor(n, "param") - newP[n]).max() <= 0.05 * step + 2.4e-7, n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("num", [1, 2])
+def test_cuda_training_resumes_from_its_own_checkpoint(tmp_path, num):
+    """a restarted run must continue, not start over.  Train 3 steps, save (variables + Adam slots + gs +
+    beta powers), restore into a fresh handle with Engine.restore_training, take one more step on both: identical losses
+    and identical updated weights (what tf.train.Supervisor's restore gives train.py:144)."""
+    from dc_tts_b200 import checkpoint as ck
+    from dc_tts_b200.engine import Engine
+    P = init_params(2)
+    scope = "Text2Mel" if num == 1 else "SSRN"
+    T = hp.max_T if num == 1 else 12
+    L, mels = _batch(2, seed=5)
+    mels = mels[:, :T]
+    mags = np.random.default_rng(4).uniform(0, 1, (2, 4 * T, 1 + hp.n_fft // 2)).astype(np.float32)
+
+    def init(e):
+        e.load_params(P)
+        e.train_init(2, 0.0) if num == 1 else e.train_init_ssrn(2, T, 0.0)
+
+    def step(e, gs):
+        return e.train_step(L, mels, global_step=gs, seed=gs) if num == 1 else e.train_step_ssrn(mels, mags, global_step=gs, seed=gs)
+
+    a = Engine(0); init(a)
+    for gs in range(3):
+        step(a, gs)
+    logdir = str(tmp_path / ("LJ01-%d" % num))
+    a.save_checkpoint(logdir + "/model_gs_000k", 3, scope)
+    got = ck.load_checkpoint(logdir + "/model_gs_000k", ["beta1_power", "beta2_power", "gs/global_step"])
+    assert abs(float(got["beta1_power"]) - 0.9 ** 4) < 1e-7 and int(got["gs/global_step"]) == 3
+    b = Engine(0); init(b)
+    assert b.restore_training(str(tmp_path / "nothing-here"), scope) is None
+    assert b.restore_training(logdir, scope) == 3
+    probe = "Text2Mel/AudioDec/HC_4/conv1d/kernel" if num == 1 else "SSRN/D_4/conv2d_transpose/kernel"
+    for what in ("param", "m", "v"):                                   # the restored state is the saved state, bit for bit
+        assert np.array_equal(a.train_tensor(probe, what), b.train_tensor(probe, what)), what
+    la, lb = step(a, 3), step(b, 3)
+    for k in la:                                                       # float atomics reorder sums: tolerance, not bits
+        assert abs(la[k] - lb[k]) <= 1e-4 * max(1.0, abs(la[k])), k
+    for what in ("param", "m", "v"):
+        x, y = a.train_tensor(probe, what), b.train_tensor(probe, what)
+        assert np.abs(x - y).max() <= 1e-3 * np.abs(x).max() + 1e-12, what
+    a.close(); b.close()

@@ -30,6 +30,13 @@ class FakeEngine:
     def save_checkpoint(self, prefix, gs, scope):
         self.saved.append((prefix, gs, scope))
 
+    restored_from = None
+    resume_at = None
+
+    def restore_training(self, logdir, scope):
+        self.restored_from = (logdir, scope)
+        return self.resume_at
+
 
 def _dataset(tmp_path, n=7):
     d = tmp_path / "LJSpeech-1.0"
@@ -99,3 +106,58 @@ def test_prepo_writes_what_the_trainer_reads(tmp_path):
     assert n == 3 and sorted(os.listdir(tmp_path / "mels")) == ["LJ000.npy", "LJ001.npy", "LJ002.npy"]
     fname, mel, mag = trainer._load_spectrograms_npy(os.path.join(d, "wavs", "LJ001.wav"), str(tmp_path / "mels"), str(tmp_path / "mags"))
     assert fname == "LJ001.wav" and np.array_equal(mel, store[fname][0]) and np.array_equal(mag, store[fname][1])
+
+
+def test_resume_and_empty_dataset(tmp_path):
+    """a logdir that already holds a checkpoint is resumed (tf.train.Supervisor, train.py:144), and a data set
+    that can never fill a batch raises instead of spinning."""
+    d, loader, _ = _dataset(tmp_path)
+    fpaths, _, texts = trainer.load_train_data(d)
+    eng = FakeEngine(); eng.resume_at = 4000
+    logdir = str(tmp_path / "LJ01-1")
+    gs = trainer.train(1, eng, trainer.fixed_size_batches(fpaths, texts, B=2, seed=0, loader=loader), num_iterations=4002,
+                       logdir=logdir, log=lambda *_: None)
+    assert eng.restored_from == (logdir, "Text2Mel") and [c[3] for c in eng.calls] == [4000, 4001, 4002] and gs == 4003
+    eng = FakeEngine(); eng.resume_at = 4000
+    gs = trainer.train(1, eng, trainer.fixed_size_batches(fpaths, texts, B=2, seed=0, loader=loader), num_iterations=1,
+                       logdir=logdir, global_step=0, log=lambda *_: None)
+    assert eng.restored_from is None and gs == 2                     # an explicit global_step starts over
+    with pytest.raises(ValueError):
+        next(trainer.fixed_size_batches(fpaths, texts, B=6, seed=0, loader=loader))   # only 5 utterances fit
+
+
+def test_bucketed_batches_follow_the_reference_queue(tmp_path):
+    """data_load.py:120-129: bucket boundaries every 20 characters from minlen+1, a batch = B utterances of ONE bucket,
+    padded to the longest member of that batch; pad_to_fixed extends the padding to the CUDA step's fixed shapes."""
+    rng = np.random.default_rng(1)
+    n = 60
+    lens = [int(x) for x in rng.integers(12, 150, n)]
+    texts = [rng.integers(2, 30, l).astype(np.int32) for l in lens]
+    frames = [int(1.2 * l) + 5 for l in lens]
+    fpaths = ["wavs/U%03d.wav" % i for i in range(n)]
+    store = {os.path.basename(p): (np.full((t, hp.n_mels), i + 1, np.float32), np.full((4 * t, 5), i + 1, np.float32))
+             for i, (p, t) in enumerate(zip(fpaths, frames))}
+    loader = lambda p: (os.path.basename(p),) + store[os.path.basename(p)]
+    bounds = trainer.bucket_boundaries(lens)
+    assert bounds == list(range(min(lens) + 1, max(lens) - 1, 20))
+    assert trainer.bucket_index(bounds[0] - 1, bounds) == 0 and trainer.bucket_index(bounds[0], bounds) == 1
+    assert trainer.bucket_index(10 ** 6, bounds) == len(bounds)
+    seen = []
+    for L, mels, mags, names, k in trainer.bucketed_batches(fpaths, lens, texts, B=4, seed=3, loader=loader, epochs=2):
+        idx = [int(nm[1:4]) for nm in names]
+        assert all(trainer.bucket_index(lens[i], bounds) == k for i in idx)             # one bucket per batch
+        assert L.shape == (4, max(lens[i] for i in idx))                                  # dynamic_pad: longest member
+        assert mels.shape == (4, max(frames[i] for i in idx), hp.n_mels) and mags.shape[1] == 4 * mels.shape[1]
+        for b, i in enumerate(idx):
+            assert np.array_equal(L[b, :lens[i]], texts[i]) and not L[b, lens[i]:].any()
+            assert (mels[b, :frames[i]] == i + 1).all() and not mels[b, frames[i]:].any()
+        fixed = trainer.pad_to_fixed(L, mels, mags)
+        if L.shape[1] <= hp.max_N and mels.shape[1] <= hp.max_T:
+            Lf, mf, gf = fixed
+            assert Lf.shape == (4, hp.max_N) and mf.shape == (4, hp.max_T, hp.n_mels) and gf.shape[1] == 4 * hp.max_T
+            assert np.array_equal(Lf[:, :L.shape[1]], L) and not Lf[:, L.shape[1]:].any() and not mf[:, mels.shape[1]:].any()
+        else:
+            assert fixed is None
+        seen += idx
+    assert len(seen) >= 2 * n - 4 * (len(bounds) + 1)                                     # only partial buckets are left over
+    assert max(np.bincount(seen)) <= 2                                                    # each utterance at most once per epoch
