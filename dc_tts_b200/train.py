@@ -8,9 +8,12 @@ symbols and `Session.run` evaluates them eagerly on the GPU, so that the referen
 loop (synthesize.py:47-57) runs unmodified in structure.  `Graph.generate` is the fast
 path: the whole loop on the device, replayed from a CUDA graph.
 
-The training branch is not a symbolic graph here: losses, backward pass and optimiser (train.py:82-135) are
-`Engine.train_step` / `train_step_ssrn`, and the loop of train.py:137-160 is `dc_tts_b200/trainer.py: train`;
-`Graph(mode="train")` raises NotImplementedError and says so.
+`Graph(num, mode="train")` is the reference's training object (train.py:22-135): `num_batch`, `global_step`, `lr`, the
+losses and `train_op` are fetchable with `Session.run` exactly as train.py:148 does (`sess.run([g.global_step,
+g.train_op])`): fetching `train_op` takes the next batch of the input pipeline (data_load.get_batch -> here an iterator of
+(L, mels, mags, ...) batches, dc_tts_b200/trainer.py) and runs ONE optimiser step -- forward with dropout, the losses of
+train.py:83-113, backward, clipping, Adam with the Noam rate (train.py:120-131) -- through `Engine.train_step` /
+`train_step_ssrn`.  Plots and summaries (train.py:100-104,116-119,154-157) are out of scope.
 """
 import numpy as np
 import torch
@@ -36,13 +39,33 @@ _TEXT2MEL = ("S", "K", "V", "Q", "R", "alignments", "max_attentions", "Y_logits"
 _FUSED_OK = {"Y", "max_attentions", "alignments", "global_step"}
 
 
+_TRAIN = {1: ("loss", "loss_mels", "loss_bd1", "loss_att"), 2: ("loss", "loss_mags", "loss_bd2")}
+
+
 class Graph:
-    def __init__(self, num=1, mode="train", engine=None, fused=True):
-        if mode != "synthesize":
-            raise NotImplementedError("Graph(mode='train'): use dc_tts_b200.trainer.train (Engine.train_step / train_step_ssrn)")
+    def __init__(self, num=1, mode="train", engine=None, fused=True, batches=None, num_batch=None, global_step=0):
+        """mode "synthesize": the inference graph.  mode "train" (the reference default): `num` = 1 trains Text2Mel, 2 SSRN;
+        `batches` is the input pipeline, an iterator of (L, mels, mags, ...) tuples with fixed shapes (trainer.py)."""
+        if mode not in ("train", "synthesize"):
+            raise ValueError("mode: 'train' or 'synthesize' (train.py:22)")
         self.char2idx, self.idx2char = load_vocab()
         self.engine = engine or get_engine()
         self.fused = fused
+        self.mode, self.num = mode, num
+        if mode == "train":
+            if num not in (1, 2):
+                raise ValueError("num: 1 for Text2Mel, 2 for SSRN (train.py:24)")
+            if batches is None:
+                raise ValueError("Graph(mode='train') needs `batches`: the reference reads them from data_load.get_batch(); "
+                                 "here pass trainer.fixed_size_batches(...) or bucketed batches through pad_to_fixed")
+            self.batches = iter(batches)
+            self.num_batch = num_batch                       # train.py:33; only used for the progress bar
+            self.global_step_value = int(global_step)
+            self.last = {}
+            self._initialised = False
+            for name in ("global_step", "train_op", "lr") + _TRAIN[num]:
+                setattr(self, name, Symbol(self, name))
+            return
         self.global_step_value = 0          # `gs/global_step` (train.py:79-80); no checkpoint offline
         for name in ("L", "mels", "prev_max_attentions") + _TEXT2MEL + ("Z_logits", "Z", "global_step"):
             setattr(self, name, Symbol(self, name))
@@ -66,11 +89,40 @@ class Graph:
                 vals["Y_logits"], vals["Y"] = AudioDec(vals["R"], training=False, fused=self.fused)
         return vals
 
+    def _train_run(self, names):
+        """One `sess.run` of the training graph: fetching train_op consumes a batch and applies one update."""
+        from .utils import learning_rate_decay
+        if "train_op" in names:
+            L, mels, mags = next(self.batches)[:3]
+            if not self._initialised:
+                if self.num == 1:
+                    self.engine.train_init(len(L))
+                else:
+                    self.engine.train_init_ssrn(len(L), mels.shape[1])
+                self._initialised = True
+            gs = self.global_step_value
+            if self.num == 1:
+                self.last = self.engine.train_step(L, mels, global_step=gs, seed=gs)
+            else:
+                self.last = self.engine.train_step_ssrn(mels, mags, global_step=gs, seed=gs)
+            self.global_step_value = gs + 1                   # apply_gradients(global_step=...) increments (train.py:131)
+        out = {"train_op": None, "global_step": np.int64(self.global_step_value),
+               "lr": np.float32(learning_rate_decay(hp.lr, self.global_step_value))}
+        for k in _TRAIN[self.num]:
+            if k in names and k not in self.last:
+                raise ValueError("%s: no training step has run yet (fetch it together with train_op)" % k)
+            out[k] = np.float32(self.last.get(k, np.nan))
+        return out
+
     def run(self, fetches, feed_dict=None, as_numpy=True):
         """`sess.run` equivalent.  Feeding `self.Y` cuts Text2Mel out of the evaluation,
         exactly as feeding g.Y does in the reference (synthesize.py:57)."""
         single = isinstance(fetches, Symbol)
         names = [fetches.name] if single else [f.name for f in fetches]
+        if self.mode == "train":
+            vals = self._train_run(names)
+            out = [vals[n] for n in names]
+            return out[0] if single else out
         feed = {k.name: v for k, v in (feed_dict or {}).items()}
         vals = dict(global_step=np.int64(self.global_step_value))
         need_t2m = any(n in _TEXT2MEL for n in names if n not in feed) or \

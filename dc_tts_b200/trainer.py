@@ -40,17 +40,18 @@ def _load_spectrograms_npy(fpath, mels_dir="mels", mags_dir="mags"):
     return fname, np.load(os.path.join(mels_dir, fname.replace("wav", "npy"))), np.load(os.path.join(mags_dir, fname.replace("wav", "npy")))
 
 
-def fixed_size_batches(fpaths, texts, B=None, seed=0, loader=_load_spectrograms_npy, epochs=None):
+def fixed_size_batches(fpaths, texts, B=None, seed=0, loader=_load_spectrograms_npy, epochs=None, rank=0, world=1):
     """Shuffled batches of exactly B utterances, zero-padded to (B, max_N), (B, max_T, n_mels), (B, 4 max_T, F).
     Utterances that do not fit are skipped; an incomplete last batch of an epoch is dropped (num_batch = len // B,
-    data_load.py:97)."""
+    data_load.py:97).  Data-parallel runs: every rank draws the SAME permutation (same seed) and keeps every
+    world-th utterance, so the ranks' batches are disjoint."""
     B = B or hp.B
     F = 1 + hp.n_fft // 2
     rng = np.random.default_rng(seed)
     epoch = 0
     while epochs is None or epoch < epochs:
         yielded = 0
-        order = rng.permutation(len(fpaths))
+        order = rng.permutation(len(fpaths))[rank::world]
         L = np.zeros((B, hp.max_N), np.int32)
         mels = np.zeros((B, hp.max_T, hp.n_mels), np.float32)
         mags = np.zeros((B, hp.max_T * hp.r, F), np.float32)
@@ -144,11 +145,15 @@ def checkpoint_name(logdir, gs):
     return os.path.join(logdir, "model_gs_{}".format(str(gs // 1000).zfill(3) + "k"))
 
 
-def train(num, engine, batches, num_iterations=None, logdir=None, global_step=None, save_every=1000, log=print, resume=True):
+def train(num, engine, batches, num_iterations=None, logdir=None, global_step=None, save_every=1000, log=print, resume=True,
+          rank=0, world=1, allreduce=None):
     """train.py:137-160 for num = 1 (Text2Mel) or 2 (SSRN).  `batches` yields (L, mels, mags, names); `engine` is an
     `Engine` with parameters loaded.  Like tf.train.Supervisor (train.py:144), a `logdir` that already holds a checkpoint
     is RESUMED: variables, Adam slots and the global step come back from it (`resume=False` or an explicit `global_step`
-    starts over).  Returns the final global step."""
+    starts over).  Data parallel (BASELINE config 5, `world` > 1): every rank feeds its own disjoint `batches`, the step
+    runs with apply=False, `allreduce` (default dc_tts_b200.parallel.allreduce_mean_) averages the flat gradient arena,
+    every rank applies the identical Adam update, dropout masks differ per rank (seed = gs * world + rank) and only rank 0
+    writes checkpoints.  Returns the final global step."""
     if num not in (1, 2):
         raise ValueError("num: 1 for Text2Mel, 2 for SSRN (train.py:139)")
     num_iterations = hp.num_iterations if num_iterations is None else num_iterations
@@ -168,12 +173,22 @@ def train(num, engine, batches, num_iterations=None, logdir=None, global_step=No
                     gs = restored
                     log("resumed from %s at global step %d" % (logdir, gs))
             initialised = True
-        if num == 1:
+        if world > 1:
+            if allreduce is None:
+                from .parallel import allreduce_mean_ as allreduce
+            seed = gs * world + rank
+            if num == 1:
+                losses = engine.train_step(L, mels, global_step=gs, seed=seed, apply=False)
+            else:
+                losses = engine.train_step_ssrn(mels, mags, global_step=gs, seed=seed, apply=False)
+            allreduce(engine.train_grads())
+            engine.train_apply(gs)
+        elif num == 1:
             losses = engine.train_step(L, mels, global_step=gs, seed=gs)
         else:
             losses = engine.train_step_ssrn(mels, mags, global_step=gs, seed=gs)
         gs += 1                                   # apply_gradients(..., global_step=...) increments (train.py:131)
-        if gs % save_every == 0:                  # train.py:151-152
+        if gs % save_every == 0 and rank == 0:    # train.py:151-152
             engine.save_checkpoint(checkpoint_name(logdir, gs), gs, "Text2Mel" if num == 1 else "SSRN")
             log("step %d  %s" % (gs, "  ".join("%s %.4f" % kv for kv in sorted(losses.items()))))
         if gs > num_iterations:                   # train.py:160

@@ -98,3 +98,17 @@ def load_spectrograms(fpath):
     mag = np.pad(mag, [[0, num_paddings], [0, 0]], mode="constant")
     mel = mel[::hp.r, :]
     return fname, mel, mag
+
+
+def guided_attention(g=0.2):
+    """utils.py:134-140: W[n, t] = 1 - exp(-(t/max_T - n/max_N)^2 / (2 g^2)), shape (max_N, max_T) float32 (the device
+    training step builds the same table itself: dctts_train_init)."""
+    n = np.arange(hp.max_N, dtype=np.float64)[:, None] / float(hp.max_N)
+    t = np.arange(hp.max_T, dtype=np.float64)[None, :] / float(hp.max_T)
+    return (1.0 - np.exp(-(t - n) ** 2 / (2.0 * g * g))).astype(np.float32)
+
+
+def learning_rate_decay(init_lr, global_step, warmup_steps=4000.):
+    """utils.py:142-145, the Noam scheme: step = global_step + 1; lr * warmup^0.5 * min(step * warmup^-1.5, step^-0.5)."""
+    step = float(global_step + 1)
+    return float(init_lr) * warmup_steps ** 0.5 * min(step * warmup_steps ** -1.5, step ** -0.5)

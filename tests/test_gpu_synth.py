@@ -137,8 +137,8 @@ def test_graph_session_api(engine):
             assert np.abs(Y[:, :3] - g["Y"][:, :3]).max() < TOL
             Z = sess.run(gr.Z, {gr.Y: g["Y"]})
             assert np.abs(Z[:, ::8, ::8] - g["Z_sub"]).max() < TOL
-    with pytest.raises(NotImplementedError):
-        Graph(mode="train")
+    with pytest.raises(ValueError):
+        Graph(mode="train")                  # the training graph needs its input pipeline (tests/test_trainer.py, test_train.py)
 
 
 def test_synthesize_script(engine, tmp_path, monkeypatch):

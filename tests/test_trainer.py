@@ -12,6 +12,7 @@ from dc_tts_b200.hyperparams import Hyperparams as hp
 class FakeEngine:
     def __init__(self):
         self.calls, self.saved, self.init = [], [], None
+        self.applied, self.applies, self.grads = [], [], np.ones(4, np.float32)
 
     def train_init(self, B):
         self.init = ("t2m", B)
@@ -19,13 +20,21 @@ class FakeEngine:
     def train_init_ssrn(self, B, T):
         self.init = ("ssrn", B, T)
 
-    def train_step(self, L, mels, global_step=0, seed=0):
+    def train_step(self, L, mels, global_step=0, seed=0, apply=True):
         self.calls.append(("t2m", L.shape, mels.shape, global_step, seed))
+        self.applied.append(apply)
         return {"loss": 1.0, "loss_mels": 0.3, "loss_bd1": 0.69, "loss_att": 0.01}
 
-    def train_step_ssrn(self, mels, mags, global_step=0, seed=0):
+    def train_step_ssrn(self, mels, mags, global_step=0, seed=0, apply=True):
         self.calls.append(("ssrn", mels.shape, mags.shape, global_step, seed))
+        self.applied.append(apply)
         return {"loss": 1.0, "loss_mags": 0.3, "loss_bd2": 0.7}
+
+    def train_grads(self):
+        return self.grads
+
+    def train_apply(self, gs):
+        self.applies.append(gs)
 
     def save_checkpoint(self, prefix, gs, scope):
         self.saved.append((prefix, gs, scope))
@@ -161,3 +170,51 @@ def test_bucketed_batches_follow_the_reference_queue(tmp_path):
         seen += idx
     assert len(seen) >= 2 * n - 4 * (len(bounds) + 1)                                     # only partial buckets are left over
     assert max(np.bincount(seen)) <= 2                                                    # each utterance at most once per epoch
+
+
+def test_graph_train_surface(tmp_path):
+    """train.py:22-135 / :148: `Graph(num)` is the training object; `sess.run([g.global_step, g.train_op])` runs one
+    optimiser step on the next batch and returns the incremented step; the losses and the Noam rate are fetchable."""
+    from dc_tts_b200.train import Graph, Session
+    from dc_tts_b200.utils import guided_attention, learning_rate_decay
+    from oracle import ref_train as rtr
+    d, loader, _ = _dataset(tmp_path)
+    fpaths, _, texts = trainer.load_train_data(d)
+    for num in (1, 2):
+        eng = FakeEngine()
+        g = Graph(num=num, engine=eng, batches=trainer.fixed_size_batches(fpaths, texts, B=2, seed=0, loader=loader), global_step=3998)
+        with Session() as sess:
+            with pytest.raises(ValueError):
+                sess.run(g.loss)                                                     # nothing has run yet
+            gs, _ = sess.run([g.global_step, g.train_op])
+            assert gs == 3999 and eng.calls[-1][3] == 3998 and eng.calls[-1][0] == ("t2m" if num == 1 else "ssrn")
+            gs, _, loss, lr = sess.run([g.global_step, g.train_op, g.loss, g.lr])
+            assert gs == 4000 and loss == np.float32(1.0) and lr == np.float32(learning_rate_decay(hp.lr, 4000))
+            assert sess.run(g.loss_mels if num == 1 else g.loss_mags) == np.float32(0.3)
+        assert eng.init == (("t2m", 2) if num == 1 else ("ssrn", 2, hp.max_T))
+    with pytest.raises(ValueError):
+        Graph(num=3, engine=FakeEngine(), batches=[])
+    for gs in (0, 1, 3999, 4000, 123456):
+        assert learning_rate_decay(hp.lr, gs) == pytest.approx(rtr.learning_rate(gs), rel=1e-6)
+    np.testing.assert_allclose(guided_attention(), rtr.guided_attention(), rtol=0, atol=1e-7)
+
+
+def test_data_parallel_loop_wiring(tmp_path):
+    """BASELINE config 5 in the loop: disjoint per-rank batches, step without apply, all-reduce of the gradient arena,
+    identical apply, per-rank dropout seeds, checkpoints from rank 0 only."""
+    d, loader, _ = _dataset(tmp_path, n=11)
+    fpaths, _, texts = trainer.load_train_data(d)
+    names = []
+    for rank in (0, 1):
+        names.append([n for b in trainer.fixed_size_batches(fpaths, texts, B=2, seed=4, loader=loader, epochs=1, rank=rank, world=2) for n in b[3]])
+    assert names[0] and names[1] and not set(names[0]) & set(names[1])
+    reduced = []
+    for rank in (0, 1):
+        eng = FakeEngine()
+        gs = trainer.train(1, eng, trainer.fixed_size_batches(fpaths, texts, B=2, seed=4, loader=loader, rank=rank, world=2),
+                           num_iterations=1000, logdir=str(tmp_path / "dp"), global_step=998, save_every=1000, log=lambda *_: None,
+                           rank=rank, world=2, allreduce=lambda g: reduced.append(g.sum()))
+        assert gs == 1001 and eng.applied == [False] * 3 and eng.applies == [998, 999, 1000]
+        assert [c[4] for c in eng.calls] == [998 * 2 + rank, 999 * 2 + rank, 1000 * 2 + rank]
+        assert len(eng.saved) == (1 if rank == 0 else 0)
+    assert len(reduced) == 6
