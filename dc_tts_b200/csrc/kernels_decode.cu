@@ -66,7 +66,7 @@ struct Smem {
 };
 
 // lap timer (option decode_prof): thread 0 attributes the cycles since the previous lap to bucket i
-#define LAP(i) do { if (P.prof && threadIdx.x == 0) { const long long now_ = clock64(); S.prof[i] += now_ - S.prof_last; S.prof_last = now_; } } while (0)
+#define LAP(i) do { if constexpr (PROF) { if (threadIdx.x == 0) { const long long now_ = clock64(); S.prof[i] += now_ - S.prof_last; S.prof_last = now_; } } } while (0)
 enum { LP_START = 0, LP_WAIT = 1, LP_GEMV = 2, LP_RELEASE = 3, LP_GATHER = 4, LP_CBAR = 5, LP_LN = 6, LP_MIX = 7, LP_ATT = 8,
        LP_PYR_ATT = 9, LP_PYR_GEMM = 10, LP_PYR_LN = 11, LP_PYR_BAR = 12, LP_FRAME = 13 };
 
@@ -127,11 +127,8 @@ __device__ __forceinline__ void stream_advance(const DecParams& P, const Smem& S
 }
 // the calling warp has read its region of the current chunk: refill it with its rows of the chunk 3 ahead
 __device__ __forceinline__ void warp_release(const DecParams& P, Smem& S, Stream& st, int warp, int lane) {
-    __syncwarp();
-    if (lane == 0) {
-        fence_proxy_async_smem();                                     // generic reads before the async-proxy overwrite
-        stream_issue(P, S, st, st.prod, (int)(st.pos % DEC_NSLOT), warp);
-    }
+    __syncwarp();                                                     // every lane's loads of the region have returned (their FMAs have issued)
+    if (lane == 0) stream_issue(P, S, st, st.prod, (int)(st.pos % DEC_NSLOT), warp);
     stream_advance(P, S, st);
 }
 
@@ -141,41 +138,46 @@ __device__ __forceinline__ void prefetch_params(const DecParams& P, Smem& S, int
     float* dst = S.prm[li & 1];
     const int tid = threadIdx.x;
     cp_async16(dst + tid * 4, P.lnp[li] + tid * 4, true);                        // 1024 floats
-    if (tid < l.ns / 4 && (l.cs & 3) == 0) {                                      // bias slice in stream column order
-        const int n = tid * 4;
-        const float* src = (l.kind == 1 && n >= l.cs) ? P.bias[li] + l.cout + rank * l.cs + (n - l.cs) : P.bias[li] + rank * l.cs + n;
-        cp_async16(dst + 1024 + n, src, true);
+    if (tid < l.ns) {                                                             // bias slice in stream column order
+        // hc: columns [0,cs) gate of channels rank*cs.., [cs,2cs) info; conv: [0,cs), zero beyond
+        const int n = tid;
+        float bv = 0.f;
+        if (l.kind == 1) bv = __ldg(P.bias[li] + (n < l.cs ? rank * l.cs + n : l.cout + rank * l.cs + (n - l.cs)));
+        else if (n < l.cs) bv = __ldg(P.bias[li] + rank * l.cs + n);
+        dst[1024 + n] = bv;
     }
 }
 // taps (all but the last) of block li at frame j: rows j - (ntaps-1-tap)*rate of its input history -> xin[buf][g][tap*256..]
+// (multi-tap blocks have 256 input channels and 3 taps: pack_decode checks it)
 __device__ __forceinline__ void prefetch_taps(const DecParams& P, Smem& S, int li, int j, int b0, int G, int buf) {
     const DecLayer& l = P.L[li];
-    const int ntap_ld = l.ntaps - 1;
-    if (ntap_ld <= 0 || !P.in_hist[li]) return;
-    const int per_row = l.cin / 4;
-    const int total = G * ntap_ld * per_row;
-    for (int i = threadIdx.x; i < total; i += NT) {
-        const int c4 = i % per_row, rt = i / per_row, tap = rt % ntap_ld, g = rt / ntap_ld;
-        const int t = j - (l.ntaps - 1 - tap) * l.rate;
-        const float* src = P.in_hist[li] + ((size_t)(b0 + g) * P.T + (t < 0 ? 0 : t)) * l.ldin + c4 * 4;
+    if (l.ntaps != 3 || !P.in_hist[li]) return;
+    for (int i = threadIdx.x; i < G * 128; i += NT) {
+        const int c4 = i & 63, tap = (i >> 6) & 1, g = i >> 7;
+        const int t = j - (2 - tap) * l.rate;
+        const float* src = P.in_hist[li] + ((size_t)(b0 + g) * P.T + (t < 0 ? 0 : t)) * 256 + c4 * 4;
         cp_async16(&S.xin[buf][g][tap * 256 + c4 * 4], src, t >= 0);
     }
 }
 
 // ---- GEMV of the calling warp's k rows of one chunk: acc[g] += sum_k x[g][k] * W[k][n] ----------------------
-// wreg: the warp's region ([k/4][column][4]); x: row 0 of the input vectors at the warp's first k; NS columns per CTA
-template <int NS>
-__device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const float* __restrict__ x, int xld, int kr8, int G,
+// wreg: the warp's region ([k/4][column][4]); x: row 0 of the input vectors at the warp's first k; ns = 32 / 16 / 8 columns
+// per CTA.  ONE runtime-generic body on purpose: the per-frame loop has to fit the instruction cache (round 1 and the first
+// version of this kernel were instruction-fetch bound at ~11k SASS lines).
+__device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const float* __restrict__ x, int xld, int kr8, int ns, int G,
                                           float (&acc)[GMAX]) {
-    constexpr int SG = 32 / NS;                                      // k sub-groups inside the warp
-    const int lane = threadIdx.x & 31, n = lane % NS, sg = lane / NS;
-    const int kper = kr8 / SG;                                       // multiple of 8
-    const float* w = wreg + ((size_t)(sg * kper / 4) * NS + n) * 4;
+    const int lane = threadIdx.x & 31;
+    const int lg = (ns == 32) ? 5 : (ns == 16 ? 4 : 3);
+    const int n = lane & (ns - 1), sg = lane >> lg;                  // column, k sub-group inside the warp
+    const int kper = kr8 >> (5 - lg);                                // k rows per sub-group, multiple of 8
+    const float* w = wreg + ((size_t)((sg * kper) >> 2) * ns + n) * 4;
     const float* xs = x + sg * kper;
-#pragma unroll 2
+    const int wstep = ns * 4;
+#pragma unroll 1
     for (int k = 0; k < kper; k += 8) {
-        const float4 w0 = *reinterpret_cast<const float4*>(w + (size_t)(k >> 2) * NS * 4);
-        const float4 w1 = *reinterpret_cast<const float4*>(w + (size_t)((k >> 2) + 1) * NS * 4);
+        const float4 w0 = *reinterpret_cast<const float4*>(w);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + wstep);
+        w += 2 * wstep;
 #pragma unroll
         for (int g = 0; g < GMAX; ++g) {
             if (g < G) {
@@ -188,11 +190,6 @@ __device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const 
             }
         }
     }
-}
-__device__ __forceinline__ void gemv_dispatch(int ns, const float* wreg, const float* x, int xld, int kr8, int G, float (&acc)[GMAX]) {
-    if (ns == 32) gemv_warp<32>(wreg, x, xld, kr8, G, acc);
-    else if (ns == 16) gemv_warp<16>(wreg, x, xld, kr8, G, acc);
-    else gemv_warp<8>(wreg, x, xld, kr8, G, acc);
 }
 
 // global column of stream column n of rank r (hc: gate | info halves of the 2*cout pre-LN row)
@@ -228,7 +225,8 @@ __device__ __forceinline__ void ln_row(float (&v)[8], int C, int lane, const flo
 // ---- one block on ONE row per utterance -------------------------------------------------------------------
 // in: S.xin[cb][g] = [taps | current row] of the block's input, S.prm[li&1] = its parameters (both prefetched).
 // out: S.xin[cb^1][g][next_off ..] = the block's output row; this CTA's channel slice appended to the output history.
-__device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j, int b0, int G, int rank, int cb, unsigned& lcount) {
+template <bool PROF>
+__device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j, int b0, int G, int rank, int cb, unsigned& lcount) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool last = (li + 1 == P.nl);
@@ -258,7 +256,7 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
         mbar_wait(bar64(&S.fullw[slot][warp]), (st.pos / DEC_NSLOT) & 1u);
         LAP(LP_WAIT);
         const int kr8 = ch.krows >> 3;
-        gemv_dispatch(l.ns, &S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], XLD, kr8, G, acc);
+        gemv_warp(&S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], XLD, kr8, l.ns, G, acc);
         LAP(LP_GEMV);
         warp_release(P, S, st, warp, lane);
         LAP(LP_RELEASE);
@@ -267,18 +265,19 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
     for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
     __syncthreads();
     // warp 0: final sums of the slice -> staging -> one bulk copy per peer (all-gather through distributed shared memory)
+    const int lgns = (l.ns == 32) ? 5 : (l.ns == 16 ? 4 : 3);
     if (warp == 0) {
-        const int nvals = G * l.ns, ng = NT / l.ns;
+        const int nvals = G << lgns, ng = NT >> lgns;
         float* ov = S.outv[pb];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int idx = lane + 32 * i;
-            if (idx < nvals) {
-                const int g = idx / l.ns, n = idx % l.ns;
-                float s = bias_smem_or_global(P, S.prm[li & 1], li, rank, n);
-                for (int q = 0; q < ng; ++q) s += S.red[g][q * l.ns + n];
-                ov[idx] = s;
-            }
+        const float* bs = S.prm[li & 1] + 1024;
+#pragma unroll 1
+        for (int idx = lane; idx < nvals; idx += 32) {
+            const int g = idx >> lgns, n = idx & (l.ns - 1);
+            const float* rp = &S.red[g][n];
+            float s = bs[n];
+#pragma unroll 4
+            for (int q = 0; q < ng; ++q) s += rp[q << lgns];
+            ov[idx] = s;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -288,48 +287,56 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
     LAP(LP_GATHER);
     mbar_wait(bar64(&S.gbar[pb]), gpar);
     LAP(LP_CBAR);
-    // one warp per utterance: both LayerNorms, gate, highway mix in registers (redundantly in every CTA)
+    // one warp per utterance: both LayerNorms, gate, highway mix (redundantly in every CTA).  Two passes over the gathered row in
+    // shared memory (statistics, then normalise + mix) with rolled loops: small code, no register arrays.
     if (warp < G) {
         const int g = warp, C = l.cout, cs = l.cs;
+        const bool hcb = l.kind == 1;
         const float* prm = S.prm[li & 1];
-        const float* pr = &S.pre[pb][0][g * l.ns];
-        float v1[8], v2[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = lane + 32 * i;
-            const int rk = (cs == 16) ? (c >> 4) : c / cs, wi = (cs == 16) ? (c & 15) : c % cs;
-            v1[i] = (c < C) ? pr[rk * PLD + wi] : 0.f;
-            v2[i] = (c < C && l.kind == 1) ? pr[rk * PLD + cs + wi] : 0.f;
+        const float* pr = &S.pre[pb][0][g << lgns];
+        // channel c lives in the slice of rank c / cs at column c % cs (cs = 16, or 5 for the n_mels-wide last block)
+        auto pre_off = [&](int c) { const int rk = (cs == 16) ? (c >> 4) : ((c * 205) >> 10); return rk * PLD + (c - rk * cs); };
+        const float piv1 = pr[0], piv2 = hcb ? pr[cs] : 0.f;         // pivots: channel 0 of each half (constant row -> exact zeros, quirk Q4)
+        float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
+#pragma unroll 2
+        for (int c = lane; c < C; c += 32) {
+            const int o = pre_off(c);
+            const float a = pr[o] - piv1, b = hcb ? pr[o + cs] - piv2 : 0.f;
+            s1 += a; q1 = fmaf(a, a, q1); s2 += b; q2 = fmaf(b, b, q2);
         }
-        ln_row(v1, C, lane, prm, prm + 256);
-        if (l.kind == 1) ln_row(v2, C, lane, prm + 512, prm + 768);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+        }
+        const float fC = (float)C;
+        const float m1 = s1 / fC, m2 = s2 / fC;
+        const float inv1 = 1.0f / sqrtf(fmaxf(q1 / fC - m1 * m1, 0.f) + 1e-12f);
+        const float inv2 = 1.0f / sqrtf(fmaxf(q2 / fC - m2 * m2, 0.f) + 1e-12f);
         LAP(LP_LN);
         const int cur_off = (l.ntaps - 1) * 256;
         const int next_off = (last || li + 1 == P.n_enc) ? 0 : (P.L[li + 1].ntaps - 1) * 256;
         const size_t row = (size_t)(b0 + g) * P.T + j;
         float* oh = P.out_hist[li];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = lane + 32 * i;
-            if (c < C) {
-                float o;
-                if (l.kind == 1) {
-                    const float h1 = sigmoid_acc(v1[i]);
-                    o = h1 * v2[i] + (1.0f - h1) * S.xin[cb][g][cur_off + c];
-                } else {
-                    o = v1[i];
-                    if (l.act == 1) o = fmaxf(o, 0.f);
-                }
-                const int rk = (cs == 16) ? (c >> 4) : c / cs;
-                if (rk == rank && oh) oh[row * C + c] = o;           // this CTA's slice of the history row
-                if (last) {                                           // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
-                    o = sigmoid_acc(o);
-                    if (rank == 0) P.ybuf[row * C + c] = o;
-                }
-                S.xin[cb ^ 1][g][next_off + c] = o;
+        const float* xres = &S.xin[cb][g][cur_off];
+        float* xout = &S.xin[cb ^ 1][g][next_off];
+#pragma unroll 2
+        for (int c = lane; c < C; c += 32) {
+            const int po = pre_off(c);
+            float o = (pr[po] - piv1 - m1) * inv1 * prm[c] + prm[256 + c];
+            if (hcb) {
+                const float h2 = (pr[po + cs] - piv2 - m2) * inv2 * prm[512 + c] + prm[768 + c];
+                const float h1 = sigmoid_acc(o);
+                o = h1 * h2 + (1.0f - h1) * xres[c];
+            } else if (l.act == 1) o = fmaxf(o, 0.f);
+            if (po / PLD == rank && oh) oh[row * C + c] = o;         // this CTA's slice of the history row
+            if (last) {                                               // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
+                o = sigmoid_acc(o);
+                if (rank == 0) P.ybuf[row * C + c] = o;
             }
+            xout[c] = o;
         }
-        if (last) for (int c = C + lane; c < 128; c += 32) S.xin[cb ^ 1][g][c] = 0.f;   // AudioEnc C_1 reads K = 128 padded channels
+        if (last) for (int c = C + lane; c < 128; c += 32) xout[c] = 0.f;   // AudioEnc C_1 reads K = 128 padded channels
     } else {
         LAP(LP_LN);
     }
@@ -340,7 +347,7 @@ __device__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j,
 
 // ---- attention of ONE query row under the 3-key window (networks.py:140-153) -------------------------------
 // lane holds q[lane*8 .. +8); returns ctx[8] in the same layout and the argmax key (first index among equal maxima)
-__device__ __forceinline__ int attend_row(const DecParams& P, const float (&qv)[8], int b, int p, int lane, float (&ctx)[8]) {
+__device__ __noinline__ int attend_row(const DecParams& P, const float (&qv)[8], int b, int p, int lane, float (&ctx)[8]) {
     const int d = P.d;
     const int n_lo = min(max(p, 0), P.N - 1), n_hi = min(n_lo + P.win_size, P.N);
     const float scale = rsqrtf((float)d);
@@ -412,7 +419,7 @@ __device__ __forceinline__ const float* w_quad(const Smem& S, const DecLayer& l,
 // register-tiled fp32 GEMM of ONE utterance: rows {rg, rg+32, rg+64} x TN columns {q, q+8, ..} per thread; the source rows
 // of a 16-channel slab are staged once (cp.async, 3 stages) and used for every tap
 template <int TN>
-__device__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
+__device__ __noinline__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
     constexpr int NS = 8 * TN;
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, q = tid & 7, rg = tid >> 3;
@@ -482,7 +489,7 @@ __device__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0,
 }
 
 // <= 4 rows of one utterance: the GEMV path with the rows in the role of the utterances
-__device__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
+__device__ __noinline__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5;
     float* xs = S.wrk;                                                // [m][tap*cin + c], pitch 768
@@ -500,7 +507,7 @@ __device__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0
     for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
     const int kr8 = l.krows >> 3;
     for (int c = 0; c * l.krows < K; ++c)
-        gemv_dispatch(l.ns, &S.ring[(pos0 + c) % DEC_NSLOT][warp][0], xs + c * l.krows + warp * kr8, 768, kr8, n_out, acc);
+        gemv_warp(&S.ring[(pos0 + c) % DEC_NSLOT][warp][0], xs + c * l.krows + warp * kr8, 768, kr8, l.ns, n_out, acc);
 #pragma unroll
     for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
     __syncthreads();
@@ -515,7 +522,7 @@ __device__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0
 }
 
 // LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
-__device__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRows& rl, int rank, const float* scr) {
+__device__ __noinline__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRows& rl, int rank, const float* scr) {
     const DecLayer& l = P.L[li];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* prm = &S.red[0][0];
@@ -561,6 +568,7 @@ __device__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRow
 
 }  // namespace
 
+template <bool PROF>
 __global__ void __cluster_dims__(DEC_NC, 1, 1) __launch_bounds__(DEC_THREADS, 1)
 decode_cluster_kernel(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -611,11 +619,11 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
         const bool any_moved = S.fmoved[j & 1] != 0;
         if (rank == 0 && tid < G) P.p_hist[(size_t)(b0 + tid) * P.T + j] = S.p_cur[tid];
 
-        // AudioEnc (networks.py:81-124): input Y[j-1] (train.py:51), already in xin[cb]
-        for (int li = 0; li < P.n_enc; ++li) cb = layer_row(P, S, st, li, j, b0, G, rank, cb, lcount);
-
+        // AudioEnc (networks.py:81-124; input Y[j-1], train.py:51, already in xin[cb]), Attention, AudioDec (networks.py:166-212):
+        // ONE copy of the block body in the instruction stream -- the per-frame loop has to stay inside the instruction cache
+        for (int li = 0; li < P.nl; ++li) {
+        if (li == P.n_enc) {
         // Attention of row j under the current window, redundantly in every CTA: R[j] = [A.V ; Q] (networks.py:140-153)
-        __syncthreads();
         if (warp < G) {
             const int g = warp;
             float qv[8], ctx[8];
@@ -650,8 +658,8 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
             }
             cluster_sync_all();
             LAP(LP_PYR_ATT);
-            for (int li = P.n_enc; li < P.nl && P.L[li].prow > 1; ++li) {
-                const DecLayer& l = P.L[li];
+            for (int lp = P.n_enc; lp < P.nl && P.L[lp].prow > 1; ++lp) {
+                const DecLayer& l = P.L[lp];
                 // every warp waits for ALL regions of the block's chunks (lane w watches region w)
                 for (int c = 0; c < l.nch; ++c) {
                     const unsigned pp = st.pos + c;
@@ -662,9 +670,9 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
                 for (int g = 0; g < G; ++g) {
                     if (rl.n[g] <= 0) continue;
                     float* rows = scr + (size_t)rl.off[g] * 512;
-                    if (rl.n[g] <= GMAX) pyr_small_utt(P, S, li, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
-                    else if (l.ns == 32) pyr_gemm_utt<4>(P, S, li, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
-                    else pyr_gemm_utt<2>(P, S, li, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                    if (rl.n[g] <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                    else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                    else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
                 }
                 __syncthreads();                          // every warp is done with every region of these chunks
                 for (int c = 0; c < l.nch; ++c) {
@@ -672,18 +680,19 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
                     stream_advance(P, S, st);
                 }
                 for (int i = tid; i < 256; i += NT)       // this block's LayerNorm parameters for pyr_ln
-                    *reinterpret_cast<float4*>(&S.red[0][0] + i * 4) = __ldg(reinterpret_cast<const float4*>(P.lnp[li]) + i);
+                    *reinterpret_cast<float4*>(&S.red[0][0] + i * 4) = __ldg(reinterpret_cast<const float4*>(P.lnp[lp]) + i);
                 LAP(LP_PYR_GEMM);
                 cluster_sync_all();
                 LAP(LP_PYR_BAR);
-                pyr_ln(P, S, li, b0, rl, rank, scr);
+                pyr_ln(P, S, lp, b0, rl, rank, scr);
                 LAP(LP_PYR_LN);
                 cluster_sync_all();
                 LAP(LP_PYR_BAR);
             }
         }
-        // AudioDec (networks.py:166-212), one row per utterance
-        for (int li = P.n_enc; li < P.nl; ++li) cb = layer_row(P, S, st, li, j, b0, G, rank, cb, lcount);
+        }   // li == n_enc
+        cb = layer_row<PROF>(P, S, st, li, j, b0, G, rank, cb, lcount);
+        }   // blocks
 
         __syncthreads();
         if (tid < GMAX) { S.p_prev[tid] = S.p_cur[tid]; S.p_cur[tid] = S.p_next[tid]; }
@@ -692,7 +701,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
     }
     if (rank == 0 && tid < G) P.p_final[b0 + tid] = S.p_cur[tid];
     if (rank == 0 && tid == 0 && P.stats) { P.stats[2 * cluster] = n_moved_frames; P.stats[2 * cluster + 1] = n_moved_utt; }
-    if (P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
+    if (PROF && P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
     cp_async_wait<0>();
     cluster_sync_all();                                   // no CTA exits while a peer may still write into its shared memory
 }
@@ -700,9 +709,14 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
 size_t decode_smem_bytes() { return sizeof(Smem) + 128; }
 
 static cudaError_t decode_prepare() {
-    cudaError_t e = cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes());
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(decode_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e = cudaSuccess;
+    for (auto* k : {decode_cluster_kernel<false>, decode_cluster_kernel<true>}) {
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes());
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return e;
+    }
+    return e;
 }
 
 int decode_max_active_clusters() {
@@ -713,7 +727,7 @@ int decode_max_active_clusters() {
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = DEC_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
@@ -723,7 +737,7 @@ cudaError_t launch_decode_cluster(const DecParams& p, int n_clusters, cudaStream
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_clusters * DEC_NC); cfg.blockDim = dim3(DEC_THREADS); cfg.dynamicSmemBytes = decode_smem_bytes(); cfg.stream = s;
     cfg.attrs = nullptr; cfg.numAttrs = 0;               // cluster dims are compiled in (__cluster_dims__)
-    return cudaLaunchKernelEx(&cfg, decode_cluster_kernel, p);
+    return p.prof ? cudaLaunchKernelEx(&cfg, decode_cluster_kernel<true>, p) : cudaLaunchKernelEx(&cfg, decode_cluster_kernel<false>, p);
 }
 
 }  // namespace dctts
