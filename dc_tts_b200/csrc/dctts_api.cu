@@ -167,6 +167,7 @@ struct dctts_handle_s {
         int tc_resid_tma = 1;     // hc: residual in / planes out through TMA
         int tc_debug = 0;         // progress markers + in-kernel cycle stamps (synchronising)
         int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
+        int decode_prepass = 0;   // persistent decode, receptive-field pre-pass: 0 = fp32 FMA GEMM, 1 = tcgen05 split-fp16 (3 MMAs)
         int decode_prof = 0;      // persistent decode: record SM-clock lap timers of cluster 0 / rank 0 (dctts_decode_profile)
         int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
     } opt;
@@ -448,14 +449,36 @@ void pack_decode(H* h) {
     if (P.L[P.nl - 1].prow != 1 || P.L[P.n_enc].ntaps != 1 || P.nch_enc <= DEC_NSLOT) { D.why = "persistent decode: unexpected AudioDec shape"; return; }
     for (int li = P.n_enc; li < P.nl; ++li)                        // the receptive-field blocks must be a prefix of AudioDec
         if (P.L[li].prow > 1 && li > P.n_enc && P.L[li - 1].prow <= 1) { D.why = "persistent decode: receptive-field blocks not contiguous"; return; }
-    P.nch = nch; P.stream_len = off;
+    P.nch = nch;
+    // the receptive-field blocks a second time, as split-fp16 MMA slabs (tcgen05 pre-pass): same chunk sizes, appended
+    for (int li = 0; li < P.nl; ++li) {
+        const DecLayer& L = P.L[li];
+        if (L.prow <= 1) continue;
+        if (L.krows % 128 || (L.ns != 32 && L.ns != 16)) { D.why = "persistent decode: tcgen05 pre-pass geometry"; return; }
+        for (int c = L.ch0; c < L.ch0 + L.nch; ++c) { P.C[c].off16 = off; off += L.krows * L.ns; }
+    }
+    P.stream_len = off;
     // streams: chunk = 8 warp regions, region w = rows [w*kr8, (w+1)*kr8) as [k/4][column][4]
     std::vector<float> st((size_t)DEC_NC * off, 0.f);
+    for (int li = 0; li < P.nl; ++li) {                              // power-of-two scale per receptive-field block (as pack_tc)
+        const LayerDev& l = *nets[li]; const DecLayer& L = P.L[li];
+        P.inv_scale[li] = 1.f;
+        if (L.prow <= 1) continue;
+        float maxabs = 0.f;
+        for (size_t i = 0; i < l.hostW.size(); ++i) maxabs = std::max(maxabs, std::fabs(l.hostW[i]));
+        float scale = 1.f;
+        if (maxabs > 0.f) { int e; std::frexp(maxabs, &e); scale = std::ldexp(1.f, 11 - e); }
+        P.inv_scale[li] = 1.f / scale;
+    }
     for (int r = 0; r < DEC_NC; ++r)
         for (int li = 0; li < P.nl; ++li) {
             const LayerDev& l = *nets[li]; const DecLayer& L = P.L[li];
             REQUIRE(!l.hostW.empty(), "persistent decode: host weights missing");
             const int cinp = roundup(l.cin, 128), kr8 = L.krows / 8;
+            auto column = [&](int n) -> int {
+                if (L.kind) return n < L.cs ? r * L.cs + n : l.cout + r * L.cs + (n - L.cs);
+                return n < L.cs ? r * L.cs + n : -1;
+            };
             for (int c = L.ch0; c < L.ch0 + L.nch; ++c) {
                 const DecChunk& ch = P.C[c];
                 float* dst = st.data() + (size_t)r * off + ch.off;
@@ -465,10 +488,28 @@ void pack_decode(H* h) {
                     const int w = kc / kr8, kk = kc % kr8;
                     const float* wrow = l.hostW.data() + ((size_t)tap * l.cin + ci) * l.ldw;
                     for (int n = 0; n < L.ns; ++n) {
-                        int col;
-                        if (L.kind) col = n < L.cs ? r * L.cs + n : l.cout + r * L.cs + (n - L.cs);
-                        else { if (n >= L.cs) continue; col = r * L.cs + n; }
+                        const int col = column(n);
+                        if (col < 0) continue;
                         dst[(size_t)w * kr8 * L.ns + ((size_t)(kk / 4) * L.ns + n) * 4 + (kk % 4)] = wrow[col];
+                    }
+                }
+                if (L.prow <= 1) continue;
+                // the same rows as MMA slabs of 16 k: [plane hi | lo][k8 group][column][8 halfs], 16*ns floats per slab, in k order
+                // (slab s of the chunk sits at float offset s*16*ns: region w of the chunk = slabs [w*spr, (w+1)*spr))
+                __half* d16 = reinterpret_cast<__half*>(st.data() + (size_t)r * off + ch.off16);
+                const float scale = 1.f / P.inv_scale[li];
+                for (int kc = 0; kc < ch.krows; ++kc) {
+                    const int k = ch.k0 + kc, tap = k / cinp, ci = k % cinp;
+                    const int slab = kc / 16, k16 = kc % 16, grp = k16 / 8, e8 = k16 % 8;
+                    const float* wrow = l.hostW.data() + ((size_t)tap * l.cin + ci) * l.ldw;
+                    for (int n = 0; n < L.ns; ++n) {
+                        const int col = column(n);
+                        const float v = (col >= 0 && ci < l.cin) ? wrow[col] * scale : 0.f;
+                        const __half hv = __float2half_rn(v);
+                        const size_t base = (size_t)slab * 32 * L.ns;                  // halfs per slab = 2 planes * 2 groups * ns * 8
+                        const size_t idx = ((size_t)grp * L.ns + n) * 8 + e8;
+                        d16[base + idx] = hv;
+                        d16[base + (size_t)2 * L.ns * 8 + idx] = __float2half_rn(v - __half2float(hv));
                     }
                 }
             }
@@ -970,6 +1011,7 @@ bool decode_cluster(H* h, int B, int steps, cudaStream_t s) {
     if (h->opt.decode_prof) { D.prof.ensure(16 * sizeof(long long)); CUDA_CHECK(cudaMemsetAsync(D.prof.p, 0, 16 * sizeof(long long), s)); P.prof = D.prof.as<long long>(); }
     P.B = B; P.G = std::min(DEC_GMAX, (B + 7) / 8); P.T = hp.max_T; P.N = hp.max_N; P.d = hp.d; P.n_mels = hp.n_mels;
     P.win_size = hp.attention_win_size; P.steps = steps;
+    P.tc_pre = h->opt.decode_prepass ? 1 : 0;
     const int n_clusters = (B + P.G - 1) / P.G;
     cudaError_t e = launch_decode_cluster(P, n_clusters, s);
     if (e != cudaSuccess) throw std::runtime_error(std::string("decode_cluster_kernel launch failed: ") + cudaGetErrorString(e));
@@ -1944,6 +1986,7 @@ static int* option_slot(dctts_handle h, const char* name) {
     if (n == "fused_ln") return &h->opt.fused_ln;
     if (n == "decode_mode") return &h->opt.decode_mode;
     if (n == "decode_prof") return &h->opt.decode_prof;
+    if (n == "decode_prepass") return &h->opt.decode_prepass;
     return nullptr;
 }
 

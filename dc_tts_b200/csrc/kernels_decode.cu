@@ -36,6 +36,7 @@
 #include "kernels_decode.cuh"
 #include "tc_ptx.cuh"
 
+#include <cuda_fp16.h>
 #include <math.h>
 
 namespace dctts {
@@ -52,14 +53,16 @@ static_assert(WRK_F >= 4 * 768, "work buffer too small for the few-row inputs");
 
 struct Smem {
     float ring[DEC_NSLOT][NWARP][DEC_REG_F];
+    float wrk[WRK_F];                   // directly after the ring: the tcgen05 pre-pass reads up to 128 + 54 rows past a slab start
     float xin[2][GMAX][XLD];
     float pre[2][NC][PLD];
     float outv[2][GMAX * 32];
     float red[GMAX][NT];
     float prm[2][DEC_PRM_F];
-    float wrk[WRK_F];
     unsigned long long fullw[DEC_NSLOT][NWARP];
     unsigned long long gbar[2];
+    unsigned long long sbar[3], dbar;   // tcgen05 pre-pass: slab stage free / accumulator complete
+    uint32_t tmem_base, pad_;
     int p_cur[GMAX], p_prev[GMAX], p_next[GMAX], moved[GMAX];
     int fmoved[2];
     long long prof[16], prof_last;
@@ -120,7 +123,8 @@ __device__ __forceinline__ void stream_issue(const DecParams& P, Smem& S, const 
     const DecChunk& ch = P.C[u.c];
     const uint32_t bytes = (uint32_t)ch.nfl4 * 2u;                   // nfl * 4 bytes / 8 warps
     mbar_expect_tx(bar64(&S.fullw[slot][warp]), bytes);
-    bulk_g2s(&S.ring[slot][warp][0], st.base + ch.off + warp * (ch.nfl4 >> 1), bytes, &S.fullw[slot][warp]);
+    const int off = (u.seg == 1 && P.tc_pre) ? ch.off16 : ch.off;    // pre-pass on tensor cores: the same rows as split-fp16 MMA slabs
+    bulk_g2s(&S.ring[slot][warp][0], st.base + off + warp * (ch.nfl4 >> 1), bytes, &S.fullw[slot][warp]);
 }
 __device__ __forceinline__ void stream_advance(const DecParams& P, const Smem& S, Stream& st) {
     cur_next(P, S, st.cons); cur_next(P, S, st.prod); st.pos++;
@@ -521,6 +525,123 @@ __device__ __noinline__ void pyr_small_utt(const DecParams& P, Smem& S, int li, 
     __syncthreads();                                                  // red / xs are free for the next utterance
 }
 
+// ---- the same GEMM on the 5th-generation tensor cores (option decode_prepass = 1) --------------------------------------
+// One utterance, <= 96 source rows.  A = the source rows as split-fp16 planes (hi = fp16(x), lo = fp16(x - hi)), staged per
+// 16-channel slab in the NO-SWIZZLE K-major core-matrix layout [k8][row][8 halfs]: rows are consecutive 16-byte chunks, so
+// the three taps of the dilated conv are the SAME slab read through descriptors whose start address is shifted by
+// tap * rate rows -- staged once, multiplied three times.  B = this CTA's weight columns, pre-packed in the same layout
+// ([plane][k8][column][8 halfs], 2 KB per 16-k slab) and streamed through the ring like the fp32 weights.  D = 128 x ns fp32
+// in tensor memory; per slab and tap hi*Whi + hi*Wlo + lo*Whi (the dropped lo*lo term is 2^-22 relative).
+struct TcUse { unsigned s[3]; unsigned d; };
+__device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;               // between the two 8-wide k groups of one MMA
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;               // between 8-row groups
+    d |= 1ull << 46;                                                // descriptor version (sm_100); layout type 0 = no swizzle
+    return d;
+}
+constexpr int TC_RA = 96;                                           // rows per k8 group of an A slab plane
+constexpr int TC_APLANE = 2 * TC_RA * 16;                           // bytes of one plane of one slab (2 k8 groups)
+constexpr int TC_ASTAGE = 2 * TC_APLANE;                            // hi + lo
+static_assert(3 * TC_ASTAGE <= WRK_F * 4, "A slab stages do not fit the work buffer");
+
+__device__ __noinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank,
+                                        float* scr_rows, TcUse& use) {
+    const DecLayer& l = P.L[li];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int halo = (l.ntaps - 1) * l.rate, n_src = n_out + halo;   // <= 96
+    const int nslab = l.cin / 16, ns = l.ns;
+    const int spc = l.krows / 16, spr = spc / 8;                     // weight slabs per chunk / per warp region
+    const int slab_f = 16 * ns;                                      // floats per weight slab (2 planes x 2 k8 x ns x 16 B)
+    const float* in = P.in_hist[li];
+    unsigned char* As = reinterpret_cast<unsigned char*>(S.wrk);
+    const bool loader = tid < 2 * n_src;
+    const int s_row = tid >> 1, h8 = tid & 1;
+    const int t_src = t_lo - halo + s_row;
+    const float* src = in + ((size_t)b * P.T + (t_src < 0 ? 0 : t_src)) * l.ldin + h8 * 8;
+    const bool have = loader && t_src >= 0;
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    if (have) { r0 = ldcg4(src); r1 = ldcg4(src + 4); }
+    const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ns);
+    const uint32_t tacc = S.tmem_base;
+    for (int ks = 0; ks < nslab; ++ks) {
+        const int stg = ks % 3;
+        if (use.s[stg] > 0) mbar_wait(bar64(&S.sbar[stg]), (use.s[stg] - 1) & 1u);   // the MMAs that read this stage are done
+        if (loader) {
+            const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            __align__(16) __half hi[8];
+            __align__(16) __half lo[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { hi[i] = __float2half_rn(v[i]); lo[i] = __float2half_rn(v[i] - __half2float(hi[i])); }
+            unsigned char* dst = As + stg * TC_ASTAGE + h8 * (TC_RA * 16) + s_row * 16;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(dst + TC_APLANE) = *reinterpret_cast<const uint4*>(lo);
+        }
+        if (have && ks + 1 < nslab) { r0 = ldcg4(src + (ks + 1) * 16); r1 = ldcg4(src + (ks + 1) * 16 + 4); }
+        fence_proxy_async_smem();                                     // generic-proxy stores -> visible to the tensor core's reads
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 32) {
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(As + stg * TC_ASTAGE);
+            for (int tap = 0; tap < l.ntaps; ++tap) {
+                const uint32_t aa = a0 + (uint32_t)(tap * l.rate * 16);
+                const uint64_t dAh = umma_desc_noswz(aa, TC_RA * 16, 128), dAl = umma_desc_noswz(aa + TC_APLANE, TC_RA * 16, 128);
+                const int sid = tap * nslab + ks;                     // weight slab of (tap, channels ks*16..)
+                const int c = sid / spc, wi = sid - c * spc, reg = wi / spr, jj = wi - reg * spr;
+                const uint32_t bb = smem_u32(&S.ring[(pos0 + c) % DEC_NSLOT][reg][jj * slab_f]);
+                const uint64_t dBh = umma_desc_noswz(bb, (uint32_t)ns * 16, 128), dBl = umma_desc_noswz(bb + (uint32_t)ns * 32, (uint32_t)ns * 16, 128);
+                tc_mma_f16(tacc, dAh, dBh, idesc, (ks | tap) != 0);
+                tc_mma_f16(tacc, dAh, dBl, idesc, 1u);
+                tc_mma_f16(tacc, dAl, dBh, idesc, 1u);
+            }
+            tc_commit(bar64(&S.sbar[stg]));                           // the stage may be overwritten once these MMAs have read it
+            if (ks == nslab - 1) tc_commit(bar64(&S.dbar));           // accumulator complete
+        }
+        use.s[stg]++;
+    }
+    // epilogue: thread == output row (TMEM lane); pre-LN slice (+ bias) -> scratch
+    if (warp < 4) {
+        mbar_wait(bar64(&S.dbar), use.d & 1u);
+        tc_fence_after();
+        const int m = tid;
+        const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
+        const float inv = P.inv_scale[li];
+        float v[32];
+        if (ns == 32) { tmem_ld32_nowait(taddr, v); tmem_ld_wait(); }
+        else { float w16[16]; tmem_ld16(taddr, w16);
+#pragma unroll
+               for (int i = 0; i < 16; ++i) v[i] = w16[i]; }
+        if (m < n_out) {
+            float* orow = scr_rows + (size_t)m * 512;
+            const float* bs = P.bias[li];
+            if (l.kind == 1) {                                        // columns [0,16) gate, [16,32) info of channels rank*16..
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int n = hf * 16 + q4 * 4, col = hf * 256 + rank * 16 + q4 * 4;
+                        const float4 bq = __ldg(reinterpret_cast<const float4*>(bs + hf * l.cout + rank * 16 + q4 * 4));
+                        *reinterpret_cast<float4*>(orow + col) = make_float4(fmaf(v[n], inv, bq.x), fmaf(v[n + 1], inv, bq.y),
+                                                                             fmaf(v[n + 2], inv, bq.z), fmaf(v[n + 3], inv, bq.w));
+                    }
+            } else {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int col = rank * 16 + q4 * 4;
+                    const float4 bq = __ldg(reinterpret_cast<const float4*>(bs + col));
+                    *reinterpret_cast<float4*>(orow + col) = make_float4(fmaf(v[q4 * 4], inv, bq.x), fmaf(v[q4 * 4 + 1], inv, bq.y),
+                                                                         fmaf(v[q4 * 4 + 2], inv, bq.z), fmaf(v[q4 * 4 + 3], inv, bq.w));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    use.d++;
+    __syncthreads();                                                  // the accumulator has been read: the next utterance may overwrite it
+}
+
 // LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
 __device__ __noinline__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRows& rl, int rank, const float* scr) {
     const DecLayer& l = P.L[li];
@@ -584,8 +705,11 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
         for (int s = 0; s < DEC_NSLOT; ++s)
             for (int w = 0; w < NWARP; ++w) mbar_init(bar64(&S.fullw[s][w]), 1);
         mbar_init(bar64(&S.gbar[0]), 1); mbar_init(bar64(&S.gbar[1]), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(bar64(&S.sbar[i]), 1);
+        mbar_init(bar64(&S.dbar), 1);
         fence_mbar_init();
     }
+    if (P.tc_pre && warp == 0) tmem_alloc<32>(&S.tmem_base);          // 128 lanes x 32 fp32 columns: the pre-pass accumulator
     for (int i = tid; i < 2 * GMAX * XLD; i += NT) (&S.xin[0][0][0])[i] = 0.f;
     for (int i = tid; i < 2 * NC * PLD; i += NT) (&S.pre[0][0][0])[i] = 0.f;
     if (tid < GMAX) { S.p_cur[tid] = 0; S.p_prev[tid] = 0; S.p_next[tid] = 0; S.moved[tid] = 0; }
@@ -607,6 +731,8 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
     int cb = 0;
     unsigned lcount = 0;
     int n_moved_frames = 0, n_moved_utt = 0;
+    TcUse tcuse{{0u, 0u, 0u}, 0u};
+    if (P.tc_pre) { tc_fence_before(); __syncthreads(); tc_fence_after(); }
     if (tid == 0) S.prof_last = clock64();
     for (int j = 0; j < P.steps; ++j) {
         if (tid < GMAX) S.moved[tid] = (tid < G && j > 0 && S.p_cur[tid] != S.p_prev[tid]) ? 1 : 0;
@@ -670,7 +796,8 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
                 for (int g = 0; g < G; ++g) {
                     if (rl.n[g] <= 0) continue;
                     float* rows = scr + (size_t)rl.off[g] * 512;
-                    if (rl.n[g] <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                    if (P.tc_pre) pyr_tc_utt(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows, tcuse);
+                    else if (rl.n[g] <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
                     else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
                     else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
                 }
@@ -704,6 +831,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
     if (PROF && P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
     cp_async_wait<0>();
     cluster_sync_all();                                   // no CTA exits while a peer may still write into its shared memory
+    if (P.tc_pre && warp == 0) tmem_dealloc<32>(S.tmem_base);
 }
 
 size_t decode_smem_bytes() { return sizeof(Smem) + 128; }

@@ -31,7 +31,8 @@ struct DecLayer {
     int prow;        // AudioDec receptive-field rows to recompute when the attention window moved (1 otherwise)
     int ldin;        // leading dimension of the input history
 };
-struct DecChunk { int off; short nfl4; short k0; short krows; short layer; };   // off: float offset in a rank's stream; nfl4: floats / 4; k0: first k row (tap*cin + ci)
+struct DecChunk { int off; int off16; short nfl4; short k0; short krows; short layer; };   // off: float offset in a rank's stream (off16: of the
+                                                                   // same rows as split-fp16 MMA slabs); nfl4: floats / 4; k0: first k row (tap*cin + ci)
 
 struct DecParams {
     DecLayer L[DEC_MAXL];
@@ -47,10 +48,12 @@ struct DecParams {
     float* pre_scr;                    // [clusters][G * max prow][512] pre-LN scratch of the recompute path
     int* p_hist;                       // (B, T) window used at every step
     int* p_final;                      // (B) window after the last step
+    float inv_scale[DEC_MAXL];         // 1 / (power-of-two scale of the block's split-fp16 weight planes), tcgen05 pre-pass
     int* stats;                        // [clusters][2]: frames with a window move, utterance-frames recomputed
     long long* prof;                   // optional [16] SM-clock lap timers of cluster 0 / rank 0 (option decode_prof), else nullptr
     int nl, n_enc, nch, nch_enc, pyr_ch0, pyr_ch1, stream_len;   // pyr_ch0..pyr_ch1: chunks of the AudioDec blocks with prow > 1
     int B, G, T, N, d, n_mels, win_size, steps;
+    int tc_pre;                        // 1: the receptive-field pre-pass runs on tcgen05 (split-fp16 3-MMA), 0: fp32 FMA
 };
 static_assert(sizeof(DecParams) <= 4000, "DecParams must fit the kernel parameter space");
 

@@ -73,7 +73,9 @@ class OverlappedGather:
         self.total, self.dst, self.group, self.device = total, dst, group, device
         self.lo, self.hi = shard_bounds(total, self.rank, self.world)
         n = self.hi - self.lo
-        self.nchunks = max(1, min(chunks, n))
+        self.nchunks = max(1, min(chunks, n)) if n > 0 else 1
+        base, rem = divmod(total, self.world)
+        self.nchunks_max = max(1, min(chunks, base + (1 if rem else 0)))
         self.cuda = torch.device(device).type == "cuda"
         self.side = torch.cuda.Stream(device=device) if self.cuda else None
         self.out = torch.empty((total,) + tuple(shape_tail), dtype=dtype, device=device) if self.rank == dst else None
@@ -90,7 +92,9 @@ class OverlappedGather:
         return [self.Chunk(c, (n * c) // self.nchunks, (n * (c + 1)) // self.nchunks) for c in range(self.nchunks)]
 
     def begin(self):
-        """Destination: post the receives of every chunk of every other rank (they complete as the chunks arrive)."""
+        """Destination: post the receives, one NCCL group per chunk index holding that chunk of EVERY other rank, so that the
+        peers' chunk c arrive concurrently while chunk c+1 is still being computed (receives posted one by one would serialise
+        the peers on the destination's communication stream)."""
         self._pending = []
         if self.world == 1 or self.rank != self.dst:
             return
@@ -98,15 +102,19 @@ class OverlappedGather:
         if self.cuda:
             self.side.wait_stream(torch.cuda.current_stream(self.device))      # the buffer's previous consumer is done
         with ctx:
-            for g in range(self.world):
-                if g == self.dst:
-                    continue
-                glo, ghi = shard_bounds(self.total, g, self.world)
-                nch = max(1, min(self.nchunks, ghi - glo))
-                for c in range(nch):
-                    a, b = self._bounds(g, c, nch)
-                    if b > a:
-                        self._pending.append(dist.irecv(self.out[a:b], src=g, group=self.group, tag=c))
+            for c in range(self.nchunks_max):
+                ops = []
+                for g in range(self.world):
+                    if g == self.dst:
+                        continue
+                    glo, ghi = shard_bounds(self.total, g, self.world)
+                    nch = max(1, min(self.nchunks, ghi - glo))
+                    if c < nch:
+                        a, b = self._bounds(g, c, nch)
+                        if b > a:
+                            ops.append(dist.P2POp(dist.irecv, self.out[a:b], g, self.group))
+                if ops:
+                    self._pending.extend(dist.batch_isend_irecv(ops))
 
     def send(self, chunk, z):
         """Hand over the finished local rows [chunk.lo, chunk.hi) (a tensor of exactly those rows)."""
@@ -121,9 +129,9 @@ class OverlappedGather:
             self.side.wait_stream(torch.cuda.current_stream(self.device))      # chunk is complete on the compute stream
             with torch.cuda.stream(self.side):
                 z.record_stream(self.side)
-                self._pending.append(dist.isend(z.contiguous(), dst=self.dst, group=self.group, tag=chunk.index))
+                self._pending.extend(dist.batch_isend_irecv([dist.P2POp(dist.isend, z.contiguous(), self.dst, self.group)]))
         else:
-            self._pending.append(dist.isend(z.contiguous(), dst=self.dst, group=self.group, tag=chunk.index))
+            self._pending.extend(dist.batch_isend_irecv([dist.P2POp(dist.isend, z.contiguous(), self.dst, self.group)]))
 
     def local_view(self, chunk):
         """Destination rank: the slice of the receive buffer its own chunk belongs in (produce straight into it)."""

@@ -19,7 +19,9 @@ B = 32
 def default_engine(engine):
     engine.set_tensor_path(1)
     engine.set_option("decode_mode", 1)
-    return engine
+    engine.set_option("decode_prepass", 0)
+    yield engine
+    engine.set_option("decode_prepass", 0)
 
 
 def test_ssrn_config3_b32_t210(default_engine, params):
@@ -62,12 +64,13 @@ def _compare_prefix(Y, P, Yo, Po, margin, steps):
     return checked
 
 
-@pytest.mark.parametrize("decode_mode", [1, 0], ids=["cluster", "graph"])
-def test_generate_config4_b32_210_frames(default_engine, params, decode_mode):
+@pytest.mark.parametrize("decode_mode,prepass", [(1, 0), (1, 1), (0, 0)], ids=["cluster-fma", "cluster-tcgen05", "graph"])
+def test_generate_config4_b32_210_frames(default_engine, params, decode_mode, prepass):
     """The benchmark's own workload (32 synthetic 100-character utterances, 210 frames, free running): four
     utterances spread over different clusters are checked against the oracle's schedule (synthesize.py:45-57)."""
     e = default_engine
     e.set_option("decode_mode", decode_mode)
+    e.set_option("decode_prepass", prepass)
     try:
         L = synthetic_text(B, 100, seed=0)
         rows = [0, 9, 18, 31]
@@ -93,13 +96,15 @@ def test_generate_config2_b1_210_frames(default_engine, params):
     assert _compare_prefix(Y.cpu().numpy(), P.cpu().numpy(), Yo, Po, margin, hp.max_T) >= 100
 
 
+@pytest.mark.parametrize("prepass", [0, 1], ids=["fma", "tcgen05"])
 @pytest.mark.parametrize("Bn", [2, 3, 5, 13])
-def test_cluster_decode_equals_graph_decode(default_engine, Bn):
+def test_cluster_decode_equals_graph_decode(default_engine, Bn, prepass):
     """Ragged group sizes (last cluster partly filled, G = 1 and G = 2): the persistent kernel and the
     graph-per-frame loop follow the same windows and agree to float32 re-association noise."""
     e = default_engine
     L = np.concatenate([synthetic_text(1, 30 + 11 * i, seed=100 + i) for i in range(Bn)])
     steps = 70
+    e.set_option("decode_prepass", prepass)
     Y1, P1, _, _ = e.text2mel_generate(L, steps=steps)
     e.set_option("decode_mode", 0)
     try:

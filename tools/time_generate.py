@@ -14,7 +14,7 @@ from dc_tts_b200.params import init_params, synthetic_text  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("batches", type=int, nargs="*", default=[1, 32])
 ap.add_argument("--steps", type=int, default=210)
-ap.add_argument("--modes", default="1,0")
+ap.add_argument("--modes", default="1,0", help="decode modes to time: 1 persistent cluster kernel (fp32 pre-pass), 2 the same with the tcgen05 pre-pass, 0 graph per frame")
 ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--prof", action="store_true", help="print the in-kernel lap timers of the persistent decode")
 a = ap.parse_args()
@@ -25,7 +25,8 @@ for B in a.batches:
     L = synthetic_text(B, 100, seed=0)
     outs = {}
     for mode in [int(m) for m in a.modes.split(",")]:
-        e.set_option("decode_mode", mode)
+        e.set_option("decode_mode", 1 if mode else 0)
+        e.set_option("decode_prepass", 1 if mode == 2 else 0)
         for _ in range(2):
             e.text2mel_generate(L, steps=a.steps)
         torch.cuda.synchronize()
@@ -35,13 +36,13 @@ for B in a.batches:
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / a.iters
         extra = ""
-        if mode == 1:
+        if mode >= 1:
             fr, ut, cl = e.decode_stats()
             extra = "  clusters %d, cluster-frames with a recompute %d, utterance-frames recomputed %d" % (cl, fr, ut)
         print("generate B=%d mode=%d: %.2f ms (%.1f us/frame)  checksum %.6f%s"
               % (B, mode, dt * 1e3, dt * 1e6 / a.steps, float(Y.double().sum()), extra), flush=True)
         outs[mode] = (Y, P)
-        if mode == 1 and a.prof:
+        if mode >= 1 and a.prof:
             e.set_option("decode_prof", 1)
             e.text2mel_generate(L, steps=a.steps)
             pr = e.decode_profile()
@@ -49,9 +50,11 @@ for B in a.batches:
             tot = float(sum(pr.values())) or 1.0
             print("   lap timers (cluster 0, rank 0; %% of %.1f Mcycles): " % (tot / 1e6)
                   + ", ".join("%s %.1f" % (k, 100.0 * v / tot) for k, v in pr.items()), flush=True)
-    if len(outs) == 2:
-        (Y1, P1), (Y0, P0) = outs[1], outs[0]
-        same = (P0 == P1).all(dim=1)
-        print("   windows equal for %d/%d utterances; max|dY| over those %.3e"
-              % (int(same.sum()), B, float((Y0[same] - Y1[same]).abs().max()) if same.any() else float("nan")), flush=True)
-e.set_option("decode_mode", 1)
+    ref = outs.get(0, outs.get(1))
+    for m, (Y1, P1) in outs.items():
+        if (Y1 is ref[0]):
+            continue
+        same = (ref[1] == P1).all(dim=1)
+        print("   mode %d vs mode %d: windows equal for %d/%d utterances; max|dY| over those %.3e"
+              % (m, 0 if 0 in outs else 1, int(same.sum()), B, float((ref[0][same] - Y1[same]).abs().max()) if same.any() else float("nan")), flush=True)
+e.set_option("decode_mode", 1); e.set_option("decode_prepass", 0)
