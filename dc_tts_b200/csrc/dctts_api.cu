@@ -1014,7 +1014,13 @@ bool decode_cluster(H* h, int B, int steps, cudaStream_t s) {
     P.tc_pre = h->opt.decode_prepass ? 1 : 0;
     const int n_clusters = (B + P.G - 1) / P.G;
     cudaError_t e = launch_decode_cluster(P, n_clusters, s);
-    if (e != cudaSuccess) throw std::runtime_error(std::string("decode_cluster_kernel launch failed: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        // a device on which the 16-CTA cluster cannot be placed after all: remember it and let the caller take the
+        // graph-per-frame loop (another GPU path, not a CPU fallback)
+        cudaGetLastError();
+        D.ok = false; D.why = std::string("decode_cluster_kernel launch failed: ") + cudaGetErrorString(e);
+        return false;
+    }
     h->launches += 1;
     D.last_clusters = n_clusters; D.last_moved_frames = -1;
     return true;
@@ -1033,9 +1039,10 @@ void text2mel_generate(H* h, const int* L, int B, int steps, float* Y, int* prev
     run_textenc(lc, L, B, h->kv.as<float>());
     CUDA_CHECK(cudaMemsetAsync(h->ybuf.p, 0, (size_t)B * T * hp.n_mels * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(h->ibuf.p, 0, (size_t)(4 + 3 * h->ws_B + (size_t)h->ws_B * T) * sizeof(int), s));
-    if (cluster) {
-        decode_cluster(h, B, steps, s);
+    if (cluster && decode_cluster(h, B, steps, s)) {
+        // the whole loop ran as one launch
     } else {
+        if (cluster) { CUDA_CHECK(cudaStreamSynchronize(s)); build_ar_graph(h, B); }
         for (int j = 0; j < steps; ++j) {
             CUDA_CHECK(cudaGraphLaunch(h->ar_exec, s));
             h->launches += h->ar_nodes;

@@ -63,10 +63,14 @@ struct Smem {
     unsigned long long gbar[2];
     unsigned long long sbar[3], dbar;   // tcgen05 pre-pass: slab stage free / accumulator complete
     uint32_t tmem_base, pad_;
+    DecParams P;                        // the kernel's parameter block: indexed per block / chunk on the critical path; in the
+                                        // constant bank those indexed loads missed the (instruction-shared) constant cache
     int p_cur[GMAX], p_prev[GMAX], p_next[GMAX], moved[GMAX];
     int fmoved[2];
     long long prof[16], prof_last;
 };
+
+static_assert(sizeof(Smem) + 128 <= 232448, "decode kernel: shared memory budget (227 KB per CTA)");
 
 // lap timer (option decode_prof): thread 0 attributes the cycles since the previous lap to bucket i
 #define LAP(i) do { if constexpr (PROF) { if (threadIdx.x == 0) { const long long now_ = clock64(); S.prof[i] += now_ - S.prof_last; S.prof_last = now_; } } } while (0)
@@ -78,6 +82,9 @@ __device__ __forceinline__ float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+// NOTE on `__noinline__` in this file: there is none.  With 227 KB of shared memory per CTA the L1 data cache is ~0 KB, so every
+// stack access (ABI spills of a non-inlined call, a dynamically indexed local array) is an L2 round trip of ~500 cycles: the
+// first three versions of this kernel spent 60 % of their time there (ptxas must report a 0-byte stack frame).
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -279,7 +286,7 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
             const int g = idx >> lgns, n = idx & (l.ns - 1);
             const float* rp = &S.red[g][n];
             float s = bs[n];
-#pragma unroll 4
+#pragma unroll 2
             for (int q = 0; q < ng; ++q) s += rp[q << lgns];
             ov[idx] = s;
         }
@@ -302,7 +309,7 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
         auto pre_off = [&](int c) { const int rk = (cs == 16) ? (c >> 4) : ((c * 205) >> 10); return rk * PLD + (c - rk * cs); };
         const float piv1 = pr[0], piv2 = hcb ? pr[cs] : 0.f;         // pivots: channel 0 of each half (constant row -> exact zeros, quirk Q4)
         float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
-#pragma unroll 2
+#pragma unroll 1
         for (int c = lane; c < C; c += 32) {
             const int o = pre_off(c);
             const float a = pr[o] - piv1, b = hcb ? pr[o + cs] - piv2 : 0.f;
@@ -324,7 +331,7 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
         float* oh = P.out_hist[li];
         const float* xres = &S.xin[cb][g][cur_off];
         float* xout = &S.xin[cb ^ 1][g][next_off];
-#pragma unroll 2
+#pragma unroll 1
         for (int c = lane; c < C; c += 32) {
             const int po = pre_off(c);
             float o = (pr[po] - piv1 - m1) * inv1 * prm[c] + prm[256 + c];
@@ -351,7 +358,7 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
 
 // ---- attention of ONE query row under the 3-key window (networks.py:140-153) -------------------------------
 // lane holds q[lane*8 .. +8); returns ctx[8] in the same layout and the argmax key (first index among equal maxima)
-__device__ __noinline__ int attend_row(const DecParams& P, const float (&qv)[8], int b, int p, int lane, float (&ctx)[8]) {
+__device__ __forceinline__ int attend_row(const DecParams& P, const float (&qv)[8], int b, int p, int lane, float (&ctx)[8]) {
     const int d = P.d;
     const int n_lo = min(max(p, 0), P.N - 1), n_hi = min(n_lo + P.win_size, P.N);
     const float scale = rsqrtf((float)d);
@@ -395,24 +402,28 @@ __device__ __noinline__ int attend_row(const DecParams& P, const float (&qv)[8],
 }
 
 // ---- pre-pass: refresh the receptive field (rows t < j) of the utterances whose window moved -------------------
-struct PreRows { int t_lo[GMAX], n[GMAX], off[GMAX + 1]; };        // per utterance: first row, row count (rows t_lo .. j-1), scratch offset
+// every moved utterance refreshes the SAME rows t_lo .. j-1 (t_lo depends on the block and the frame only), so the row list is
+// (bit mask of moved utterances, first row, rows per utterance): no local arrays (see the note on the stack above)
+struct PreRows { unsigned mask; int t_lo, n, total; };
 __device__ __forceinline__ PreRows pre_rows(const Smem& S, int G, int j, int prow) {
-    PreRows r; r.off[0] = 0;
+    PreRows r;
+    r.mask = 0;
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) {
-        const bool mv = g < G && S.moved[g];
-        r.t_lo[g] = max(0, j - (prow - 1));
-        r.n[g] = mv ? j - r.t_lo[g] : 0;
-        r.off[g + 1] = r.off[g] + r.n[g];
-    }
+    for (int g = 0; g < GMAX; ++g) if (g < G && S.moved[g]) r.mask |= 1u << g;
+    r.t_lo = max(0, j - (prow - 1));
+    r.n = j - r.t_lo;
+    r.total = r.n * __popc(r.mask);
     return r;
 }
+// scratch row m -> (utterance, time row): the k-th moved utterance owns rows [k*n, (k+1)*n)
 __device__ __forceinline__ void pre_row_of(const PreRows& r, int m, int& g, int& t) {
-    g = 0;
-#pragma unroll
-    for (int i = 1; i < GMAX; ++i) if (m >= r.off[i]) g = i;
-    t = r.t_lo[g] + (m - r.off[g]);
+    const int k = m / r.n;
+    unsigned mk = r.mask;
+    for (int i = 0; i < k; ++i) mk &= mk - 1;                        // drop the k lowest set bits
+    g = __ffs(mk) - 1;
+    t = r.t_lo + (m - k * r.n);
 }
+__device__ __forceinline__ int pre_off_of(const PreRows& r, int g) { return r.n * __popc(r.mask & ((1u << g) - 1u)); }
 // address of W[k][n] (k = row within the layer's K) inside the ring; the layer's chunks occupy consecutive slots from pos0
 __device__ __forceinline__ const float* w_quad(const Smem& S, const DecLayer& l, unsigned pos0, int k, int ns, int n) {
     const int c = k / l.krows, kc = k - c * l.krows, kr8 = l.krows >> 3;
@@ -423,7 +434,7 @@ __device__ __forceinline__ const float* w_quad(const Smem& S, const DecLayer& l,
 // register-tiled fp32 GEMM of ONE utterance: rows {rg, rg+32, rg+64} x TN columns {q, q+8, ..} per thread; the source rows
 // of a 16-channel slab are staged once (cp.async, 3 stages) and used for every tap
 template <int TN>
-__device__ __noinline__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
+__device__ __forceinline__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
     constexpr int NS = 8 * TN;
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, q = tid & 7, rg = tid >> 3;
@@ -493,7 +504,7 @@ __device__ __noinline__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, u
 }
 
 // <= 4 rows of one utterance: the GEMV path with the rows in the role of the utterances
-__device__ __noinline__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
+__device__ __forceinline__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5;
     float* xs = S.wrk;                                                // [m][tap*cin + c], pitch 768
@@ -532,7 +543,7 @@ __device__ __noinline__ void pyr_small_utt(const DecParams& P, Smem& S, int li, 
 // tap * rate rows -- staged once, multiplied three times.  B = this CTA's weight columns, pre-packed in the same layout
 // ([plane][k8][column][8 halfs], 2 KB per 16-k slab) and streamed through the ring like the fp32 weights.  D = 128 x ns fp32
 // in tensor memory; per slab and tap hi*Whi + hi*Wlo + lo*Whi (the dropped lo*lo term is 2^-22 relative).
-struct TcUse { unsigned s[3]; unsigned d; };
+struct TcUse { unsigned s0, s1, s2, d; };
 __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
@@ -546,7 +557,7 @@ constexpr int TC_APLANE = 2 * TC_RA * 16;                           // bytes of 
 constexpr int TC_ASTAGE = 2 * TC_APLANE;                            // hi + lo
 static_assert(3 * TC_ASTAGE <= WRK_F * 4, "A slab stages do not fit the work buffer");
 
-__device__ __noinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank,
+__device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank,
                                         float* scr_rows, TcUse& use) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -567,7 +578,8 @@ __device__ __noinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, uns
     const uint32_t tacc = S.tmem_base;
     for (int ks = 0; ks < nslab; ++ks) {
         const int stg = ks % 3;
-        if (use.s[stg] > 0) mbar_wait(bar64(&S.sbar[stg]), (use.s[stg] - 1) & 1u);   // the MMAs that read this stage are done
+        const unsigned used = stg == 0 ? use.s0 : (stg == 1 ? use.s1 : use.s2);
+        if (used > 0) mbar_wait(bar64(&S.sbar[stg]), (used - 1) & 1u);   // the MMAs that read this stage are done
         if (loader) {
             const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             __align__(16) __half hi[8];
@@ -599,7 +611,7 @@ __device__ __noinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, uns
             tc_commit(bar64(&S.sbar[stg]));                           // the stage may be overwritten once these MMAs have read it
             if (ks == nslab - 1) tc_commit(bar64(&S.dbar));           // accumulator complete
         }
-        use.s[stg]++;
+        if (stg == 0) use.s0++; else if (stg == 1) use.s1++; else use.s2++;
     }
     // epilogue: thread == output row (TMEM lane); pre-LN slice (+ bias) -> scratch
     if (warp < 4) {
@@ -643,12 +655,12 @@ __device__ __noinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, uns
 }
 
 // LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
-__device__ __noinline__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRows& rl, int rank, const float* scr) {
+__device__ __forceinline__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0, const PreRows& rl, int rank, const float* scr) {
     const DecLayer& l = P.L[li];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* prm = &S.red[0][0];
     const float fC = 256.f;
-    for (int m = rank * NWARP + warp; m < rl.off[GMAX]; m += NC * NWARP) {
+    for (int m = rank * NWARP + warp; m < rl.total; m += NC * NWARP) {
         int g, t; pre_row_of(rl, m, g, t);
         const float* y = scr + (size_t)m * 512;
         const size_t row = (size_t)(b0 + g) * P.T + t;
@@ -691,10 +703,17 @@ __device__ __noinline__ void pyr_ln(const DecParams& P, Smem& S, int li, int b0,
 
 template <bool PROF>
 __global__ void __cluster_dims__(DEC_NC, 1, 1) __launch_bounds__(DEC_THREADS, 1)
-decode_cluster_kernel(const __grid_constant__ DecParams P) {
+decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem& S = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    {
+        const int* src = reinterpret_cast<const int*>(&Pc);
+        int* dst = reinterpret_cast<int*>(&S.P);
+        for (int i = tid; i < (int)(sizeof(DecParams) / 4); i += NT) dst[i] = src[i];
+    }
+    __syncthreads();
+    const DecParams& P = S.P;
     const int rank = (int)cluster_ctarank();
     const int cluster = blockIdx.x / NC;
     const int b0 = cluster * P.G;
@@ -731,7 +750,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
     int cb = 0;
     unsigned lcount = 0;
     int n_moved_frames = 0, n_moved_utt = 0;
-    TcUse tcuse{{0u, 0u, 0u}, 0u};
+    TcUse tcuse{0u, 0u, 0u, 0u};
     if (P.tc_pre) { tc_fence_before(); __syncthreads(); tc_fence_after(); }
     if (tid == 0) S.prof_last = clock64();
     for (int j = 0; j < P.steps; ++j) {
@@ -769,7 +788,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
             for (int g = 0; g < G; ++g) n_moved_utt += S.moved[g];
             const PreRows ra = pre_rows(S, G, j, P.L[P.n_enc].prow);
             const float* Qh = P.out_hist[P.n_enc - 1];
-            for (int m = rank * NWARP + warp; m < ra.off[GMAX]; m += NC * NWARP) {
+            for (int m = rank * NWARP + warp; m < ra.total; m += NC * NWARP) {
                 int g, t; pre_row_of(ra, m, g, t);
                 const size_t row = (size_t)(b0 + g) * P.T + t;
                 float qv[8], ctx[8];
@@ -793,13 +812,15 @@ decode_cluster_kernel(const __grid_constant__ DecParams P) {
                 }
                 __syncwarp();
                 const PreRows rl = pre_rows(S, G, j, l.prow);
-                for (int g = 0; g < G; ++g) {
-                    if (rl.n[g] <= 0) continue;
-                    float* rows = scr + (size_t)rl.off[g] * 512;
-                    if (P.tc_pre) pyr_tc_utt(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows, tcuse);
-                    else if (rl.n[g] <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
-                    else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
-                    else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo[g], rl.n[g], rank, rows);
+                if (rl.n > 0) {
+                    for (int g = 0; g < G; ++g) {
+                        if (!((rl.mask >> g) & 1u)) continue;
+                        float* rows = scr + (size_t)pre_off_of(rl, g) * 512;
+                        if (P.tc_pre) pyr_tc_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows, tcuse);
+                        else if (rl.n <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                    }
                 }
                 __syncthreads();                          // every warp is done with every region of these chunks
                 for (int c = 0; c < l.nch; ++c) {

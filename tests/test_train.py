@@ -221,11 +221,12 @@ def test_ssrn_relu_margins_explain_the_tie_case():
     assert min(_ssrn_relu_margins(2, 16, 0.0, 0).values()) < 1e-6
     assert min(_ssrn_relu_margins(2, 12, 0.05, 9).values()) > 4e-6
     assert min(_ssrn_relu_margins(1, 8, 0.0, 0).values()) > 4e-6
+    assert min(_ssrn_relu_margins(2, 14, 0.0, 7).values()) > 4e-6
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,T,rate,seed", [pytest.param(2, 16, 0.0, 0, marks=pytest.mark.xfail(reason=_RELU_TIE, strict=False)),
-                                           (2, 12, 0.05, 9)])
+                                           (2, 12, 0.05, 9), (1, 8, 0.0, 0), (2, 14, 0.0, 7)])
 def test_cuda_ssrn_train_step_vs_oracle(B, T, rate, seed):
     """The SSRN trainer (train.py num=2): transposed-conv blocks, C = 1024 highway blocks and the F = 1025 wide blocks.
     The first case is kept as a documented ReLU tie (see _RELU_TIE)."""
