@@ -167,7 +167,7 @@ struct dctts_handle_s {
         int tc_resid_tma = 1;     // hc: residual in / planes out through TMA
         int tc_debug = 0;         // progress markers + in-kernel cycle stamps (synchronising)
         int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
-        int decode_prepass = 0;   // persistent decode, receptive-field pre-pass: 0 = fp32 FMA GEMM, 1 = tcgen05 split-fp16 (3 MMAs)
+        int decode_prepass = 1;   // persistent decode, receptive-field pre-pass: 1 = tcgen05 split-fp16 (3 MMAs, default), 0 = fp32 FMA GEMM
         int decode_prof = 0;      // persistent decode: record SM-clock lap timers of cluster 0 / rank 0 (dctts_decode_profile)
         int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
     } opt;

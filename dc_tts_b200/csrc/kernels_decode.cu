@@ -63,6 +63,9 @@ struct Smem {
     unsigned long long gbar[2];
     unsigned long long sbar[3], dbar;   // tcgen05 pre-pass: slab stage free / accumulator complete
     uint32_t tmem_base, pad_;
+    float stat[GMAX][2][2];             // per utterance and LN half: mean, 1/sqrt(var + eps)
+    unsigned tc_use[4];                 // tcgen05 pre-pass: commits so far on sbar[0..2] / dbar (phase parities)
+    int n_moved_frames, n_moved_utt;
     DecParams P;                        // the kernel's parameter block: indexed per block / chunk on the critical path; in the
                                         // constant bank those indexed loads missed the (instruction-shared) constant cache
     int p_cur[GMAX], p_prev[GMAX], p_next[GMAX], moved[GMAX];
@@ -86,6 +89,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // stack access (ABI spills of a non-inlined call, a dynamically indexed local array) is an L2 round trip of ~500 cycles: the
 // first three versions of this kernel spent 60 % of their time there (ptxas must report a 0-byte stack frame).
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// the per-frame path: ex2.approx + rcp (2 ulp each; far inside the 1e-3 budget, half the instructions)
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
     const int sz = valid ? 16 : 0;                                   // 0: zero fill (TF zero padding of the causal conv)
@@ -149,13 +154,14 @@ __device__ __forceinline__ void prefetch_params(const DecParams& P, Smem& S, int
     float* dst = S.prm[li & 1];
     const int tid = threadIdx.x;
     cp_async16(dst + tid * 4, P.lnp[li] + tid * 4, true);                        // 1024 floats
-    if (tid < l.ns) {                                                             // bias slice in stream column order
-        // hc: columns [0,cs) gate of channels rank*cs.., [cs,2cs) info; conv: [0,cs), zero beyond
-        const int n = tid;
-        float bv = 0.f;
-        if (l.kind == 1) bv = __ldg(P.bias[li] + (n < l.cs ? rank * l.cs + n : l.cout + rank * l.cs + (n - l.cs)));
-        else if (n < l.cs) bv = __ldg(P.bias[li] + rank * l.cs + n);
-        dst[1024 + n] = bv;
+    // bias slice in stream column order -- hc: columns [0,cs) gate of channels rank*cs.., [cs,2cs) info; conv: [0,cs), zero beyond
+    if ((l.cs & 3) == 0) {
+        if (tid < l.ns / 4) {
+            const int n = tid * 4;
+            cp_async16(dst + 1024 + n, P.bias[li] + ((l.kind == 1 && n >= l.cs) ? l.cout + rank * l.cs + (n - l.cs) : rank * l.cs + n), true);
+        }
+    } else if (tid < l.ns) {                                                     // the n_mels-wide last block (5 channels per CTA)
+        dst[1024 + tid] = (tid < l.cs) ? __ldg(P.bias[li] + rank * l.cs + tid) : 0.f;
     }
 }
 // taps (all but the last) of block li at frame j: rows j - (ntaps-1-tap)*rate of its input history -> xin[buf][g][tap*256..]
@@ -298,58 +304,64 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
     LAP(LP_GATHER);
     mbar_wait(bar64(&S.gbar[pb]), gpar);
     LAP(LP_CBAR);
-    // one warp per utterance: both LayerNorms, gate, highway mix (redundantly in every CTA).  Two passes over the gathered row in
-    // shared memory (statistics, then normalise + mix) with rolled loops: small code, no register arrays.
-    if (warp < G) {
-        const int g = warp, C = l.cout, cs = l.cs;
-        const bool hcb = l.kind == 1;
-        const float* prm = S.prm[li & 1];
-        const float* pr = &S.pre[pb][0][g << lgns];
+    // LayerNorm statistics: one warp per (utterance, half), pivoted single pass (pivot = channel 0: a constant row gives exactly 0,
+    // quirk Q4); then gate / highway mix one thread per channel.  Redundantly in every CTA: the next block's input is local.
+    {
+        const int C = l.cout, cs = l.cs, nh = l.kind + 1;
+        const float rC = (C == 256) ? (1.0f / 256.0f) : __frcp_rn((float)C);
         // channel c lives in the slice of rank c / cs at column c % cs (cs = 16, or 5 for the n_mels-wide last block)
         auto pre_off = [&](int c) { const int rk = (cs == 16) ? (c >> 4) : ((c * 205) >> 10); return rk * PLD + (c - rk * cs); };
-        const float piv1 = pr[0], piv2 = hcb ? pr[cs] : 0.f;         // pivots: channel 0 of each half (constant row -> exact zeros, quirk Q4)
-        float s1 = 0.f, q1 = 0.f, s2 = 0.f, q2 = 0.f;
-#pragma unroll 1
-        for (int c = lane; c < C; c += 32) {
-            const int o = pre_off(c);
-            const float a = pr[o] - piv1, b = hcb ? pr[o + cs] - piv2 : 0.f;
-            s1 += a; q1 = fmaf(a, a, q1); s2 += b; q2 = fmaf(b, b, q2);
-        }
+        for (int pr = warp; pr < G * nh; pr += NWARP) {
+            const int g = (nh == 2) ? (pr >> 1) : pr, hf = (nh == 2) ? (pr & 1) : 0;
+            const float* base = &S.pre[pb][0][(g << lgns) + hf * cs];
+            const float piv = base[0];
+            float sv = 0.f, qv = 0.f;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o); q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+            for (int i = 0; i < 8; ++i) {
+                const int c = lane + 32 * i;
+                if (c < C) { const float d = base[pre_off(c)] - piv; sv += d; qv = fmaf(d, d, qv); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { sv += __shfl_xor_sync(0xffffffffu, sv, o); qv += __shfl_xor_sync(0xffffffffu, qv, o); }
+            if (lane == 0) {
+                const float m = sv * rC;
+                S.stat[g][hf][0] = piv + m;
+                S.stat[g][hf][1] = rsqrtf(fmaxf(qv * rC - m * m, 0.f) + 1e-12f);
+            }
         }
-        const float fC = (float)C;
-        const float m1 = s1 / fC, m2 = s2 / fC;
-        const float inv1 = 1.0f / sqrtf(fmaxf(q1 / fC - m1 * m1, 0.f) + 1e-12f);
-        const float inv2 = 1.0f / sqrtf(fmaxf(q2 / fC - m2 * m2, 0.f) + 1e-12f);
+        __syncthreads();
         LAP(LP_LN);
+        const float* prm = S.prm[li & 1];
         const int cur_off = (l.ntaps - 1) * 256;
         const int next_off = (last || li + 1 == P.n_enc) ? 0 : (P.L[li + 1].ntaps - 1) * 256;
-        const size_t row = (size_t)(b0 + g) * P.T + j;
         float* oh = P.out_hist[li];
-        const float* xres = &S.xin[cb][g][cur_off];
-        float* xout = &S.xin[cb ^ 1][g][next_off];
-#pragma unroll 1
-        for (int c = lane; c < C; c += 32) {
+        const int c = tid;
+        if (c < C) {
             const int po = pre_off(c);
-            float o = (pr[po] - piv1 - m1) * inv1 * prm[c] + prm[256 + c];
-            if (hcb) {
-                const float h2 = (pr[po + cs] - piv2 - m2) * inv2 * prm[512 + c] + prm[768 + c];
-                const float h1 = sigmoid_acc(o);
-                o = h1 * h2 + (1.0f - h1) * xres[c];
-            } else if (l.act == 1) o = fmaxf(o, 0.f);
-            if (po / PLD == rank && oh) oh[row * C + c] = o;         // this CTA's slice of the history row
-            if (last) {                                               // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
-                o = sigmoid_acc(o);
-                if (rank == 0) P.ybuf[row * C + c] = o;
+            const bool mine = (po / PLD == rank) && oh;
+            const float g1 = prm[c], b1 = prm[256 + c], g2 = prm[512 + c], b2 = prm[768 + c];
+#pragma unroll
+            for (int g = 0; g < GMAX; ++g) {
+                if (g < G) {
+                    const float* pr = &S.pre[pb][0][g << lgns];
+                    float o = (pr[po] - S.stat[g][0][0]) * S.stat[g][0][1] * g1 + b1;
+                    if (l.kind == 1) {
+                        const float h2 = (pr[po + cs] - S.stat[g][1][0]) * S.stat[g][1][1] * g2 + b2;
+                        const float h1 = sigmoid_fast(o);
+                        o = h1 * h2 + (1.0f - h1) * S.xin[cb][g][cur_off + c];
+                    } else if (l.act == 1) o = fmaxf(o, 0.f);
+                    const size_t row = (size_t)(b0 + g) * P.T + j;
+                    if (mine) oh[row * C + c] = o;                    // this CTA's slice of the history row
+                    if (last) {                                       // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
+                        o = sigmoid_fast(o);
+                        if (rank == 0) P.ybuf[row * C + c] = o;
+                    }
+                    S.xin[cb ^ 1][g][next_off + c] = o;
+                }
             }
-            xout[c] = o;
+        } else if (last && c < 128) {                                 // AudioEnc C_1 reads K = 128 padded channels
+            for (int g = 0; g < G; ++g) S.xin[cb ^ 1][g][c] = 0.f;
         }
-        if (last) for (int c = C + lane; c < 128; c += 32) xout[c] = 0.f;   // AudioEnc C_1 reads K = 128 padded channels
-    } else {
-        LAP(LP_LN);
     }
     LAP(LP_MIX);
     lcount++;
@@ -465,12 +477,15 @@ __device__ __forceinline__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li
         const float* A = As + (ks % 3) * SROWS * SLD;
         for (int tap = 0; tap < l.ntaps; ++tap) {
             const int soff = tap * l.rate;                            // slot of output row m under this tap = m + tap*rate
+            // the 16 k rows of this slab and tap are contiguous in ONE warp region of the ring (regions hold multiples of 16 rows):
+            // one address computation (two integer divisions) per slab and tap, not per quad
+            const float* wb = w_quad(S, l, pos0, tap * l.cin + ks * 16, NS, q);
 #pragma unroll
             for (int k4 = 0; k4 < 4; ++k4) {
                 float4 w4[TN];
 #pragma unroll
                 for (int cc = 0; cc < TN; ++cc)
-                    w4[cc] = *reinterpret_cast<const float4*>(w_quad(S, l, pos0, tap * l.cin + ks * 16 + k4 * 4, NS, q + 8 * cc));
+                    w4[cc] = *reinterpret_cast<const float4*>(wb + (k4 * NS + 8 * cc) * 4);
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const int m = rg + 32 * i;
@@ -543,7 +558,6 @@ __device__ __forceinline__ void pyr_small_utt(const DecParams& P, Smem& S, int l
 // tap * rate rows -- staged once, multiplied three times.  B = this CTA's weight columns, pre-packed in the same layout
 // ([plane][k8][column][8 halfs], 2 KB per 16-k slab) and streamed through the ring like the fp32 weights.  D = 128 x ns fp32
 // in tensor memory; per slab and tap hi*Whi + hi*Wlo + lo*Whi (the dropped lo*lo term is 2^-22 relative).
-struct TcUse { unsigned s0, s1, s2, d; };
 __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
@@ -558,7 +572,7 @@ constexpr int TC_ASTAGE = 2 * TC_APLANE;                            // hi + lo
 static_assert(3 * TC_ASTAGE <= WRK_F * 4, "A slab stages do not fit the work buffer");
 
 __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank,
-                                        float* scr_rows, TcUse& use) {
+                                        float* scr_rows) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int halo = (l.ntaps - 1) * l.rate, n_src = n_out + halo;   // <= 96
@@ -578,7 +592,7 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
     const uint32_t tacc = S.tmem_base;
     for (int ks = 0; ks < nslab; ++ks) {
         const int stg = ks % 3;
-        const unsigned used = stg == 0 ? use.s0 : (stg == 1 ? use.s1 : use.s2);
+        const unsigned used = S.tc_use[stg];                         // written by thread 32 >= 3 block barriers ago
         if (used > 0) mbar_wait(bar64(&S.sbar[stg]), (used - 1) & 1u);   // the MMAs that read this stage are done
         if (loader) {
             const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
@@ -610,12 +624,13 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
             }
             tc_commit(bar64(&S.sbar[stg]));                           // the stage may be overwritten once these MMAs have read it
             if (ks == nslab - 1) tc_commit(bar64(&S.dbar));           // accumulator complete
+            S.tc_use[stg] = used + 1;
         }
-        if (stg == 0) use.s0++; else if (stg == 1) use.s1++; else use.s2++;
     }
     // epilogue: thread == output row (TMEM lane); pre-LN slice (+ bias) -> scratch
+    const unsigned dused = S.tc_use[3];                               // read before the barrier below, bumped after it
     if (warp < 4) {
-        mbar_wait(bar64(&S.dbar), use.d & 1u);
+        mbar_wait(bar64(&S.dbar), dused & 1u);
         tc_fence_after();
         const int m = tid;
         const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
@@ -650,8 +665,8 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
         }
         tc_fence_before();
     }
-    use.d++;
     __syncthreads();                                                  // the accumulator has been read: the next utterance may overwrite it
+    if (tid == 32) S.tc_use[3] = dused + 1;
 }
 
 // LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
@@ -701,6 +716,68 @@ __device__ __forceinline__ void pyr_ln(const DecParams& P, Smem& S, int li, int 
 
 }  // namespace
 
+// ---- the pre-pass as ONE out-of-line function: cold code (most frames do not have it) kept out of the per-frame
+// instruction stream.  The stream cursors go in and come back by value; everything else lives in shared memory.
+template <bool PROF>
+__device__ __noinline__ Stream prepass(const DecParams& P, Smem& S, Stream st, int j, int b0, int G, int rank, float* scr) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+            // ---- pre-pass: rows t < j of the moved utterances under the new window (uniform branch: see the file header) ----
+            if (threadIdx.x == 0) { S.n_moved_frames++; for (int g = 0; g < G; ++g) S.n_moved_utt += S.moved[g]; }
+            const PreRows ra = pre_rows(S, G, j, P.L[P.n_enc].prow);
+            const float* Qh = P.out_hist[P.n_enc - 1];
+            for (int m = rank * NWARP + warp; m < ra.total; m += NC * NWARP) {
+                int g, t; pre_row_of(ra, m, g, t);
+                const size_t row = (size_t)(b0 + g) * P.T + t;
+                float qv[8], ctx[8];
+                const float4 q0 = ldcg4(Qh + row * P.d + lane * 8), q1 = ldcg4(Qh + row * P.d + lane * 8 + 4);
+                qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+                attend_row(P, qv, b0 + g, S.p_cur[g], lane, ctx);
+                float* rr = P.rbuf + row * (2 * P.d);
+                *reinterpret_cast<float4*>(rr + lane * 8) = make_float4(ctx[0], ctx[1], ctx[2], ctx[3]);
+                *reinterpret_cast<float4*>(rr + lane * 8 + 4) = make_float4(ctx[4], ctx[5], ctx[6], ctx[7]);
+                *reinterpret_cast<float4*>(rr + P.d + lane * 8) = q0;
+                *reinterpret_cast<float4*>(rr + P.d + lane * 8 + 4) = q1;
+            }
+            cluster_sync_all();
+            LAP(LP_PYR_ATT);
+            for (int lp = P.n_enc; lp < P.nl && P.L[lp].prow > 1; ++lp) {
+                const DecLayer& l = P.L[lp];
+                // every warp waits for ALL regions of the block's chunks (lane w watches region w)
+                for (int c = 0; c < l.nch; ++c) {
+                    const unsigned pp = st.pos + c;
+                    if (lane < NWARP) mbar_wait(bar64(&S.fullw[pp % DEC_NSLOT][lane]), (pp / DEC_NSLOT) & 1u);
+                }
+                __syncwarp();
+                const PreRows rl = pre_rows(S, G, j, l.prow);
+                if (rl.n > 0) {
+                    for (int g = 0; g < G; ++g) {
+                        if (!((rl.mask >> g) & 1u)) continue;
+                        float* rows = scr + (size_t)pre_off_of(rl, g) * 512;
+                        if (P.tc_pre) pyr_tc_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        else if (rl.n <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                    }
+                }
+                __syncthreads();                          // every warp is done with every region of these chunks
+                for (int c = 0; c < l.nch; ++c) {
+                    if (lane == 0) { fence_proxy_async_smem(); stream_issue(P, S, st, st.prod, (int)(st.pos % DEC_NSLOT), warp); }
+                    stream_advance(P, S, st);
+                }
+                for (int i = tid; i < 256; i += NT)       // this block's LayerNorm parameters for pyr_ln
+                    *reinterpret_cast<float4*>(&S.red[0][0] + i * 4) = __ldg(reinterpret_cast<const float4*>(P.lnp[lp]) + i);
+                LAP(LP_PYR_GEMM);
+                cluster_sync_all();
+                LAP(LP_PYR_BAR);
+                pyr_ln(P, S, lp, b0, rl, rank, scr);
+                LAP(LP_PYR_LN);
+                cluster_sync_all();
+                LAP(LP_PYR_BAR);
+            }
+            return st;
+}
+
 template <bool PROF>
 __global__ void __cluster_dims__(DEC_NC, 1, 1) __launch_bounds__(DEC_THREADS, 1)
 decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
@@ -734,6 +811,8 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
     if (tid < GMAX) { S.p_cur[tid] = 0; S.p_prev[tid] = 0; S.p_next[tid] = 0; S.moved[tid] = 0; }
     if (tid < 2) S.fmoved[tid] = 0;
     if (tid < 16) S.prof[tid] = 0;
+    if (tid < 4) S.tc_use[tid] = 0;
+    if (tid == 0) { S.n_moved_frames = 0; S.n_moved_utt = 0; }
     __syncthreads();
 
     Stream st;
@@ -749,8 +828,6 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
 
     int cb = 0;
     unsigned lcount = 0;
-    int n_moved_frames = 0, n_moved_utt = 0;
-    TcUse tcuse{0u, 0u, 0u, 0u};
     if (P.tc_pre) { tc_fence_before(); __syncthreads(); tc_fence_after(); }
     if (tid == 0) S.prof_last = clock64();
     for (int j = 0; j < P.steps; ++j) {
@@ -769,6 +846,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
         for (int li = 0; li < P.nl; ++li) {
         if (li == P.n_enc) {
         // Attention of row j under the current window, redundantly in every CTA: R[j] = [A.V ; Q] (networks.py:140-153)
+        __syncthreads();                                  // Q[j] was written one thread per channel
         if (warp < G) {
             const int g = warp;
             float qv[8], ctx[8];
@@ -782,62 +860,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
         cb ^= 1;
         LAP(LP_ATT);
 
-        if (any_moved) {
-            // ---- pre-pass: rows t < j of the moved utterances under the new window (uniform branch: see the file header) ----
-            n_moved_frames++;
-            for (int g = 0; g < G; ++g) n_moved_utt += S.moved[g];
-            const PreRows ra = pre_rows(S, G, j, P.L[P.n_enc].prow);
-            const float* Qh = P.out_hist[P.n_enc - 1];
-            for (int m = rank * NWARP + warp; m < ra.total; m += NC * NWARP) {
-                int g, t; pre_row_of(ra, m, g, t);
-                const size_t row = (size_t)(b0 + g) * P.T + t;
-                float qv[8], ctx[8];
-                const float4 q0 = ldcg4(Qh + row * P.d + lane * 8), q1 = ldcg4(Qh + row * P.d + lane * 8 + 4);
-                qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-                attend_row(P, qv, b0 + g, S.p_cur[g], lane, ctx);
-                float* rr = P.rbuf + row * (2 * P.d);
-                *reinterpret_cast<float4*>(rr + lane * 8) = make_float4(ctx[0], ctx[1], ctx[2], ctx[3]);
-                *reinterpret_cast<float4*>(rr + lane * 8 + 4) = make_float4(ctx[4], ctx[5], ctx[6], ctx[7]);
-                *reinterpret_cast<float4*>(rr + P.d + lane * 8) = q0;
-                *reinterpret_cast<float4*>(rr + P.d + lane * 8 + 4) = q1;
-            }
-            cluster_sync_all();
-            LAP(LP_PYR_ATT);
-            for (int lp = P.n_enc; lp < P.nl && P.L[lp].prow > 1; ++lp) {
-                const DecLayer& l = P.L[lp];
-                // every warp waits for ALL regions of the block's chunks (lane w watches region w)
-                for (int c = 0; c < l.nch; ++c) {
-                    const unsigned pp = st.pos + c;
-                    if (lane < NWARP) mbar_wait(bar64(&S.fullw[pp % DEC_NSLOT][lane]), (pp / DEC_NSLOT) & 1u);
-                }
-                __syncwarp();
-                const PreRows rl = pre_rows(S, G, j, l.prow);
-                if (rl.n > 0) {
-                    for (int g = 0; g < G; ++g) {
-                        if (!((rl.mask >> g) & 1u)) continue;
-                        float* rows = scr + (size_t)pre_off_of(rl, g) * 512;
-                        if (P.tc_pre) pyr_tc_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows, tcuse);
-                        else if (rl.n <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
-                        else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
-                        else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
-                    }
-                }
-                __syncthreads();                          // every warp is done with every region of these chunks
-                for (int c = 0; c < l.nch; ++c) {
-                    if (lane == 0) { fence_proxy_async_smem(); stream_issue(P, S, st, st.prod, (int)(st.pos % DEC_NSLOT), warp); }
-                    stream_advance(P, S, st);
-                }
-                for (int i = tid; i < 256; i += NT)       // this block's LayerNorm parameters for pyr_ln
-                    *reinterpret_cast<float4*>(&S.red[0][0] + i * 4) = __ldg(reinterpret_cast<const float4*>(P.lnp[lp]) + i);
-                LAP(LP_PYR_GEMM);
-                cluster_sync_all();
-                LAP(LP_PYR_BAR);
-                pyr_ln(P, S, lp, b0, rl, rank, scr);
-                LAP(LP_PYR_LN);
-                cluster_sync_all();
-                LAP(LP_PYR_BAR);
-            }
-        }
+        if (any_moved) st = prepass<PROF>(P, S, st, j, b0, G, rank, scr);
         }   // li == n_enc
         cb = layer_row<PROF>(P, S, st, li, j, b0, G, rank, cb, lcount);
         }   // blocks
@@ -848,7 +871,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
         LAP(LP_FRAME);
     }
     if (rank == 0 && tid < G) P.p_final[b0 + tid] = S.p_cur[tid];
-    if (rank == 0 && tid == 0 && P.stats) { P.stats[2 * cluster] = n_moved_frames; P.stats[2 * cluster + 1] = n_moved_utt; }
+    if (rank == 0 && tid == 0 && P.stats) { P.stats[2 * cluster] = S.n_moved_frames; P.stats[2 * cluster + 1] = S.n_moved_utt; }
     if (PROF && P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
     cp_async_wait<0>();
     cluster_sync_all();                                   // no CTA exits while a peer may still write into its shared memory

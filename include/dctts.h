@@ -193,7 +193,7 @@ int dctts_set_tensor_path(dctts_handle h, int32_t mode);
  *   "decode_mode"  1 = the whole AR loop (synthesize.py:45-54) as ONE persistent cluster kernel (default),
  *                  0 = one captured CUDA graph per mel frame (round-1 path)
  *   "decode_prepass" persistent decode, recompute of the AudioDec receptive field after a window move:
- *                  0 = fp32 FMA GEMM, 1 = tcgen05 (split-fp16 operands, 3 MMAs, fp32 accumulate in tensor memory)
+ *                  1 = tcgen05 (split-fp16 operands, 3 MMAs, fp32 accumulate in tensor memory; default), 0 = fp32 FMA GEMM
  *   "tc_occ2" 0/1, "tc_cg2" 0/1/2, "tc_tile_pair" 0/1, "tc_mcast" 0/1, "tc_resid_tma" 0/1: tcgen05 block kernel variants
  *   "fused_ln" 0/1: graph decode, GEMM + LN in one launch;  "tc_debug" 0/1;  "decode_prof" 0/1;  "pdl" 0/1 (process-wide)
  * dctts_get_option also answers "decode_available" (1 when this handle / device can run the persistent decode). */

@@ -19,9 +19,9 @@ B = 32
 def default_engine(engine):
     engine.set_tensor_path(1)
     engine.set_option("decode_mode", 1)
-    engine.set_option("decode_prepass", 0)
+    engine.set_option("decode_prepass", 1)
     yield engine
-    engine.set_option("decode_prepass", 0)
+    engine.set_option("decode_prepass", 1)
 
 
 def test_ssrn_config3_b32_t210(default_engine, params):

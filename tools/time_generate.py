@@ -57,4 +57,4 @@ for B in a.batches:
         same = (ref[1] == P1).all(dim=1)
         print("   mode %d vs mode %d: windows equal for %d/%d utterances; max|dY| over those %.3e"
               % (m, 0 if 0 in outs else 1, int(same.sum()), B, float((ref[0][same] - Y1[same]).abs().max()) if same.any() else float("nan")), flush=True)
-e.set_option("decode_mode", 1); e.set_option("decode_prepass", 0)
+e.set_option("decode_mode", 1); e.set_option("decode_prepass", 1)
