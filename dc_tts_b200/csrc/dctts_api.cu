@@ -167,7 +167,6 @@ struct dctts_handle_s {
         int tc_resid_tma = 1;     // hc: residual in / planes out through TMA
         int tc_debug = 0;         // progress markers + in-kernel cycle stamps (synchronising)
         int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
-        int decode_prepass = 1;   // persistent decode, receptive-field pre-pass: 1 = tcgen05 split-fp16 (3 MMAs, default), 0 = fp32 FMA GEMM
         int decode_prof = 0;      // persistent decode: record SM-clock lap timers of cluster 0 / rank 0 (dctts_decode_profile)
         int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
     } opt;
@@ -593,7 +592,7 @@ void ensure_ws(H* h, int B) {
         h->arpl[i].ensure(bytes);
         CUDA_CHECK(cudaMemset(h->arpl[i].p, 0, h->arpl[i].bytes));
     }
-    h->dec.scr.ensure((size_t)roundup(B, DEC_GMAX) * 85 * 512 * sizeof(float));
+    h->dec.scr.ensure((size_t)(B + DEC_GMAX) * 85 * 512 * sizeof(float));
     h->dec.stats.ensure((size_t)2 * B * sizeof(int));
     h->dec.pfinal.ensure((size_t)B * sizeof(int));
     h->ws_B = B;
@@ -1009,9 +1008,15 @@ bool decode_cluster(H* h, int B, int steps, cudaStream_t s) {
     P.p_hist = ib.p_hist; P.p_final = D.pfinal.as<int>(); P.stats = D.stats.as<int>();
     P.prof = nullptr;
     if (h->opt.decode_prof) { D.prof.ensure(16 * sizeof(long long)); CUDA_CHECK(cudaMemsetAsync(D.prof.p, 0, 16 * sizeof(long long), s)); P.prof = D.prof.as<long long>(); }
-    P.B = B; P.G = std::min(DEC_GMAX, (B + 7) / 8); P.T = hp.max_T; P.N = hp.max_N; P.d = hp.d; P.n_mels = hp.n_mels;
+    P.B = B;
+    {   // utterances per cluster: the fewest that let every cluster be co-resident (a second wave doubles the time)
+        const int mc = std::max(1, D.max_clusters);
+        int G = 1;
+        while (G < DEC_GMAX && (B + G - 1) / G > mc) ++G;
+        P.G = G;
+    }
+    P.T = hp.max_T; P.N = hp.max_N; P.d = hp.d; P.n_mels = hp.n_mels;
     P.win_size = hp.attention_win_size; P.steps = steps;
-    P.tc_pre = h->opt.decode_prepass ? 1 : 0;
     const int n_clusters = (B + P.G - 1) / P.G;
     cudaError_t e = launch_decode_cluster(P, n_clusters, s);
     if (e != cudaSuccess) {
@@ -1993,7 +1998,6 @@ static int* option_slot(dctts_handle h, const char* name) {
     if (n == "fused_ln") return &h->opt.fused_ln;
     if (n == "decode_mode") return &h->opt.decode_mode;
     if (n == "decode_prof") return &h->opt.decode_prof;
-    if (n == "decode_prepass") return &h->opt.decode_prepass;
     return nullptr;
 }
 
@@ -2018,6 +2022,7 @@ int dctts_get_option(dctts_handle h, const char* name, int32_t* value) {
         REQUIRE(value, "dctts_get_option: null output");
         if (name && std::string(name) == "pdl") { *value = pdl_enabled() ? 1 : 0; return; }
         if (name && std::string(name) == "decode_available") { *value = h->dec.ok ? 1 : 0; return; }
+        if (name && std::string(name) == "decode_max_clusters") { *value = h->dec.max_clusters; return; }   // co-resident 16-CTA clusters
         int* slot = option_slot(h, name);
         REQUIRE(slot, "dctts_get_option: unknown option");
         *value = *slot;

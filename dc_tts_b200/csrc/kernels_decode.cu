@@ -37,6 +37,7 @@
 #include "tc_ptx.cuh"
 
 #include <cuda_fp16.h>
+#include <atomic>
 #include <math.h>
 
 namespace dctts {
@@ -47,24 +48,29 @@ namespace {
 constexpr int NC = DEC_NC, GMAX = DEC_GMAX, NT = DEC_THREADS, NWARP = NT / 32;
 constexpr int XLD = 768;                       // row pitch of the input vectors: [tap0 | tap1 | current]
 constexpr int PLD = GMAX * 32 + 16;            // pitch between the ranks' slices in `pre` (16 floats of bank skew)
-constexpr int SROWS = 96, SLD = 20;            // pre-pass A slab: <= 96 source rows x 16 channels (+4 pad)
-constexpr int WRK_F = 3 * SROWS * SLD;         // three slab stages; also 4 x 768 floats of few-row inputs
-static_assert(WRK_F >= 4 * 768, "work buffer too small for the few-row inputs");
+constexpr int TC_RA = 96;                      // pre-pass: rows per k8 group of an A slab plane (<= 96 source rows per utterance)
+constexpr int TC_APLANE = 2 * TC_RA * 16;      // bytes of one plane of one 16-channel slab (2 k8 groups)
+constexpr int TC_ASTAGE = 2 * TC_APLANE;       // hi + lo planes
+constexpr int TC_NSTG = 2;                     // A slab stages
+constexpr int WRK_F = TC_NSTG * TC_ASTAGE / 4; // the pre-pass work buffer, shared with the per-frame partial sums
+static_assert(WRK_F >= GMAX * NT && WRK_F >= 1024, "work buffer: partial sums of the per-frame path / LayerNorm parameters of the pre-pass");
 
 struct Smem {
     float ring[DEC_NSLOT][NWARP][DEC_REG_F];
-    float wrk[WRK_F];                   // directly after the ring: the tcgen05 pre-pass reads up to 128 + 54 rows past a slab start
+    union {                             // never live together: the pre-pass stages A here while no per-frame block is in flight
+        float wrk[WRK_F];               // tcgen05 pre-pass A slab stages (its reads run up to 128 + 54 rows past a slab start: xin follows)
+        float red[GMAX][NT];            // per-frame path: partial sums per warp; pre-pass: LayerNorm parameters of the block
+    };
     float xin[2][GMAX][XLD];
     float pre[2][NC][PLD];
     float outv[2][GMAX * 32];
-    float red[GMAX][NT];
     float prm[2][DEC_PRM_F];
     unsigned long long fullw[DEC_NSLOT][NWARP];
     unsigned long long gbar[2];
-    unsigned long long sbar[3], dbar;   // tcgen05 pre-pass: slab stage free / accumulator complete
+    unsigned long long sbar[TC_NSTG], abar[TC_NSTG], dbar;   // tcgen05 pre-pass: slab stage free / slab stage filled / accumulator complete
     uint32_t tmem_base, pad_;
     float stat[GMAX][2][2];             // per utterance and LN half: mean, 1/sqrt(var + eps)
-    unsigned tc_use[4];                 // tcgen05 pre-pass: commits so far on sbar[0..2] / dbar (phase parities)
+    uint32_t tc_baddr[96];              // tcgen05 pre-pass: descriptor start field of every weight slab of the current block
     int n_moved_frames, n_moved_utt;
     DecParams P;                        // the kernel's parameter block: indexed per block / chunk on the critical path; in the
                                         // constant bank those indexed loads missed the (instruction-shared) constant cache
@@ -126,8 +132,9 @@ __device__ __forceinline__ void cur_next(const DecParams& P, const Smem& S, Cur&
 }
 struct Stream {
     const float* base;          // this rank's packed stream
-    Cur cons, prod;             // chunk being consumed / chunk that will be loaded into the slot it frees
+    Cur prod;                   // chunk that will be loaded into the slot the consumer frees next (the consumer itself walks the blocks' chunk ranges)
     unsigned pos;               // number of chunks consumed so far
+    unsigned tcq, tca;          // tcgen05 pre-pass: slabs staged / accumulators completed so far (mbarrier phase parities)
 };
 // one lane of warp `warp`: load the warp's rows of chunk `u` into its region of `slot`
 __device__ __forceinline__ void stream_issue(const DecParams& P, Smem& S, const Stream& st, const Cur& u, int slot, int warp) {
@@ -135,11 +142,11 @@ __device__ __forceinline__ void stream_issue(const DecParams& P, Smem& S, const 
     const DecChunk& ch = P.C[u.c];
     const uint32_t bytes = (uint32_t)ch.nfl4 * 2u;                   // nfl * 4 bytes / 8 warps
     mbar_expect_tx(bar64(&S.fullw[slot][warp]), bytes);
-    const int off = (u.seg == 1 && P.tc_pre) ? ch.off16 : ch.off;    // pre-pass on tensor cores: the same rows as split-fp16 MMA slabs
+    const int off = (u.seg == 1) ? ch.off16 : ch.off;                // the pre-pass reads the same rows as split-fp16 MMA slabs
     bulk_g2s(&S.ring[slot][warp][0], st.base + off + warp * (ch.nfl4 >> 1), bytes, &S.fullw[slot][warp]);
 }
 __device__ __forceinline__ void stream_advance(const DecParams& P, const Smem& S, Stream& st) {
-    cur_next(P, S, st.cons); cur_next(P, S, st.prod); st.pos++;
+    cur_next(P, S, st.prod); st.pos++;
 }
 // the calling warp has read its region of the current chunk: refill it with its rows of the chunk 3 ahead
 __device__ __forceinline__ void warp_release(const DecParams& P, Smem& S, Stream& st, int warp, int lane) {
@@ -179,10 +186,11 @@ __device__ __forceinline__ void prefetch_taps(const DecParams& P, Smem& S, int l
 
 // ---- GEMV of the calling warp's k rows of one chunk: acc[g] += sum_k x[g][k] * W[k][n] ----------------------
 // wreg: the warp's region ([k/4][column][4]); x: row 0 of the input vectors at the warp's first k; ns = 32 / 16 / 8 columns
-// per CTA.  ONE runtime-generic body on purpose: the per-frame loop has to fit the instruction cache (round 1 and the first
-// version of this kernel were instruction-fetch bound at ~11k SASS lines).
-__device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const float* __restrict__ x, int xld, int kr8, int ns, int G,
-                                          float (&acc)[GMAX]) {
+// per CTA.  The utterance count GT is a template parameter of the whole kernel (only ONE instantiation runs per launch, so the
+// instruction-cache footprint is that of one): no per-utterance branches, all loads of an 8-k step hoisted, two independent
+// FMA chains per utterance.  Slots g >= the cluster's real utterance count multiply zeros (their input rows stay zero).
+template <int GT>
+__device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const float* __restrict__ x, int kr8, int ns, float (&acc)[GT]) {
     const int lane = threadIdx.x & 31;
     const int lg = (ns == 32) ? 5 : (ns == 16 ? 4 : 3);
     const int n = lane & (ns - 1), sg = lane >> lg;                  // column, k sub-group inside the warp
@@ -190,59 +198,33 @@ __device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const 
     const float* w = wreg + ((size_t)((sg * kper) >> 2) * ns + n) * 4;
     const float* xs = x + sg * kper;
     const int wstep = ns * 4;
-#pragma unroll 1
+    float acc2[GT];
+#pragma unroll
+    for (int g = 0; g < GT; ++g) acc2[g] = 0.f;
+#pragma unroll 2
     for (int k = 0; k < kper; k += 8) {
         const float4 w0 = *reinterpret_cast<const float4*>(w);
         const float4 w1 = *reinterpret_cast<const float4*>(w + wstep);
         w += 2 * wstep;
 #pragma unroll
-        for (int g = 0; g < GMAX; ++g) {
-            if (g < G) {
-                const float4 x0 = *reinterpret_cast<const float4*>(xs + g * xld + k);
-                const float4 x1 = *reinterpret_cast<const float4*>(xs + g * xld + k + 4);
-                float a = acc[g];
-                a = fmaf(x0.x, w0.x, a); a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
-                a = fmaf(x1.x, w1.x, a); a = fmaf(x1.y, w1.y, a); a = fmaf(x1.z, w1.z, a); a = fmaf(x1.w, w1.w, a);
-                acc[g] = a;
-            }
+        for (int g = 0; g < GT; ++g) {
+            const float4 x0 = *reinterpret_cast<const float4*>(xs + g * XLD + k);
+            const float4 x1 = *reinterpret_cast<const float4*>(xs + g * XLD + k + 4);
+            float a = acc[g], c = acc2[g];
+            a = fmaf(x0.x, w0.x, a); a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
+            c = fmaf(x1.x, w1.x, c); c = fmaf(x1.y, w1.y, c); c = fmaf(x1.z, w1.z, c); c = fmaf(x1.w, w1.w, c);
+            acc[g] = a; acc2[g] = c;
         }
     }
+#pragma unroll
+    for (int g = 0; g < GT; ++g) acc[g] += acc2[g];
 }
 
-// global column of stream column n of rank r (hc: gate | info halves of the 2*cout pre-LN row)
-__device__ __forceinline__ int pre_col(const DecLayer& l, int rank, int n) {
-    if (l.kind == 1) return n < l.cs ? rank * l.cs + n : 256 + rank * l.cs + (n - l.cs);
-    return rank * l.cs + n;
-}
-__device__ __forceinline__ float bias_smem_or_global(const DecParams& P, const float* prm, int li, int rank, int n) {
-    const DecLayer& l = P.L[li];
-    if (prm && (l.cs & 3) == 0) return prm[1024 + n];
-    if (l.kind == 1) return __ldg(P.bias[li] + (n < l.cs ? rank * l.cs + n : l.cout + rank * l.cs + (n - l.cs)));
-    if (n >= l.cs) return 0.f;
-    return __ldg(P.bias[li] + rank * l.cs + n);
-}
-
-// LayerNorm of one row held as v[i] (channel lane + 32 i), pivoted single pass (pivot = channel 0): the sum and the
-// sum of squares of (v - pivot) reduce together; a constant row gives exactly 0 (eps = 1e-12, quirk Q4)
-__device__ __forceinline__ void ln_row(float (&v)[8], int C, int lane, const float* gam, const float* bet) {
-    const float pivot = __shfl_sync(0xffffffffu, v[0], 0);
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; v[i] = (c < C) ? v[i] - pivot : 0.f; s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-    const float fC = (float)C;
-    const float md = s1 / fC;
-    const float var = fmaxf(s2 / fC - md * md, 0.f);
-    const float inv = 1.0f / sqrtf(var + 1e-12f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { const int c = lane + 32 * i; if (c < C) v[i] = (v[i] - md) * inv * gam[c] + bet[c]; }
-}
 
 // ---- one block on ONE row per utterance -------------------------------------------------------------------
 // in: S.xin[cb][g] = [taps | current row] of the block's input, S.prm[li&1] = its parameters (both prefetched).
 // out: S.xin[cb^1][g][next_off ..] = the block's output row; this CTA's channel slice appended to the output history.
-template <bool PROF>
+template <bool PROF, int GT>
 __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st, int li, int j, int b0, int G, int rank, int cb, unsigned& lcount) {
     const DecLayer& l = P.L[li];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -250,7 +232,7 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
     const int nl_next = last ? 0 : li + 1;
     const int pb = (int)(lcount & 1u);
     const uint32_t gpar = (lcount >> 1) & 1u;
-    const uint32_t gbytes = (uint32_t)(G * l.ns * 4);
+    const uint32_t gbytes = (uint32_t)(GT * l.ns * 4);
 
     cp_async_wait<0>();                     // this block's taps and parameters (issued one block ago)
     __syncthreads();                        // ... and every warp has finished the previous block
@@ -264,42 +246,42 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
     cp_async_commit();
     LAP(LP_START);
 
-    float acc[GMAX];
+    float acc[GT];
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
+    for (int g = 0; g < GT; ++g) acc[g] = 0.f;
     for (int c = 0; c < l.nch; ++c) {
-        const DecChunk& ch = P.C[st.cons.c];
+        const DecChunk& ch = P.C[l.ch0 + c];
         const int slot = (int)(st.pos % DEC_NSLOT);
         mbar_wait(bar64(&S.fullw[slot][warp]), (st.pos / DEC_NSLOT) & 1u);
         LAP(LP_WAIT);
         const int kr8 = ch.krows >> 3;
-        gemv_warp(&S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], XLD, kr8, l.ns, G, acc);
+        gemv_warp<GT>(&S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], kr8, l.ns, acc);
         LAP(LP_GEMV);
         warp_release(P, S, st, warp, lane);
         LAP(LP_RELEASE);
     }
 #pragma unroll
-    for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
+    for (int g = 0; g < GT; ++g) S.red[g][tid] = acc[g];
     __syncthreads();
-    // warp 0: final sums of the slice -> staging -> one bulk copy per peer (all-gather through distributed shared memory)
+    // final sums of the slice (one thread per value) -> staging -> one bulk copy per peer (all-gather through distributed
+    // shared memory).  With one utterance the values fit one warp, which then issues the copies without a second block barrier.
     const int lgns = (l.ns == 32) ? 5 : (l.ns == 16 ? 4 : 3);
-    if (warp == 0) {
-        const int nvals = G << lgns, ng = NT >> lgns;
+    {
+        const int nvals = GT << lgns, ng = NT >> lgns;
         float* ov = S.outv[pb];
-        const float* bs = S.prm[li & 1] + 1024;
-#pragma unroll 1
-        for (int idx = lane; idx < nvals; idx += 32) {
-            const int g = idx >> lgns, n = idx & (l.ns - 1);
+        if (tid < nvals) {
+            const float* bs = S.prm[li & 1] + 1024;
+            const int g = tid >> lgns, n = tid & (l.ns - 1);
             const float* rp = &S.red[g][n];
-            float s = bs[n];
-#pragma unroll 2
-            for (int q = 0; q < ng; ++q) s += rp[q << lgns];
-            ov[idx] = s;
+            float s0 = bs[n], s1 = 0.f;
+#pragma unroll 4
+            for (int q = 0; q < ng; q += 2) { s0 += rp[q << lgns]; s1 += rp[(q + 1) << lgns]; }
+            ov[tid] = s0 + s1;
+            fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane < NC)
-            bulk_s2peer(mapa(smem_u32(&S.pre[pb][rank][0]), (uint32_t)lane), ov, gbytes, mapa(smem_u32(&S.gbar[pb]), (uint32_t)lane));
+        if (GT > 1) __syncthreads(); else __syncwarp();
+        if (tid < NC)
+            bulk_s2peer(mapa(smem_u32(&S.pre[pb][rank][0]), (uint32_t)tid), ov, gbytes, mapa(smem_u32(&S.gbar[pb]), (uint32_t)tid));
     }
     LAP(LP_GATHER);
     mbar_wait(bar64(&S.gbar[pb]), gpar);
@@ -311,7 +293,7 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
         const float rC = (C == 256) ? (1.0f / 256.0f) : __frcp_rn((float)C);
         // channel c lives in the slice of rank c / cs at column c % cs (cs = 16, or 5 for the n_mels-wide last block)
         auto pre_off = [&](int c) { const int rk = (cs == 16) ? (c >> 4) : ((c * 205) >> 10); return rk * PLD + (c - rk * cs); };
-        for (int pr = warp; pr < G * nh; pr += NWARP) {
+        for (int pr = warp; pr < GT * nh; pr += NWARP) {
             const int g = (nh == 2) ? (pr >> 1) : pr, hf = (nh == 2) ? (pr & 1) : 0;
             const float* base = &S.pre[pb][0][(g << lgns) + hf * cs];
             const float piv = base[0];
@@ -340,27 +322,37 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
             const int po = pre_off(c);
             const bool mine = (po / PLD == rank) && oh;
             const float g1 = prm[c], b1 = prm[256 + c], g2 = prm[512 + c], b2 = prm[768 + c];
+            float o[GT];
 #pragma unroll
-            for (int g = 0; g < GMAX; ++g) {
-                if (g < G) {
+            for (int g = 0; g < GT; ++g) {
+                const float* pr = &S.pre[pb][0][g << lgns];
+                o[g] = (pr[po] - S.stat[g][0][0]) * S.stat[g][0][1] * g1 + b1;
+            }
+            if (l.kind == 1) {
+#pragma unroll
+                for (int g = 0; g < GT; ++g) {
                     const float* pr = &S.pre[pb][0][g << lgns];
-                    float o = (pr[po] - S.stat[g][0][0]) * S.stat[g][0][1] * g1 + b1;
-                    if (l.kind == 1) {
-                        const float h2 = (pr[po + cs] - S.stat[g][1][0]) * S.stat[g][1][1] * g2 + b2;
-                        const float h1 = sigmoid_fast(o);
-                        o = h1 * h2 + (1.0f - h1) * S.xin[cb][g][cur_off + c];
-                    } else if (l.act == 1) o = fmaxf(o, 0.f);
-                    const size_t row = (size_t)(b0 + g) * P.T + j;
-                    if (mine) oh[row * C + c] = o;                    // this CTA's slice of the history row
-                    if (last) {                                       // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
-                        o = sigmoid_fast(o);
-                        if (rank == 0) P.ybuf[row * C + c] = o;
-                    }
-                    S.xin[cb ^ 1][g][next_off + c] = o;
+                    const float h2 = (pr[po + cs] - S.stat[g][1][0]) * S.stat[g][1][1] * g2 + b2;
+                    const float h1 = sigmoid_fast(o[g]);
+                    o[g] = h1 * h2 + (1.0f - h1) * S.xin[cb][g][cur_off + c];
                 }
+            } else if (l.act == 1) {
+#pragma unroll
+                for (int g = 0; g < GT; ++g) o[g] = fmaxf(o[g], 0.f);
+            }
+#pragma unroll
+            for (int g = 0; g < GT; ++g) {
+                const size_t row = (size_t)(b0 + g) * P.T + j;
+                if (mine && g < G) oh[row * C + c] = o[g];           // this CTA's slice of the history row
+                if (last) {                                           // Y = sigmoid(logits), networks.py:210; next frame's AudioEnc input
+                    o[g] = sigmoid_fast(o[g]);
+                    if (rank == 0 && g < G) P.ybuf[row * C + c] = o[g];
+                }
+                S.xin[cb ^ 1][g][next_off + c] = (g < G) ? o[g] : 0.f;   // unused slots stay zero
             }
         } else if (last && c < 128) {                                 // AudioEnc C_1 reads K = 128 padded channels
-            for (int g = 0; g < G; ++g) S.xin[cb ^ 1][g][c] = 0.f;
+#pragma unroll
+            for (int g = 0; g < GT; ++g) S.xin[cb ^ 1][g][c] = 0.f;
         }
     }
     LAP(LP_MIX);
@@ -437,121 +429,7 @@ __device__ __forceinline__ void pre_row_of(const PreRows& r, int m, int& g, int&
 }
 __device__ __forceinline__ int pre_off_of(const PreRows& r, int g) { return r.n * __popc(r.mask & ((1u << g) - 1u)); }
 // address of W[k][n] (k = row within the layer's K) inside the ring; the layer's chunks occupy consecutive slots from pos0
-__device__ __forceinline__ const float* w_quad(const Smem& S, const DecLayer& l, unsigned pos0, int k, int ns, int n) {
-    const int c = k / l.krows, kc = k - c * l.krows, kr8 = l.krows >> 3;
-    const int reg = kc / kr8, wi = kc - reg * kr8;                   // wi is a multiple of 4 for the callers
-    return &S.ring[(pos0 + c) % DEC_NSLOT][reg][((wi >> 2) * ns + n) * 4];
-}
-
-// register-tiled fp32 GEMM of ONE utterance: rows {rg, rg+32, rg+64} x TN columns {q, q+8, ..} per thread; the source rows
-// of a 16-channel slab are staged once (cp.async, 3 stages) and used for every tap
-template <int TN>
-__device__ __forceinline__ void pyr_gemm_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
-    constexpr int NS = 8 * TN;
-    const DecLayer& l = P.L[li];
-    const int tid = threadIdx.x, q = tid & 7, rg = tid >> 3;
-    const int halo = (l.ntaps - 1) * l.rate, n_src = n_out + halo;    // source rows t_lo - halo .. j-1  (<= 96)
-    const int nslab = l.cin / 16;
-    const float* in = P.in_hist[li];
-    float acc[3][TN];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int c = 0; c < TN; ++c) acc[i][c] = 0.f;
-    float* As = S.wrk;
-    auto stage = [&](int ks) {
-        float* dst = As + (ks % 3) * SROWS * SLD;
-        for (int i = tid; i < n_src * 4; i += NT) {
-            const int s = i >> 2, c4 = i & 3;
-            const int t = t_lo - halo + s;
-            cp_async16(dst + s * SLD + c4 * 4, in + ((size_t)b * P.T + (t < 0 ? 0 : t)) * l.ldin + ks * 16 + c4 * 4, t >= 0);
-        }
-        cp_async_commit();
-    };
-    stage(0);
-    if (nslab > 1) stage(1); else cp_async_commit();
-    for (int ks = 0; ks < nslab; ++ks) {
-        cp_async_wait<1>();                                           // slab ks has landed (at most the newest group is pending)
-        __syncthreads();                                              // ... for every thread, and slab ks-1 is fully consumed
-        if (ks + 2 < nslab) stage(ks + 2); else cp_async_commit();
-        const float* A = As + (ks % 3) * SROWS * SLD;
-        for (int tap = 0; tap < l.ntaps; ++tap) {
-            const int soff = tap * l.rate;                            // slot of output row m under this tap = m + tap*rate
-            // the 16 k rows of this slab and tap are contiguous in ONE warp region of the ring (regions hold multiples of 16 rows):
-            // one address computation (two integer divisions) per slab and tap, not per quad
-            const float* wb = w_quad(S, l, pos0, tap * l.cin + ks * 16, NS, q);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-                float4 w4[TN];
-#pragma unroll
-                for (int cc = 0; cc < TN; ++cc)
-                    w4[cc] = *reinterpret_cast<const float4*>(wb + (k4 * NS + 8 * cc) * 4);
-#pragma unroll
-                for (int i = 0; i < 3; ++i) {
-                    const int m = rg + 32 * i;
-                    if (m < n_out) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(A + (m + soff) * SLD + k4 * 4);
-#pragma unroll
-                        for (int cc = 0; cc < TN; ++cc) {
-                            float a = acc[i][cc];
-                            a = fmaf(a4.x, w4[cc].x, a); a = fmaf(a4.y, w4[cc].y, a);
-                            a = fmaf(a4.z, w4[cc].z, a); a = fmaf(a4.w, w4[cc].w, a);
-                            acc[i][cc] = a;
-                        }
-                    }
-                }
-            }
-        }
-    }
-    cp_async_wait<0>();
-    __syncthreads();                                                  // the slab buffers are free for the next utterance
-#pragma unroll
-    for (int cc = 0; cc < TN; ++cc) {
-        const int n = q + 8 * cc;
-        const float bs = bias_smem_or_global(P, nullptr, li, rank, n);
-        const int col = pre_col(l, rank, n);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            const int m = rg + 32 * i;
-            if (m < n_out) scr_rows[(size_t)m * 512 + col] = acc[i][cc] + bs;
-        }
-    }
-}
-
-// <= 4 rows of one utterance: the GEMV path with the rows in the role of the utterances
-__device__ __forceinline__ void pyr_small_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank, float* scr_rows) {
-    const DecLayer& l = P.L[li];
-    const int tid = threadIdx.x, warp = tid >> 5;
-    float* xs = S.wrk;                                                // [m][tap*cin + c], pitch 768
-    const int per_row = l.cin / 4, K = l.ntaps * l.cin;
-    for (int i = tid; i < n_out * l.ntaps * per_row; i += NT) {
-        const int c4 = i % per_row, rt = i / per_row, tap = rt % l.ntaps, m = rt / l.ntaps;
-        const int t = t_lo + m - (l.ntaps - 1 - tap) * l.rate;
-        cp_async16(xs + m * 768 + tap * l.cin + c4 * 4, P.in_hist[li] + ((size_t)b * P.T + (t < 0 ? 0 : t)) * l.ldin + c4 * 4, t >= 0);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    __syncthreads();
-    float acc[GMAX];
-#pragma unroll
-    for (int g = 0; g < GMAX; ++g) acc[g] = 0.f;
-    const int kr8 = l.krows >> 3;
-    for (int c = 0; c * l.krows < K; ++c)
-        gemv_warp(&S.ring[(pos0 + c) % DEC_NSLOT][warp][0], xs + c * l.krows + warp * kr8, 768, kr8, l.ns, n_out, acc);
-#pragma unroll
-    for (int g = 0; g < GMAX; ++g) S.red[g][tid] = acc[g];
-    __syncthreads();
-    for (int idx = tid; idx < n_out * l.ns; idx += NT) {
-        const int m = idx / l.ns, n = idx % l.ns, ng = NT / l.ns;
-        if (l.kind == 0 && n >= l.cs) continue;
-        float s = bias_smem_or_global(P, nullptr, li, rank, n);
-        for (int qq = 0; qq < ng; ++qq) s += S.red[m][qq * l.ns + n];
-        scr_rows[(size_t)m * 512 + pre_col(l, rank, n)] = s;
-    }
-    __syncthreads();                                                  // red / xs are free for the next utterance
-}
-
-// ---- the same GEMM on the 5th-generation tensor cores (option decode_prepass = 1) --------------------------------------
+// ---- the pre-pass GEMM on the 5th-generation tensor cores ---------------------------------------------------------------
 // One utterance, <= 96 source rows.  A = the source rows as split-fp16 planes (hi = fp16(x), lo = fp16(x - hi)), staged per
 // 16-channel slab in the NO-SWIZZLE K-major core-matrix layout [k8][row][8 halfs]: rows are consecutive 16-byte chunks, so
 // the three taps of the dilated conv are the SAME slab read through descriptors whose start address is shifted by
@@ -566,71 +444,95 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t addr, uint32_t lbo_
     d |= 1ull << 46;                                                // descriptor version (sm_100); layout type 0 = no swizzle
     return d;
 }
-constexpr int TC_RA = 96;                                           // rows per k8 group of an A slab plane
-constexpr int TC_APLANE = 2 * TC_RA * 16;                           // bytes of one plane of one slab (2 k8 groups)
-constexpr int TC_ASTAGE = 2 * TC_APLANE;                            // hi + lo
-static_assert(3 * TC_ASTAGE <= WRK_F * 4, "A slab stages do not fit the work buffer");
+constexpr int TC_LOADW = 6;                                         // warps 0..5 stage A (2 threads per source row, <= 96 rows)
+constexpr int TC_ISSUER = 7 * 32;                                   // lane 0 of warp 7 issues the MMAs and does nothing else
 
-__device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned pos0, int b, int t_lo, int n_out, int rank,
-                                        float* scr_rows) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+// (descriptor start-address field, i.e. address >> 4) of every weight slab of block li, tap-major: S.tc_baddr[tap * nslab + ks].
+// One division chain per entry, computed by 96 threads in parallel, OFF the single-thread MMA issue path.
+__device__ __forceinline__ void pyr_tc_table(const DecParams& P, Smem& S, int li, unsigned pos0) {
     const DecLayer& l = P.L[li];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int nslab = l.cin / 16, spc = l.krows / 16, spr = spc / 8, slab_f = 16 * l.ns;
+    const int sid = (int)threadIdx.x;
+    if (sid < l.ntaps * nslab) {
+        const int c = sid / spc, wi = sid - c * spc, reg = wi / spr, jj = wi - reg * spr;
+        S.tc_baddr[sid] = (smem_u32(&S.ring[(pos0 + c) % DEC_NSLOT][reg][jj * slab_f]) & 0x3FFFFu) >> 4;
+    }
+}
+
+// The slab pipeline has no block barrier: the loader warps fill stage s and arrive on abar[s]; the issuer thread waits for
+// abar[s], issues the 3 x ntaps MMAs of the slab and commits them to sbar[s], which the loaders wait for before they overwrite
+// the stage.  Slabs are numbered through the whole launch (st.tcq): slab q lives in stage q % TC_NSTG and is that stage's
+// (q / TC_NSTG)-th use, which gives every wait its phase parity without any shared counter.
+__device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned q0, unsigned acc_use, int b, int t_lo, int n_out,
+                                        int rank, float* scr_rows) {
+    const DecLayer& l = P.L[li];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int halo = (l.ntaps - 1) * l.rate, n_src = n_out + halo;   // <= 96
     const int nslab = l.cin / 16, ns = l.ns;
-    const int spc = l.krows / 16, spr = spc / 8;                     // weight slabs per chunk / per warp region
-    const int slab_f = 16 * ns;                                      // floats per weight slab (2 planes x 2 k8 x ns x 16 B)
-    const float* in = P.in_hist[li];
     unsigned char* As = reinterpret_cast<unsigned char*>(S.wrk);
-    const bool loader = tid < 2 * n_src;
-    const int s_row = tid >> 1, h8 = tid & 1;
-    const int t_src = t_lo - halo + s_row;
-    const float* src = in + ((size_t)b * P.T + (t_src < 0 ? 0 : t_src)) * l.ldin + h8 * 8;
-    const bool have = loader && t_src >= 0;
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-    if (have) { r0 = ldcg4(src); r1 = ldcg4(src + 4); }
-    const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ns);
+    unsigned use = q0 / TC_NSTG;
+    int stg = (int)(q0 - use * TC_NSTG);
     const uint32_t tacc = S.tmem_base;
-    for (int ks = 0; ks < nslab; ++ks) {
-        const int stg = ks % 3;
-        const unsigned used = S.tc_use[stg];                         // written by thread 32 >= 3 block barriers ago
-        if (used > 0) mbar_wait(bar64(&S.sbar[stg]), (used - 1) & 1u);   // the MMAs that read this stage are done
-        if (loader) {
-            const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            __align__(16) __half hi[8];
-            __align__(16) __half lo[8];
+    if (warp < TC_LOADW) {
+        const float* in = P.in_hist[li];
+        const bool loader = tid < 2 * n_src;
+        const int s_row = tid >> 1, h8 = tid & 1;
+        const int t_src = t_lo - halo + s_row;
+        const float* src = in + ((size_t)b * P.T + (t_src < 0 ? 0 : t_src)) * l.ldin + h8 * 8;
+        const bool have = loader && t_src >= 0;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (have) { r0 = ldcg4(src); r1 = ldcg4(src + 4); }
+        unsigned char* dst0 = As + h8 * (TC_RA * 16) + s_row * 16;
+#pragma unroll 1
+        for (int ks = 0; ks < nslab; ++ks) {
+            if (use > 0) mbar_wait(bar64(&S.sbar[stg]), (use - 1) & 1u);   // the MMAs that read this stage are done
+            if (loader) {
+                const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                __align__(16) __half hi[8];
+                __align__(16) __half lo[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { hi[i] = __float2half_rn(v[i]); lo[i] = __float2half_rn(v[i] - __half2float(hi[i])); }
-            unsigned char* dst = As + stg * TC_ASTAGE + h8 * (TC_RA * 16) + s_row * 16;
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-            *reinterpret_cast<uint4*>(dst + TC_APLANE) = *reinterpret_cast<const uint4*>(lo);
+                for (int i = 0; i < 8; ++i) { hi[i] = __float2half_rn(v[i]); lo[i] = __float2half_rn(v[i] - __half2float(hi[i])); }
+                unsigned char* dst = dst0 + stg * TC_ASTAGE;
+                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(dst + TC_APLANE) = *reinterpret_cast<const uint4*>(lo);
+            }
+            if (have && ks + 1 < nslab) { r0 = ldcg4(src + (ks + 1) * 16); r1 = ldcg4(src + (ks + 1) * 16 + 4); }
+            fence_proxy_async_smem();                                 // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar64(&S.abar[stg]));
+            if (++stg == TC_NSTG) { stg = 0; ++use; }
         }
-        if (have && ks + 1 < nslab) { r0 = ldcg4(src + (ks + 1) * 16); r1 = ldcg4(src + (ks + 1) * 16 + 4); }
-        fence_proxy_async_smem();                                     // generic-proxy stores -> visible to the tensor core's reads
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 32) {
+    } else if (tid == TC_ISSUER) {
+        const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ns);
+        const uint64_t dA0 = umma_desc_noswz(0, TC_RA * 16, 128), dB0 = umma_desc_noswz(0, (uint32_t)ns * 16, 128);
+        const uint32_t a_base = (smem_u32(As) & 0x3FFFFu) >> 4, tap_step = (uint32_t)l.rate, lo_a = TC_APLANE >> 4, lo_b = (uint32_t)ns * 2;
+        const int ntaps = l.ntaps;
+#pragma unroll 1
+        for (int ks = 0; ks < nslab; ++ks) {
+            mbar_wait(bar64(&S.abar[stg]), use & 1u);                 // the slab is staged (all loader warps arrived)
             tc_fence_after();
-            const uint32_t a0 = smem_u32(As + stg * TC_ASTAGE);
-            for (int tap = 0; tap < l.ntaps; ++tap) {
-                const uint32_t aa = a0 + (uint32_t)(tap * l.rate * 16);
-                const uint64_t dAh = umma_desc_noswz(aa, TC_RA * 16, 128), dAl = umma_desc_noswz(aa + TC_APLANE, TC_RA * 16, 128);
-                const int sid = tap * nslab + ks;                     // weight slab of (tap, channels ks*16..)
-                const int c = sid / spc, wi = sid - c * spc, reg = wi / spr, jj = wi - reg * spr;
-                const uint32_t bb = smem_u32(&S.ring[(pos0 + c) % DEC_NSLOT][reg][jj * slab_f]);
-                const uint64_t dBh = umma_desc_noswz(bb, (uint32_t)ns * 16, 128), dBl = umma_desc_noswz(bb + (uint32_t)ns * 32, (uint32_t)ns * 16, 128);
+            uint32_t aa = a_base + (uint32_t)stg * (TC_ASTAGE >> 4);
+            const uint32_t* bt = &S.tc_baddr[ks];
+#pragma unroll 1
+            for (int tap = 0; tap < ntaps; ++tap, aa += tap_step, bt += nslab) {
+                const uint32_t bb = *bt;
+                const uint64_t dAh = dA0 | aa, dAl = dA0 | (aa + lo_a), dBh = dB0 | bb, dBl = dB0 | (bb + lo_b);
                 tc_mma_f16(tacc, dAh, dBh, idesc, (ks | tap) != 0);
                 tc_mma_f16(tacc, dAh, dBl, idesc, 1u);
                 tc_mma_f16(tacc, dAl, dBh, idesc, 1u);
             }
             tc_commit(bar64(&S.sbar[stg]));                           // the stage may be overwritten once these MMAs have read it
-            if (ks == nslab - 1) tc_commit(bar64(&S.dbar));           // accumulator complete
-            S.tc_use[stg] = used + 1;
+            if (++stg == TC_NSTG) { stg = 0; ++use; }
         }
+        tc_commit(bar64(&S.dbar));                                    // accumulator complete
     }
     // epilogue: thread == output row (TMEM lane); pre-LN slice (+ bias) -> scratch
-    const unsigned dused = S.tc_use[3];                               // read before the barrier below, bumped after it
     if (warp < 4) {
-        mbar_wait(bar64(&S.dbar), dused & 1u);
+        mbar_wait(bar64(&S.dbar), acc_use & 1u);
         tc_fence_after();
         const int m = tid;
         const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
@@ -666,7 +568,6 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
         tc_fence_before();
     }
     __syncthreads();                                                  // the accumulator has been read: the next utterance may overwrite it
-    if (tid == 32) S.tc_use[3] = dused + 1;
 }
 
 // LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
@@ -751,13 +652,13 @@ __device__ __noinline__ Stream prepass(const DecParams& P, Smem& S, Stream st, i
                 __syncwarp();
                 const PreRows rl = pre_rows(S, G, j, l.prow);
                 if (rl.n > 0) {
+                    pyr_tc_table(P, S, lp, st.pos);
+                    __syncthreads();
                     for (int g = 0; g < G; ++g) {
                         if (!((rl.mask >> g) & 1u)) continue;
                         float* rows = scr + (size_t)pre_off_of(rl, g) * 512;
-                        if (P.tc_pre) pyr_tc_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
-                        else if (rl.n <= GMAX) pyr_small_utt(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
-                        else if (l.ns == 32) pyr_gemm_utt<4>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
-                        else pyr_gemm_utt<2>(P, S, lp, st.pos, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        pyr_tc_utt(P, S, lp, st.tcq, st.tca, b0 + g, rl.t_lo, rl.n, rank, rows);
+                        st.tcq += l.cin / 16; st.tca++;
                     }
                 }
                 __syncthreads();                          // every warp is done with every region of these chunks
@@ -778,7 +679,7 @@ __device__ __noinline__ Stream prepass(const DecParams& P, Smem& S, Stream st, i
             return st;
 }
 
-template <bool PROF>
+template <bool PROF, int GT>
 __global__ void __cluster_dims__(DEC_NC, 1, 1) __launch_bounds__(DEC_THREADS, 1)
 decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -801,23 +702,22 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
         for (int s = 0; s < DEC_NSLOT; ++s)
             for (int w = 0; w < NWARP; ++w) mbar_init(bar64(&S.fullw[s][w]), 1);
         mbar_init(bar64(&S.gbar[0]), 1); mbar_init(bar64(&S.gbar[1]), 1);
-        for (int i = 0; i < 3; ++i) mbar_init(bar64(&S.sbar[i]), 1);
+        for (int i = 0; i < TC_NSTG; ++i) { mbar_init(bar64(&S.sbar[i]), 1); mbar_init(bar64(&S.abar[i]), TC_LOADW); }
         mbar_init(bar64(&S.dbar), 1);
         fence_mbar_init();
     }
-    if (P.tc_pre && warp == 0) tmem_alloc<32>(&S.tmem_base);          // 128 lanes x 32 fp32 columns: the pre-pass accumulator
+    if (warp == 0) tmem_alloc<32>(&S.tmem_base);          // 128 lanes x 32 fp32 columns: the pre-pass accumulator
     for (int i = tid; i < 2 * GMAX * XLD; i += NT) (&S.xin[0][0][0])[i] = 0.f;
     for (int i = tid; i < 2 * NC * PLD; i += NT) (&S.pre[0][0][0])[i] = 0.f;
     if (tid < GMAX) { S.p_cur[tid] = 0; S.p_prev[tid] = 0; S.p_next[tid] = 0; S.moved[tid] = 0; }
     if (tid < 2) S.fmoved[tid] = 0;
     if (tid < 16) S.prof[tid] = 0;
-    if (tid < 4) S.tc_use[tid] = 0;
     if (tid == 0) { S.n_moved_frames = 0; S.n_moved_utt = 0; }
     __syncthreads();
 
     Stream st;
     st.base = P.wstream + (size_t)rank * P.stream_len;
-    st.cons = Cur{0, 0, 0}; st.prod = Cur{0, 0, 0}; st.pos = 0;
+    st.prod = Cur{0, 0, 0}; st.pos = 0; st.tcq = 0; st.tca = 0;
     for (int s = 0; s < DEC_NSLOT; ++s) {                // the first chunks are AudioEnc chunks of frame 0 (nch_enc > DEC_NSLOT)
         if (lane == 0) stream_issue(P, S, st, st.prod, s, warp);
         cur_next(P, S, st.prod);
@@ -828,7 +728,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
 
     int cb = 0;
     unsigned lcount = 0;
-    if (P.tc_pre) { tc_fence_before(); __syncthreads(); tc_fence_after(); }
+    tc_fence_before(); __syncthreads(); tc_fence_after();
     if (tid == 0) S.prof_last = clock64();
     for (int j = 0; j < P.steps; ++j) {
         if (tid < GMAX) S.moved[tid] = (tid < G && j > 0 && S.p_cur[tid] != S.p_prev[tid]) ? 1 : 0;
@@ -862,7 +762,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
 
         if (any_moved) st = prepass<PROF>(P, S, st, j, b0, G, rank, scr);
         }   // li == n_enc
-        cb = layer_row<PROF>(P, S, st, li, j, b0, G, rank, cb, lcount);
+        cb = layer_row<PROF, GT>(P, S, st, li, j, b0, G, rank, cb, lcount);
         }   // blocks
 
         __syncthreads();
@@ -875,19 +775,39 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
     if (PROF && P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
     cp_async_wait<0>();
     cluster_sync_all();                                   // no CTA exits while a peer may still write into its shared memory
-    if (P.tc_pre && warp == 0) tmem_dealloc<32>(S.tmem_base);
+    if (warp == 0) tmem_dealloc<32>(S.tmem_base);
 }
 
 size_t decode_smem_bytes() { return sizeof(Smem) + 128; }
 
-static cudaError_t decode_prepare() {
-    cudaError_t e = cudaSuccess;
-    for (auto* k : {decode_cluster_kernel<false>, decode_cluster_kernel<true>}) {
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes());
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return e;
+using DecKernel = void (*)(DecParams);
+// one instantiation per (lap timers, utterances per cluster); exactly one of them runs in a launch
+static DecKernel decode_kernel_of(bool prof, int G) {
+    switch (G) {
+        case 1: return prof ? decode_cluster_kernel<true, 1> : decode_cluster_kernel<false, 1>;
+        case 2: return prof ? decode_cluster_kernel<true, 2> : decode_cluster_kernel<false, 2>;
+        case 3: return prof ? decode_cluster_kernel<true, 3> : decode_cluster_kernel<false, 3>;
+        case 4: return prof ? decode_cluster_kernel<true, 4> : decode_cluster_kernel<false, 4>;
+        default: return prof ? decode_cluster_kernel<true, 5> : decode_cluster_kernel<false, 5>;
     }
+}
+static_assert(DEC_GMAX == 5, "decode_kernel_of: one instantiation per utterance count");
+
+static cudaError_t decode_prepare() {
+    static std::atomic<bool> done[64];                    // per device: the attributes stick to the (device, function) pair
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+    for (int G = 1; G <= DEC_GMAX; ++G)
+        for (int prof = 0; prof < 2; ++prof) {
+            DecKernel k = decode_kernel_of(prof != 0, G);
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)decode_smem_bytes());
+            if (e != cudaSuccess) return e;
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+    if (dev >= 0 && dev < 64) done[dev].store(true, std::memory_order_release);
     return e;
 }
 
@@ -899,17 +819,18 @@ int decode_max_active_clusters() {
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = DEC_NC; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, decode_cluster_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, decode_kernel_of(false, DEC_GMAX), &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
     return n;
 }
 
 cudaError_t launch_decode_cluster(const DecParams& p, int n_clusters, cudaStream_t s) {
     cudaError_t e = decode_prepare();                     // per call: the attribute is per device, handles may live on several
     if (e != cudaSuccess) return e;
+    if (p.G < 1 || p.G > DEC_GMAX) return cudaErrorInvalidValue;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(n_clusters * DEC_NC); cfg.blockDim = dim3(DEC_THREADS); cfg.dynamicSmemBytes = decode_smem_bytes(); cfg.stream = s;
     cfg.attrs = nullptr; cfg.numAttrs = 0;               // cluster dims are compiled in (__cluster_dims__)
-    return p.prof ? cudaLaunchKernelEx(&cfg, decode_cluster_kernel<true>, p) : cudaLaunchKernelEx(&cfg, decode_cluster_kernel<false>, p);
+    return cudaLaunchKernelEx(&cfg, decode_kernel_of(p.prof != nullptr, p.G), p);
 }
 
 }  // namespace dctts

@@ -9,7 +9,7 @@
 namespace dctts {
 
 constexpr int DEC_NC = 16;          // CTAs per cluster (non-portable cluster size)
-constexpr int DEC_GMAX = 4;         // utterances per cluster
+constexpr int DEC_GMAX = 5;         // utterances per cluster (7 clusters of 16 CTAs are co-resident on a B200: 35 >= the benchmark's 32)
 constexpr int DEC_THREADS = 256;
 constexpr int DEC_NSLOT = 3;        // ring slots
 constexpr int DEC_REG_F = 1536;     // floats per warp region of a slot (6 KB): every warp streams and frees its own k-rows
@@ -53,7 +53,6 @@ struct DecParams {
     long long* prof;                   // optional [16] SM-clock lap timers of cluster 0 / rank 0 (option decode_prof), else nullptr
     int nl, n_enc, nch, nch_enc, pyr_ch0, pyr_ch1, stream_len;   // pyr_ch0..pyr_ch1: chunks of the AudioDec blocks with prow > 1
     int B, G, T, N, d, n_mels, win_size, steps;
-    int tc_pre;                        // 1: the receptive-field pre-pass runs on tcgen05 (split-fp16 3-MMA), 0: fp32 FMA
 };
 static_assert(sizeof(DecParams) <= 4000, "DecParams must fit the kernel parameter space");
 

@@ -192,11 +192,10 @@ int dctts_set_tensor_path(dctts_handle h, int32_t mode);
 /* Kernel-variant switches (every value is a parity-tested code path; defaults = measured best):
  *   "decode_mode"  1 = the whole AR loop (synthesize.py:45-54) as ONE persistent cluster kernel (default),
  *                  0 = one captured CUDA graph per mel frame (round-1 path)
- *   "decode_prepass" persistent decode, recompute of the AudioDec receptive field after a window move:
- *                  1 = tcgen05 (split-fp16 operands, 3 MMAs, fp32 accumulate in tensor memory; default), 0 = fp32 FMA GEMM
  *   "tc_occ2" 0/1, "tc_cg2" 0/1/2, "tc_tile_pair" 0/1, "tc_mcast" 0/1, "tc_resid_tma" 0/1: tcgen05 block kernel variants
  *   "fused_ln" 0/1: graph decode, GEMM + LN in one launch;  "tc_debug" 0/1;  "decode_prof" 0/1;  "pdl" 0/1 (process-wide)
- * dctts_get_option also answers "decode_available" (1 when this handle / device can run the persistent decode). */
+ * dctts_get_option also answers "decode_available" (1 when this handle / device can run the persistent decode) and
+ * "decode_max_clusters" (16-CTA clusters of the decode kernel that are co-resident on this device; 7 on a B200). */
 int dctts_set_option(dctts_handle h, const char* name, int32_t value);
 int dctts_get_option(dctts_handle h, const char* name, int32_t* value);
 /* Of the last dctts_text2mel_generate on the persistent decode path: frames in which a cluster had to recompute the

@@ -66,4 +66,3 @@ def path(engine, request):
     yield request.param
     engine.set_tensor_path(1)
     engine.set_option("decode_mode", 1)
-    engine.set_option("decode_prepass", 1)

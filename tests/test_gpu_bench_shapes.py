@@ -19,9 +19,7 @@ B = 32
 def default_engine(engine):
     engine.set_tensor_path(1)
     engine.set_option("decode_mode", 1)
-    engine.set_option("decode_prepass", 1)
     yield engine
-    engine.set_option("decode_prepass", 1)
 
 
 def test_ssrn_config3_b32_t210(default_engine, params):
@@ -64,13 +62,12 @@ def _compare_prefix(Y, P, Yo, Po, margin, steps):
     return checked
 
 
-@pytest.mark.parametrize("decode_mode,prepass", [(1, 0), (1, 1), (0, 0)], ids=["cluster-fma", "cluster-tcgen05", "graph"])
-def test_generate_config4_b32_210_frames(default_engine, params, decode_mode, prepass):
+@pytest.mark.parametrize("decode_mode", [1, 0], ids=["cluster", "graph"])
+def test_generate_config4_b32_210_frames(default_engine, params, decode_mode):
     """The benchmark's own workload (32 synthetic 100-character utterances, 210 frames, free running): four
     utterances spread over different clusters are checked against the oracle's schedule (synthesize.py:45-57)."""
     e = default_engine
     e.set_option("decode_mode", decode_mode)
-    e.set_option("decode_prepass", prepass)
     try:
         L = synthetic_text(B, 100, seed=0)
         rows = [0, 9, 18, 31]
@@ -80,7 +77,8 @@ def test_generate_config4_b32_210_frames(default_engine, params, decode_mode, pr
         assert checked >= 2 * hp.max_T                              # not everything may hide behind a tie
         if decode_mode == 1:
             frames, utt, clusters = e.decode_stats()
-            assert clusters == 8 and 0 < utt <= B * hp.max_T and frames <= clusters * hp.max_T
+            # every cluster co-resident: 7 clusters of 16 CTAs fit a B200, so 32 utterances go 5 per cluster
+            assert clusters <= e.get_option("decode_max_clusters") and 0 < utt <= B * hp.max_T and frames <= clusters * hp.max_T
             # the recompute count must equal the number of window moves of the whole batch
             Pn = P.cpu().numpy()
             assert utt == int((np.diff(Pn, axis=1) != 0).sum())
@@ -96,15 +94,13 @@ def test_generate_config2_b1_210_frames(default_engine, params):
     assert _compare_prefix(Y.cpu().numpy(), P.cpu().numpy(), Yo, Po, margin, hp.max_T) >= 100
 
 
-@pytest.mark.parametrize("prepass", [0, 1], ids=["fma", "tcgen05"])
-@pytest.mark.parametrize("Bn", [2, 3, 5, 13])
-def test_cluster_decode_equals_graph_decode(default_engine, Bn, prepass):
-    """Ragged group sizes (last cluster partly filled, G = 1 and G = 2): the persistent kernel and the
+@pytest.mark.parametrize("Bn", [2, 3, 5, 8, 13, 17, 23])
+def test_cluster_decode_equals_graph_decode(default_engine, Bn):
+    """Ragged group sizes (last cluster partly filled, 1 to 4 utterances per cluster): the persistent kernel and the
     graph-per-frame loop follow the same windows and agree to float32 re-association noise."""
     e = default_engine
     L = np.concatenate([synthetic_text(1, 30 + 11 * i, seed=100 + i) for i in range(Bn)])
     steps = 70
-    e.set_option("decode_prepass", prepass)
     Y1, P1, _, _ = e.text2mel_generate(L, steps=steps)
     e.set_option("decode_mode", 0)
     try:

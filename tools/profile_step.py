@@ -15,13 +15,11 @@ ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--tensor-path", type=int, default=1)
 ap.add_argument("--no-ssrn", action="store_true")
 ap.add_argument("--decode-mode", type=int, default=1, help="1 persistent cluster decode kernel, 0 one CUDA graph per frame")
-ap.add_argument("--prepass", type=int, default=1, help="persistent decode: 1 = tcgen05 receptive-field pre-pass")
 a = ap.parse_args()
 e = Engine(0)
 e.load_params(init_params(0, "perturbed"))
 e.set_tensor_path(a.tensor_path)
 e.set_option("decode_mode", a.decode_mode)
-e.set_option("decode_prepass", a.prepass)
 L = synthetic_text(a.batch, 100, seed=0)
 for it in range(2):
     torch.cuda.nvtx.range_push("pass%d" % it)

@@ -38,11 +38,9 @@ if "attention" in what:
     torch.cuda.synchronize(); print("attention ok", flush=True)
 L = synthetic_text(3, 60, seed=0)
 if "decode" in what:
-    for pre in (1, 0):
-        e.set_option("decode_mode", 1); e.set_option("decode_prepass", pre)
-        Y, P, _, _ = e.text2mel_generate(L, steps=8)
-        torch.cuda.synchronize(); print("cluster decode ok (prepass %d); windows" % pre, P[:, :8].tolist(), e.decode_stats(), flush=True)
-    e.set_option("decode_prepass", 1)
+    e.set_option("decode_mode", 1)
+    Y, P, _, _ = e.text2mel_generate(L, steps=8)
+    torch.cuda.synchronize(); print("cluster decode ok; windows", P[:, :8].tolist(), e.decode_stats(), flush=True)
 if "graph" in what:
     e.set_option("decode_mode", 0)
     Y, P, _, _ = e.text2mel_generate(L, steps=4)
