@@ -99,7 +99,7 @@ def test_cluster_decode_equals_graph_decode(default_engine, Bn):
     """Ragged group sizes (last cluster partly filled, 1 to 4 utterances per cluster): the persistent kernel and the
     graph-per-frame loop follow the same windows and agree to float32 re-association noise."""
     e = default_engine
-    L = np.concatenate([synthetic_text(1, 30 + 11 * i, seed=100 + i) for i in range(Bn)])
+    L = np.concatenate([synthetic_text(1, 30 + (11 * i) % 140, seed=100 + i) for i in range(Bn)])
     steps = 70
     Y1, P1, _, _ = e.text2mel_generate(L, steps=steps)
     e.set_option("decode_mode", 0)
