@@ -444,15 +444,16 @@ __device__ __forceinline__ uint64_t umma_desc_noswz(uint32_t addr, uint32_t lbo_
     d |= 1ull << 46;                                                // descriptor version (sm_100); layout type 0 = no swizzle
     return d;
 }
-constexpr int TC_LOADW = 6;                                         // warps 0..5 stage A (2 threads per source row, <= 96 rows)
-constexpr int TC_ISSUER = 7 * 32;                                   // lane 0 of warp 7 issues the MMAs and does nothing else
+constexpr int TC_LOADW = 3;                                         // warps 0..2 stage A (one thread per source row, <= 96 rows)
+constexpr int TC_NISS = 3;                                          // lane 0 of warps 3, 4, 5: one MMA issuer per split-fp16 product
+constexpr int TC_COLS = 128;                                        // tensor-memory columns: three 32-column accumulators (power of two)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
 // (descriptor start-address field, i.e. address >> 4) of every weight slab of block li, tap-major: S.tc_baddr[tap * nslab + ks].
-// One division chain per entry, computed by 96 threads in parallel, OFF the single-thread MMA issue path.
+// One division chain per entry, computed by 96 threads in parallel, OFF the single-thread MMA issue paths.
 __device__ __forceinline__ void pyr_tc_table(const DecParams& P, Smem& S, int li, unsigned pos0) {
     const DecLayer& l = P.L[li];
     const int nslab = l.cin / 16, spc = l.krows / 16, spr = spc / 8, slab_f = 16 * l.ns;
@@ -463,10 +464,13 @@ __device__ __forceinline__ void pyr_tc_table(const DecParams& P, Smem& S, int li
     }
 }
 
-// The slab pipeline has no block barrier: the loader warps fill stage s and arrive on abar[s]; the issuer thread waits for
-// abar[s], issues the 3 x ntaps MMAs of the slab and commits them to sbar[s], which the loaders wait for before they overwrite
-// the stage.  Slabs are numbered through the whole launch (st.tcq): slab q lives in stage q % TC_NSTG and is that stage's
-// (q / TC_NSTG)-th use, which gives every wait its phase parity without any shared counter.
+// The slab pipeline has no block barrier.  Loader warps fill stage s and arrive on abar[s].  THREE issuer threads (in three
+// warps, so on three schedulers) wait for abar[s]; issuer i issues product i of the split-fp16 scheme for every tap --
+// 0: hi x Whi, 1: hi x Wlo, 2: lo x Whi -- into ITS OWN 32-column accumulator and commits to sbar[s] (count 3), which the
+// loaders wait for before they overwrite the stage.  One thread issuing all nine MMAs of a slab was the bottleneck of the
+// whole pre-pass (ncu: the loaders spent their time waiting for the stage to be released).  Slabs are numbered through the
+// whole launch (st.tcq): slab q lives in stage q % TC_NSTG and is that stage's (q / TC_NSTG)-th use, which gives every wait
+// its phase parity without any shared counter.
 __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, unsigned q0, unsigned acc_use, int b, int t_lo, int n_out,
                                         int rank, float* scr_rows) {
     const DecLayer& l = P.L[li];
@@ -478,38 +482,57 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
     int stg = (int)(q0 - use * TC_NSTG);
     const uint32_t tacc = S.tmem_base;
     if (warp < TC_LOADW) {
-        const float* in = P.in_hist[li];
-        const bool loader = tid < 2 * n_src;
-        const int s_row = tid >> 1, h8 = tid & 1;
-        const int t_src = t_lo - halo + s_row;
-        const float* src = in + ((size_t)b * P.T + (t_src < 0 ? 0 : t_src)) * l.ldin + h8 * 8;
-        const bool have = loader && t_src >= 0;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        if (have) { r0 = ldcg4(src); r1 = ldcg4(src + 4); }
-        unsigned char* dst0 = As + h8 * (TC_RA * 16) + s_row * 16;
-#pragma unroll 1
-        for (int ks = 0; ks < nslab; ++ks) {
-            if (use > 0) mbar_wait(bar64(&S.sbar[stg]), (use - 1) & 1u);   // the MMAs that read this stage are done
-            if (loader) {
-                const float v[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                __align__(16) __half hi[8];
-                __align__(16) __half lo[8];
+        const bool loader = tid < n_src;
+        const int t_src = t_lo - halo + tid;
+        const float* src = P.in_hist[li] + ((size_t)b * P.T + (t_src < 0 ? 0 : t_src)) * l.ldin;
+        const bool have = loader && t_src >= 0;                      // rows before the utterance start: TF zero padding
+        // The loop is bound by the latency of the activation loads (L2, ~700 cycles), not by the conversion or the MMAs: each
+        // thread keeps FOUR slabs (4 x 64 bytes of its row) in flight in registers.  (nslab is 16 or 32.)
+        constexpr int PF = 4;
+        float4 r[PF][4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { hi[i] = __float2half_rn(v[i]); lo[i] = __float2half_rn(v[i] - __half2float(hi[i])); }
-                unsigned char* dst = dst0 + stg * TC_ASTAGE;
-                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-                *reinterpret_cast<uint4*>(dst + TC_APLANE) = *reinterpret_cast<const uint4*>(lo);
+        for (int u = 0; u < PF; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) r[u][i] = (have && u < nslab) ? ldcg4(src + u * 16 + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        unsigned char* dst0 = As + tid * 16;
+#pragma unroll 1
+        for (int ks0 = 0; ks0 < nslab; ks0 += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                if (ks0 + u < nslab) {
+                    if (use > 0) mbar_wait(bar64(&S.sbar[stg]), (use - 1) & 1u);   // the MMAs that read this stage are done
+                    if (loader) {
+                        unsigned char* dst = dst0 + stg * TC_ASTAGE;
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {              // the two 8-channel k groups of the slab
+                            const float4 p0 = r[u][2 * h8], p1 = r[u][2 * h8 + 1];
+                            const float v[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                            __align__(16) __half hi[8];
+                            __align__(16) __half lo[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) { hi[i] = __float2half_rn(v[i]); lo[i] = __float2half_rn(v[i] - __half2float(hi[i])); }
+                            *reinterpret_cast<uint4*>(dst + h8 * (TC_RA * 16)) = *reinterpret_cast<const uint4*>(hi);
+                            *reinterpret_cast<uint4*>(dst + h8 * (TC_RA * 16) + TC_APLANE) = *reinterpret_cast<const uint4*>(lo);
+                        }
+                    }
+                    if (have && ks0 + u + PF < nslab) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) r[u][i] = ldcg4(src + (ks0 + u + PF) * 16 + i * 4);
+                    }
+                    fence_proxy_async_smem();                         // generic-proxy stores -> visible to the tensor core's reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar64(&S.abar[stg]));
+                    if (++stg == TC_NSTG) { stg = 0; ++use; }
+                }
             }
-            if (have && ks + 1 < nslab) { r0 = ldcg4(src + (ks + 1) * 16); r1 = ldcg4(src + (ks + 1) * 16 + 4); }
-            fence_proxy_async_smem();                                 // generic-proxy stores -> visible to the tensor core's reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar64(&S.abar[stg]));
-            if (++stg == TC_NSTG) { stg = 0; ++use; }
         }
-    } else if (tid == TC_ISSUER) {
+    } else if (warp < TC_LOADW + TC_NISS && lane == 0) {
+        const int prod = warp - TC_LOADW;                            // 0: hi x Whi, 1: hi x Wlo, 2: lo x Whi
         const uint32_t idesc = umma_idesc_f16(128, (uint32_t)ns);
         const uint64_t dA0 = umma_desc_noswz(0, TC_RA * 16, 128), dB0 = umma_desc_noswz(0, (uint32_t)ns * 16, 128);
-        const uint32_t a_base = (smem_u32(As) & 0x3FFFFu) >> 4, tap_step = (uint32_t)l.rate, lo_a = TC_APLANE >> 4, lo_b = (uint32_t)ns * 2;
+        const uint32_t a_base = ((smem_u32(As) & 0x3FFFFu) >> 4) + (prod == 2 ? (TC_APLANE >> 4) : 0u);
+        const uint32_t b_plane = prod == 1 ? (uint32_t)ns * 2 : 0u, tap_step = (uint32_t)l.rate;
+        const uint32_t dacc = tacc + (uint32_t)prod * 32u;
         const int ntaps = l.ntaps;
 #pragma unroll 1
         for (int ks = 0; ks < nslab; ++ks) {
@@ -518,19 +541,14 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
             uint32_t aa = a_base + (uint32_t)stg * (TC_ASTAGE >> 4);
             const uint32_t* bt = &S.tc_baddr[ks];
 #pragma unroll 1
-            for (int tap = 0; tap < ntaps; ++tap, aa += tap_step, bt += nslab) {
-                const uint32_t bb = *bt;
-                const uint64_t dAh = dA0 | aa, dAl = dA0 | (aa + lo_a), dBh = dB0 | bb, dBl = dB0 | (bb + lo_b);
-                tc_mma_f16(tacc, dAh, dBh, idesc, (ks | tap) != 0);
-                tc_mma_f16(tacc, dAh, dBl, idesc, 1u);
-                tc_mma_f16(tacc, dAl, dBh, idesc, 1u);
-            }
-            tc_commit(bar64(&S.sbar[stg]));                           // the stage may be overwritten once these MMAs have read it
+            for (int tap = 0; tap < ntaps; ++tap, aa += tap_step, bt += nslab)
+                tc_mma_f16(dacc, dA0 | aa, dB0 | (*bt + b_plane), idesc, (ks | tap) != 0);
+            tc_commit(bar64(&S.sbar[stg]));                           // the stage may be overwritten once all three issuers' MMAs have read it
             if (++stg == TC_NSTG) { stg = 0; ++use; }
         }
-        tc_commit(bar64(&S.dbar));                                    // accumulator complete
+        tc_commit(bar64(&S.dbar));                                    // this product's accumulator is complete
     }
-    // epilogue: thread == output row (TMEM lane); pre-LN slice (+ bias) -> scratch
+    // epilogue: thread == output row (TMEM lane); the three partial accumulators summed, scaled, + bias -> scratch
     if (warp < 4) {
         mbar_wait(bar64(&S.dbar), acc_use & 1u);
         tc_fence_after();
@@ -538,10 +556,23 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
         const uint32_t taddr = tacc + ((uint32_t)(warp * 32) << 16);
         const float inv = P.inv_scale[li];
         float v[32];
-        if (ns == 32) { tmem_ld32_nowait(taddr, v); tmem_ld_wait(); }
-        else { float w16[16]; tmem_ld16(taddr, w16);
+        if (ns == 32) {
+            float w[32];
+            tmem_ld32_nowait(taddr, v); tmem_ld32_nowait(taddr + 32, w); tmem_ld_wait();
 #pragma unroll
-               for (int i = 0; i < 16; ++i) v[i] = w16[i]; }
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
+            tmem_ld32_nowait(taddr + 64, w); tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += w[i];
+        } else {
+            float w16[16], x16[16];
+            tmem_ld16(taddr, w16); tmem_ld16(taddr + 32, x16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = w16[i] + x16[i];
+            tmem_ld16(taddr + 64, x16);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += x16[i];
+        }
         if (m < n_out) {
             float* orow = scr_rows + (size_t)m * 512;
             const float* bs = P.bias[li];
@@ -567,7 +598,7 @@ __device__ __forceinline__ void pyr_tc_utt(const DecParams& P, Smem& S, int li, 
         }
         tc_fence_before();
     }
-    __syncthreads();                                                  // the accumulator has been read: the next utterance may overwrite it
+    __syncthreads();                                                  // the accumulators have been read: the next utterance may overwrite them
 }
 
 // LayerNorm / gate / highway mix of the refreshed rows: one warp per row over the whole cluster (parameters in S.red)
@@ -702,11 +733,11 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
         for (int s = 0; s < DEC_NSLOT; ++s)
             for (int w = 0; w < NWARP; ++w) mbar_init(bar64(&S.fullw[s][w]), 1);
         mbar_init(bar64(&S.gbar[0]), 1); mbar_init(bar64(&S.gbar[1]), 1);
-        for (int i = 0; i < TC_NSTG; ++i) { mbar_init(bar64(&S.sbar[i]), 1); mbar_init(bar64(&S.abar[i]), TC_LOADW); }
-        mbar_init(bar64(&S.dbar), 1);
+        for (int i = 0; i < TC_NSTG; ++i) { mbar_init(bar64(&S.sbar[i]), TC_NISS); mbar_init(bar64(&S.abar[i]), TC_LOADW); }
+        mbar_init(bar64(&S.dbar), TC_NISS);
         fence_mbar_init();
     }
-    if (warp == 0) tmem_alloc<32>(&S.tmem_base);          // 128 lanes x 32 fp32 columns: the pre-pass accumulator
+    if (warp == 0) tmem_alloc<TC_COLS>(&S.tmem_base);          // 128 lanes x 32 fp32 columns: the pre-pass accumulator
     for (int i = tid; i < 2 * GMAX * XLD; i += NT) (&S.xin[0][0][0])[i] = 0.f;
     for (int i = tid; i < 2 * NC * PLD; i += NT) (&S.pre[0][0][0])[i] = 0.f;
     if (tid < GMAX) { S.p_cur[tid] = 0; S.p_prev[tid] = 0; S.p_next[tid] = 0; S.moved[tid] = 0; }
@@ -775,7 +806,7 @@ decode_cluster_kernel(const __grid_constant__ DecParams Pc) {
     if (PROF && P.prof && cluster == 0 && rank == 0 && tid < 16) P.prof[tid] = S.prof[tid];
     cp_async_wait<0>();
     cluster_sync_all();                                   // no CTA exits while a peer may still write into its shared memory
-    if (warp == 0) tmem_dealloc<32>(S.tmem_base);
+    if (warp == 0) tmem_dealloc<TC_COLS>(S.tmem_base);
 }
 
 size_t decode_smem_bytes() { return sizeof(Smem) + 128; }
