@@ -96,7 +96,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // first three versions of this kernel spent 60 % of their time there (ptxas must report a 0-byte stack frame).
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 // the per-frame path: ex2.approx + rcp (2 ulp each; far inside the 1e-3 budget, half the instructions)
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.0f + __expf(-x)); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
     const int sz = valid ? 16 : 0;                                   // 0: zero fill (TF zero padding of the causal conv)
@@ -198,9 +198,12 @@ __device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const 
     const float* w = wreg + ((size_t)((sg * kper) >> 2) * ns + n) * 4;
     const float* xs = x + sg * kper;
     const int wstep = ns * 4;
-    float acc2[GT];
+    // packed fp32 FMA (FFMA2, new on sm_100): one instruction multiplies two consecutive k of the column -- half the issue
+    // slots of the fma pipe, which two warps per scheduler otherwise saturate (ncu: the GEMV was fma-pipe bound at G = 5).
+    // Four partial sums per utterance (k mod 4 = {0,1} and {2,3} of either float4), added at the end.
+    float2 p0[GT], p1[GT];
 #pragma unroll
-    for (int g = 0; g < GT; ++g) acc2[g] = 0.f;
+    for (int g = 0; g < GT; ++g) { p0[g] = make_float2(acc[g], 0.f); p1[g] = make_float2(0.f, 0.f); }
 #pragma unroll 2
     for (int k = 0; k < kper; k += 8) {
         const float4 w0 = *reinterpret_cast<const float4*>(w);
@@ -210,14 +213,16 @@ __device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const 
         for (int g = 0; g < GT; ++g) {
             const float4 x0 = *reinterpret_cast<const float4*>(xs + g * XLD + k);
             const float4 x1 = *reinterpret_cast<const float4*>(xs + g * XLD + k + 4);
-            float a = acc[g], c = acc2[g];
-            a = fmaf(x0.x, w0.x, a); a = fmaf(x0.y, w0.y, a); a = fmaf(x0.z, w0.z, a); a = fmaf(x0.w, w0.w, a);
-            c = fmaf(x1.x, w1.x, c); c = fmaf(x1.y, w1.y, c); c = fmaf(x1.z, w1.z, c); c = fmaf(x1.w, w1.w, c);
-            acc[g] = a; acc2[g] = c;
+            float2 a = p0[g], c = p1[g];
+            a = __ffma2_rn(make_float2(x0.x, x0.y), make_float2(w0.x, w0.y), a);
+            c = __ffma2_rn(make_float2(x1.x, x1.y), make_float2(w1.x, w1.y), c);
+            a = __ffma2_rn(make_float2(x0.z, x0.w), make_float2(w0.z, w0.w), a);
+            c = __ffma2_rn(make_float2(x1.z, x1.w), make_float2(w1.z, w1.w), c);
+            p0[g] = a; p1[g] = c;
         }
     }
 #pragma unroll
-    for (int g = 0; g < GT; ++g) acc[g] += acc2[g];
+    for (int g = 0; g < GT; ++g) acc[g] = (p0[g].x + p0[g].y) + (p1[g].x + p1[g].y);
 }
 
 
