@@ -324,6 +324,51 @@ def run_b200(args, rank, local_rank, world):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = total * T * e2e_steps / float(te.item())
 
+    # ---- BASELINE config 5: Text2Mel training step -- forward with dropout, losses, backward, clip, Adam -- at the
+    # benchmark batch per GPU, data parallel over the launched ranks (NCCL all-reduce of the flat gradient arena); own handle
+    # (a trained handle stops using the packed synthesis weights).  Not part of `value`.
+    train = None
+    if args.train_steps > 0:
+        teng = Engine(local_rank)
+        teng.load_params(init_params(0))
+        teng.set_option("train_tc", args.train_tc)
+        teng.train_init(B)
+        mels = torch.from_numpy(np.random.default_rng(rank).uniform(0, 1, (B, T, hp.n_mels)).astype(np.float32)).to(dev)
+        grads = teng.train_grads()
+
+        def tstep(i):
+            o = teng.train_step(L_dev, mels, global_step=4000 + i, seed=i * world + rank, apply=(world == 1))
+            if world > 1:
+                dist.all_reduce(grads)
+                grads.mul_(1.0 / world)
+                teng.train_apply(4000 + i)
+            return o
+        for i in range(3):
+            first = tstep(i)
+        barrier()
+        n0 = teng.launch_count()
+        ta, tb = ev(), ev()
+        ta.record()
+        for i in range(args.train_steps):
+            last = tstep(3 + i)
+        tb.record()
+        barrier()
+        tt = torch.tensor([ta.elapsed_time(tb) / args.train_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tms = float(tt.item())
+        tfl = 3 * 2 * B * (hp.max_N * MAC_TEXTENC_PER_CHAR + T * (MAC_AUDIOENC_PER_FRAME + MAC_AUDIODEC_PER_FRAME))   # fwd MACs x 2 x 3 GEMMs
+        train = {"config": "BASELINE config 5: Text2Mel train step (fwd + bwd + clip + Adam), B=%d per GPU, N=180, T=210, dropout %.2f, "
+                           "dp%d (all-reduce of %d gradients)" % (B, hp.dropout_rate, world, grads.numel()),
+                 "ms_per_step": tms, "steps_per_sec": 1e3 / tms, "mel_frames_per_sec": world * B * T * 1e3 / tms, "steps": args.train_steps,
+                 "achieved_tflops": world * tfl / (tms * 1e-3) / 1e12, "gpu_launches_per_step": (teng.launch_count() - n0) // args.train_steps,
+                 "dtype": ("f32 tensors; forward / data-gradient / weight-gradient GEMMs as split-fp16 x3 on tcgen05, fp32 accumulate"
+                           if args.train_tc else "f32 (CUDA-core kernels)"),
+                 "loss_first": first["loss"], "loss_last": last["loss"], "scaling": "weak"}
+        teng.close()
+        del teng, grads, mels
+        torch.cuda.empty_cache()
+
     if rank == 0:
         peaks = measured_peaks()
         tensor = args.tensor_path != 0
@@ -440,6 +485,8 @@ def run_b200(args, rank, local_rank, world):
             line["next_row_vocoder"] = voc
         if cpu:
             line["cpu_baseline"] = cpu
+        if train:
+            line["train_config5"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -459,6 +506,8 @@ def main():
     ap.add_argument("--gather-chunks", type=int, default=4, help="N > 1: SSRN / gather chunks per rank (transfer of a chunk runs under the next chunk's SSRN)")
     ap.add_argument("--no-parity-check", dest="parity_check", action="store_false", help="skip the oracle check of the timed output")
     ap.add_argument("--tensor-path", type=int, default=1, choices=[0, 1], help="1 = tcgen05 blocks (default), 0 = fp32 CUDA-core kernels only")
+    ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the BASELINE config 5 training step reported as train_config5 (0 = skip)")
+    ap.add_argument("--train-tc", type=int, default=7, help="training GEMMs on tcgen05, bit mask (1 forward, 2 data gradient, 4 weight gradient); 0 = fp32 CUDA cores")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

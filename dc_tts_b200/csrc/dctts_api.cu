@@ -132,6 +132,7 @@ struct dctts_handle_s {
         LayerDev* l = nullptr; int li = 0; long long rows = 0; int L = 0, L_in = 0, ld_out = 0; const float* in = nullptr; int ld_in = 0;
         float* pre = nullptr; float* out = nullptr; int extra_shift = 0; bool need_dgrad = true;
         float *dW = nullptr, *dbias = nullptr, *dg1 = nullptr, *db1 = nullptr, *dg2 = nullptr, *db2 = nullptr;
+        GemmTcSlots tc_slots;      // abs-max slots of this block's input and weights, set by the forward GEMM of the current step
     };
     struct TrainTensor { float* p; float* g; float* m; float* v; long long n; int layout, d0, d1, d2, ld; };
     struct {
@@ -140,6 +141,8 @@ struct dctts_handle_s {
         std::map<std::string, TrainTensor> tensors;            // by TF variable name
         DevBuf pre, out, emb, R, align, dS, gbuf[4], dy, wT, zeros, gts, sums, ids, grads, mom, vel, entries;
         long long n_grad = 0; int n_entries = 0; float* d_table = nullptr;
+        DevBuf tc_a_hi, tc_a_lo, tc_b_hi, tc_b_lo, tc_slots;    // operand planes of the tcgen05 training GEMMs (kernels_gemm_tc.cu)
+        GemmTcWs tc;
         int first[3] = {0, 0, 0}, last[3] = {0, 0, 0};         // layer index ranges: TextEnc, AudioEnc, AudioDec
     } tr;
 
@@ -169,6 +172,7 @@ struct dctts_handle_s {
         int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
         int decode_prof = 0;      // persistent decode: record SM-clock lap timers of cluster 0 / rank 0 (dctts_decode_profile)
         int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
+        int train_tc = 7;         // training GEMMs on tcgen05, bit mask: 1 forward conv, 2 data gradient, 4 weight gradient; 0 = fp32 CUDA-core kernels
     } opt;
 
     // persistent decode (kernels_decode.cu)
@@ -185,7 +189,8 @@ struct dctts_handle_s {
         if (ar_exec) cudaGraphExecDestroy(ar_exec);
         for (void* p : param_allocs) cudaFree(p);
         for (DevBuf* b : {&tr.pre, &tr.out, &tr.emb, &tr.R, &tr.align, &tr.dS, &tr.gbuf[0], &tr.gbuf[1], &tr.gbuf[2], &tr.gbuf[3], &tr.dy,
-                          &tr.wT, &tr.zeros, &tr.gts, &tr.sums, &tr.ids, &tr.grads, &tr.mom, &tr.vel, &tr.entries}) b->release();
+                          &tr.wT, &tr.zeros, &tr.gts, &tr.sums, &tr.ids, &tr.grads, &tr.mom, &tr.vel, &tr.entries, &tr.tc_a_hi, &tr.tc_a_lo, &tr.tc_b_hi,
+                          &tr.tc_b_lo, &tr.tc_slots}) b->release();
         dec.prof.release(); dec.wstream.release(); dec.lnp.release(); dec.scr.release(); dec.stats.release(); dec.pfinal.release();
         tickets.release(); scratch.release(); act0.release(); act1.release(); kv.release(); ybuf.release();
         rbuf.release(); ad_sig.release(); ibuf.release(); lbuf.release(); zbuf.release();
@@ -1196,7 +1201,7 @@ void train_init(H* h, int B, float rate, int num, int T_in) {
     tr.layers.clear(); tr.tensors.clear();
     std::vector<std::vector<LayerDev>*> nets;
     if (num == 1) nets = {&h->textenc, &h->audioenc, &h->audiodec}; else nets = {&h->ssrn};
-    size_t pre_f = 0, out_f = 0, g_f = 0, dy_f = 0, wt_f = 0;
+    size_t pre_f = 0, out_f = 0, g_f = 0, dy_f = 0, wt_f = 0, tca_f = 0, tcb_f = 0;
     long long n_grad = 0;
     auto reserve = [&](long long n) { long long o = n_grad; n_grad += (n + 3) / 4 * 4; return o; };
     struct Off { long long W, bias, g1, b1, g2, b2; };
@@ -1215,6 +1220,12 @@ void train_init(H* h, int B, float rate, int num, int T_in) {
             g_f = std::max(g_f, (size_t)t.rows * std::max(t.ld_out, roundup(l.cin, 4)));
             dy_f = std::max(dy_f, (size_t)t.rows * l.ldw);
             wt_f = std::max(wt_f, (size_t)l.size * l.ldw * roundup(l.cin, 4));
+            {   // operand planes of the tensor-core GEMMs: activations / gradients (plain and transposed), packed weights
+                const size_t rows_in = (size_t)B * t.L_in, cmax = (size_t)roundup(std::max(l.cin, l.ldw), 8);
+                tca_f = std::max(tca_f, std::max(rows_in * cmax, (size_t)l.size * B * roundup(l.cin, 8) * roundup(t.L_in, 8)));
+                tcb_f = std::max(tcb_f, std::max((size_t)B * cmax * roundup(t.L_in, 8),
+                                                 (size_t)l.size * roundup(std::max(l.cin, l.ldw) + 255, 256) * roundup(std::max(l.cin, l.ldw), 32)));
+            }
             Off o{};
             o.W = reserve((long long)l.size * l.cin * l.ldw); o.bias = reserve(l.ldw);
             o.g1 = reserve(l.cout); o.b1 = reserve(l.cout);
@@ -1234,6 +1245,13 @@ void train_init(H* h, int B, float rate, int num, int T_in) {
     for (auto& g : tr.gbuf) g.ensure(g_f * sizeof(float));
     tr.dy.ensure(dy_f * sizeof(float)); tr.wT.ensure(wt_f * sizeof(float));
     tr.zeros.ensure(4096 * sizeof(float)); CUDA_CHECK(cudaMemset(tr.zeros.p, 0, 4096 * sizeof(float)));
+    tr.tc_a_hi.ensure(tca_f * sizeof(__half)); tr.tc_a_lo.ensure(tca_f * sizeof(__half));
+    tr.tc_b_hi.ensure(tcb_f * sizeof(__half)); tr.tc_b_lo.ensure(tcb_f * sizeof(__half));
+    tr.tc_slots.ensure(2048 * sizeof(unsigned));
+    tr.tc = GemmTcWs{};
+    tr.tc.a_hi = tr.tc_a_hi.as<__half>(); tr.tc.a_lo = tr.tc_a_lo.as<__half>(); tr.tc.a_elems = tca_f;
+    tr.tc.b_hi = tr.tc_b_hi.as<__half>(); tr.tc.b_lo = tr.tc_b_lo.as<__half>(); tr.tc.b_elems = tcb_f;
+    tr.tc.slots = tr.tc_slots.as<unsigned>(); tr.tc.n_slots = 2048;
     tr.sums.ensure(4 * sizeof(double));
     tr.grads.ensure(n_grad * sizeof(float)); tr.mom.ensure(n_grad * sizeof(float)); tr.vel.ensure(n_grad * sizeof(float));
     CUDA_CHECK(cudaMemset(tr.grads.p, 0, n_grad * sizeof(float)));
@@ -1326,7 +1344,9 @@ void train_fwd(H* h, Launch& lc, int first, int last, int B, uint32_t seed) {
             int sh[3]; layer_shifts(l, t.extra_shift, sh);
             for (int j = 0; j < l.size; ++j) { c.taps[j].W = l.W + (size_t)j * l.cin * l.ldw; c.taps[j].shift = sh[j]; }
             c.Lout = t.L; c.ostride = 1; c.ooff = 0;
-            launch_conv_gemm(c, s, 0, false); lc.count();
+            t.tc_slots = GemmTcSlots{};
+            if ((h->opt.train_tc & 1) && conv_gemm_tc_ok(c, tr.tc)) lc.count(launch_conv_gemm_tc(c, tr.tc, s, &t.tc_slots));
+            else { launch_conv_gemm(c, s, 0, false); lc.count(); }
         }
         launch_ln_rows(n, s); lc.count();
         if (tr.rate > 0.f) { launch_train_dropout(t.out, t.rows, l.cout, t.ld_out, drop_args(tr.rate, t.li, seed), s); lc.count(); }
@@ -1377,12 +1397,16 @@ float* train_bwd(H* h, Launch& lc, int first, int last, int B, uint32_t seed, fl
         } else {
             w.rows = t.rows; w.dy = dy; w.ldy = l.ldw; w.dW = t.dW; w.N = l.nconv; w.ntaps = l.size;
             layer_shifts(l, t.extra_shift, w.shifts);
-            launch_conv_wgrad(w, s); lc.count();
+            GemmTcSlots gs{t.tc_slots.x, nullptr};                   // X's abs-max is known from the forward; dy's is computed once, for both gradients
+            if ((h->opt.train_tc & 4) && conv_wgrad_tc_ok(w, B, tr.tc)) lc.count(launch_conv_wgrad_tc(w, B, tr.tc, s, &gs));
+            else { launch_conv_wgrad(w, s); lc.count(); }
             if (!t.need_dgrad) continue;
             c.X = dy; c.ldx = l.ldw; c.ntaps = l.size;
             for (int j = 0; j < l.size; ++j) { c.taps[j].W = wT + (size_t)j * tsz; c.taps[j].shift = -w.shifts[j]; }
             c.accumulate = a.mode;
-            launch_conv_gemm(c, s, 0, false); lc.count();
+            GemmTcSlots gd{gs.w, t.tc_slots.w};                       // operands: dy and W^T (same magnitudes as W)
+            if ((h->opt.train_tc & 2) && conv_gemm_tc_ok(c, tr.tc)) lc.count(launch_conv_gemm_tc(c, tr.tc, s, &gd));
+            else { launch_conv_gemm(c, s, 0, false); lc.count(); }
         }
         std::swap(g_cur, g_other);
     }
@@ -1408,14 +1432,20 @@ void train_forward_backward(H* h, const int* L, const float* mels, int B, uint32
     Launch lc{h, s};
     CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
+    gemm_tc_begin_step(tr.tc, s);
     tr.layers[tr.first[1]].in = mels;
     launch_embed(L, h->embed_table, tr.emb.as<float>(), B * N, hp.e, s); lc.count();
     train_fwd(h, lc, tr.first[0], tr.last[0], B, seed);
     train_fwd(h, lc, tr.first[1], tr.last[1], B, seed);
     const float* KV = tr.layers[tr.last[0]].out;               // (B, N, 2d): K | V
     const float* Q = tr.layers[tr.last[1]].out;                // (B, T, d)
-    run_attention(lc, Q, d, KV, 2 * d, KV + d, 2 * d, RowWin{B, T, T, nullptr}, N, nullptr, tr.R.as<float>(), tr.align.as<float>(),
-                  nullptr, nullptr, nullptr);
+    // dense softmax attention (training: no window, networks.py:140-153): the tcgen05 kernel of the synthesis path when the
+    // forward GEMMs are on the tensor cores (it does not touch the weights), else one warp per query row on CUDA cores
+    if ((h->opt.train_tc & 1) && d == 256 && N <= attn_tc_padded_keys())
+        run_attention_tc(lc, Q, d, KV, 2 * d, KV + d, 2 * d, B, T, N, nullptr, tr.R.as<float>(), tr.align.as<float>(), nullptr, Planes{});
+    else
+        run_attention(lc, Q, d, KV, 2 * d, KV + d, 2 * d, RowWin{B, T, T, nullptr}, N, nullptr, tr.R.as<float>(), tr.align.as<float>(),
+                      nullptr, nullptr, nullptr);
     train_fwd(h, lc, tr.first[2], tr.last[2], B, seed);
     const auto& lastl = tr.layers[tr.last[2]];
     launch_train_loss(lastl.out, lastl.ld_out, mels, tr.gbuf[0].as<float>(), lastl.ld_out, tr.sums.as<double>(), (long long)B * T, hp.n_mels, s);
@@ -1441,6 +1471,7 @@ void train_forward_backward_ssrn(H* h, const float* mels, const float* mags, int
     Launch lc{h, s};
     CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
+    gemm_tc_begin_step(tr.tc, s);
     tr.layers[0].in = mels;
     const int last = (int)tr.layers.size() - 1;
     train_fwd(h, lc, 0, last, B, seed);
@@ -1998,6 +2029,7 @@ static int* option_slot(dctts_handle h, const char* name) {
     if (n == "fused_ln") return &h->opt.fused_ln;
     if (n == "decode_mode") return &h->opt.decode_mode;
     if (n == "decode_prof") return &h->opt.decode_prof;
+    if (n == "train_tc") return &h->opt.train_tc;
     return nullptr;
 }
 
@@ -2006,7 +2038,7 @@ int dctts_set_option(dctts_handle h, const char* name, int32_t value) {
         if (name && std::string(name) == "pdl") { pdl_enabled() = value != 0; return; }     // process-wide launch attribute
         int* slot = option_slot(h, name);
         REQUIRE(slot, "dctts_set_option: unknown option");
-        REQUIRE(value >= 0 && value <= 2, "dctts_set_option: value out of range");
+        REQUIRE(value >= 0 && value <= (std::string(name) == "train_tc" ? 7 : 2), "dctts_set_option: value out of range");
         if (std::string(name) == "decode_mode" && value == 1 && !h->dec.ok && h->committed)
             throw std::runtime_error("dctts_set_option: persistent decode unavailable: " + h->dec.why);
         if (*slot != value && h->ar_exec) {                  // the captured AR step bakes the variant in

@@ -161,6 +161,19 @@ void launch_guided_attention(float* W, int N, int T, cudaStream_t s);
 void launch_embed_bwd(const int* ids, const float* g, float* dtable, int rows, int e, cudaStream_t s);
 void launch_adam(const AdamEntry* entries_dev, int n_entries, float lr_t, float beta1, float beta2, float eps, cudaStream_t s);
 
+// ---- the training GEMMs on tcgen05 (kernels_gemm_tc.cu): drop-ins for launch_conv_gemm (tiled path) / launch_conv_wgrad ----
+struct GemmTcWs {
+    __half* a_hi = nullptr; __half* a_lo = nullptr; size_t a_elems = 0;   // operand A planes (activations / gradients, plain or transposed)
+    __half* b_hi = nullptr; __half* b_lo = nullptr; size_t b_elems = 0;   // operand B planes (weights / transposed gradients)
+    unsigned* slots = nullptr; int n_slots = 0; int cursor = 0;           // per-tensor abs-max slots, cleared once per step
+};
+void gemm_tc_begin_step(GemmTcWs& ws, cudaStream_t s);
+bool conv_gemm_tc_ok(const ConvArgs& c, const GemmTcWs& ws);
+struct GemmTcSlots { unsigned* x = nullptr; unsigned* w = nullptr; };   // in: abs-max already known (same tensor converted earlier this step); out: the slots used
+int launch_conv_gemm_tc(const ConvArgs& c, GemmTcWs& ws, cudaStream_t s, GemmTcSlots* io = nullptr);
+bool conv_wgrad_tc_ok(const WgradArgs& w, int B, const GemmTcWs& ws);
+int launch_conv_wgrad_tc(const WgradArgs& w, int B, GemmTcWs& ws, cudaStream_t s, GemmTcSlots* io = nullptr);
+
 // scratch_bytes bounds the split-K partial buffer of the skinny path
 GemmOut launch_conv_gemm(const ConvArgs& a, cudaStream_t s, size_t scratch_bytes, bool allow_skinny = true);
 void launch_ln_rows(const LnArgs& a, cudaStream_t s);

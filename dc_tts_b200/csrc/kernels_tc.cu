@@ -590,6 +590,21 @@ void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, i
     if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
 }
 
+// generic rank-3 fp16 map: dims {d0, d1, d2} (d0 contiguous), byte strides of d1 / d2, box {b0, b1, 1}; the swizzle follows the
+// box's inner extent (64 elements -> 128 bytes, 32 -> 64 bytes), out-of-range coordinates (negative too) read zeros
+void tc_make_map3(CUtensorMap* m, const __half* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                  uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+    cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    cuuint64_t strides[2] = {(cuuint64_t)stride1_bytes, (cuuint64_t)stride2_bytes};
+    cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (b0 != 64 && b0 != 32) throw std::runtime_error("tc_make_map3: the inner box extent must be 32 or 64 halfs");
+    CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, b0 == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(map3) failed: " + std::to_string((int)r));
+}
+
 void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn, int bk) {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Nrows};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};

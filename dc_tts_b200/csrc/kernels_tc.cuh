@@ -53,6 +53,10 @@ void tc_make_act_map(CUtensorMap* m, const __half* base, int C, int ld, int L, i
 // Encodes the rank-2 (Ktot, Nrows) K-major weight map with a {bk, bn} box, same swizzle rule.
 void tc_make_w_map(CUtensorMap* m, const __half* base, int Ktot, int Nrows, int bn, int bk);
 
+// Generic rank-3 fp16 map {d0 (contiguous), d1, d2} with byte strides and a {b0, b1, 1} box (b0 = 32 or 64 halfs).
+void tc_make_map3(CUtensorMap* m, const __half* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                  uint64_t stride2_bytes, uint32_t b0, uint32_t b1);
+
 // pipeline depth that fits the shared-memory budget for `bn` accumulator columns per CTA
 int tc_stages_for(int bn, int bk, int mt);
 // reduction slab per pipeline stage (fp16 elements): 64 (128B swizzle); DCTTS_TC_BK=32 selects 32 (64B swizzle, deeper pipeline)

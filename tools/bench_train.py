@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--train-tc", type=int, default=7, help="bit mask: 1 forward conv, 2 data gradient, 4 weight gradient on tcgen05 (default 7 = all), 0 = fp32 CUDA-core kernels")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -28,6 +29,7 @@ if world > 1:
 eng = Engine(local)
 eng.load_params(init_params(0))
 B = a.batch
+eng.set_option("train_tc", a.train_tc)
 eng.train_init(B)
 L = torch.from_numpy(synthetic_text(B, 100, seed=rank)).cuda()
 mels = torch.from_numpy(np.random.default_rng(rank).uniform(0, 1, (B, hp.max_T, hp.n_mels)).astype(np.float32)).cuda()
@@ -65,7 +67,7 @@ if rank == 0:
                       "mel_frames_per_sec": world * B * hp.max_T * 1e3 / ms, "steps": a.steps, "warmup": a.warmup,
                       "config": {"workload": "BASELINE config 5: Text2Mel train step (fwd + bwd + clip + Adam), B=%d per GPU, N=180, T=210, dropout %.2f" % (B, hp.dropout_rate),
                                  "parallelism": "dp%d (all-reduce of %d gradients)" % (world, grads.numel())},
-                      "dtype": "f32 (CUDA-core kernels, first correct path)", "data": "synthetic",
+                      "dtype": ("f32 tensors; GEMMs as split-fp16 x3 on tcgen05, fp32 accumulate" if a.train_tc else "f32 (CUDA-core kernels)"), "data": "synthetic",
                       "achieved_tflops": world * flops / (ms * 1e-3) / 1e12, "gpu_launches_per_step": (eng.launch_count() - n0) // a.steps,
                       "loss_first": first["loss"], "loss_last": last["loss"]}))
 if world > 1:
