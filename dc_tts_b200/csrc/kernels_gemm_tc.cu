@@ -216,6 +216,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
 }
 
 // ---- operand conversion ------------------------------------------------------------------------------------------------
+// one atomicMax per CTA (8 warps -> shared memory -> thread 0): thousands of same-address atomics serialise in L2
+__device__ __forceinline__ void block_max_to_slot(float m, unsigned* slot) {
+    __shared__ float wm[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = wm[0];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) v = fmaxf(v, wm[i]);
+        if (v > 0.f) atomicMax(slot, __float_as_uint(v));
+    }
+}
+
 // largest magnitude of a (rows, C) tensor with leading dimension ld -> atomicMax on the float bits (magnitudes order like uints).
 // VEC: C, ld multiples of 4 and a 16-byte aligned base (float4 loads); else scalar.
 template <bool VEC>
@@ -236,14 +251,12 @@ __global__ void absmax_kernel(const float* __restrict__ x, int ld, long long row
             m = fmaxf(m, fabsf(x[r * ld + (i - r * C)]));
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+    block_max_to_slot(m, slot);
 }
 void launch_absmax(const float* x, int ld, long long rows, int C, unsigned* slot, cudaStream_t s) {
     const bool vec = (C & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     const long long n = vec ? rows * (C >> 2) : rows * C;
-    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(1184, (n + 255) / 256));
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(592, (n + 255) / 256));
     if (vec) absmax_kernel<true><<<grid, 256, 0, s>>>(x, ld, rows, C, slot);
     else absmax_kernel<false><<<grid, 256, 0, s>>>(x, ld, rows, C, slot);
 }
@@ -321,9 +334,7 @@ __global__ void absmax_w_kernel(WTaps taps, int ntaps, int K, int N, int ldw, un
         const long long k = j / N;
         m = fmaxf(m, fabsf(taps.w[tp][k * ldw + (j - k * N)]));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+    block_max_to_slot(m, slot);
 }
 // W_tap[k][n] (ldw) -> K-major planes out[n][tap * Kp2 + k], n < Nrows, zero where k >= K or n >= N
 __global__ void w_to_planes_kernel(WTaps taps, int K, int N, int ldw, __half* __restrict__ hi, __half* __restrict__ lo, int Kp2,

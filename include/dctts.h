@@ -152,8 +152,10 @@ int dctts_get_spectrograms(dctts_handle h, const float* wav, int64_t n_samples, 
  * every block, full softmax attention), losses train.py:83-99 (L1 + sigmoid cross-entropy on the mels + guided
  * attention), elementwise clipping to [-1, 1] and tf.train.AdamOptimizer defaults with the Noam learning rate
  * (train.py:122-132, utils.py:141-145) -- for fixed-size batches L (B, max_N) int32, mels (B, max_T, n_mels), DEVICE
- * pointers.  float32 CUDA-core kernels (first correct path).  dctts_train_init allocates the saved activations and the
- * gradient / Adam arenas and switches the handle to the fp32 kernel set (the optimiser updates the fp32 weights only).
+ * pointers.  All tensors are float32; the three GEMMs of every block (forward conv, data gradient, weight gradient) run on
+ * tcgen05 as split-fp16 x3 with per-tensor power-of-two scales (option "train_tc", default 7; 0 = the float32 CUDA-core
+ * kernels).  dctts_train_init allocates the saved activations and the gradient / Adam arenas and switches the handle's
+ * SYNTHESIS entry points to the fp32 kernel set (the optimiser updates the fp32 weights only, the packed planes go stale).
  * Dropout uses a stateless hash of (element, block index, seed) -- TF's random stream cannot be reproduced.
  * losses_host (optional): {total, mels L1, binary divergence, guided attention}; reading them synchronises.
  * apply = 0 leaves the gradients in the arena (dctts_train_grads: one flat device buffer, what a data-parallel job
@@ -194,6 +196,7 @@ int dctts_set_tensor_path(dctts_handle h, int32_t mode);
  *                  0 = one captured CUDA graph per mel frame (round-1 path)
  *   "tc_occ2" 0/1, "tc_cg2" 0/1/2, "tc_tile_pair" 0/1, "tc_mcast" 0/1, "tc_resid_tma" 0/1: tcgen05 block kernel variants
  *   "fused_ln" 0/1: graph decode, GEMM + LN in one launch;  "tc_debug" 0/1;  "decode_prof" 0/1;  "pdl" 0/1 (process-wide)
+ *   "train_tc" 0..7: training GEMMs on tcgen05, bit mask 1 forward conv (+ tcgen05 attention), 2 data gradient, 4 weight gradient
  * dctts_get_option also answers "decode_available" (1 when this handle / device can run the persistent decode) and
  * "decode_max_clusters" (16-CTA clusters of the decode kernel that are co-resident on this device; 7 on a B200). */
 int dctts_set_option(dctts_handle h, const char* name, int32_t value);

@@ -5,12 +5,12 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-for tool in memcheck synccheck; do
-    timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_run.py decode graph attention > $O/r02_sanitizer_${tool}_decode.log 2>&1
-    echo "rc=$?" >> $O/r02_sanitizer_${tool}_decode.log
-done
-timeout 1500 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py blocks > $O/r02_sanitizer_memcheck_blocks.log 2>&1
-echo "rc=$?" >> $O/r02_sanitizer_memcheck_blocks.log
-timeout 1500 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_run.py decode > $O/r02_sanitizer_racecheck_decode.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py decode graph attention > $O/r02_sanitizer_memcheck_decode.log 2>&1
+echo "rc=$?" >> $O/r02_sanitizer_memcheck_decode.log
+timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize_run.py blocks train > $O/r02_sanitizer_memcheck_blocks_train.log 2>&1
+echo "rc=$?" >> $O/r02_sanitizer_memcheck_blocks_train.log
+timeout 900 compute-sanitizer --tool synccheck --print-limit 20 python tools/sanitize_run.py decode attention train > $O/r02_sanitizer_synccheck.log 2>&1
+echo "rc=$?" >> $O/r02_sanitizer_synccheck.log
+timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_run.py decode > $O/r02_sanitizer_racecheck_decode.log 2>&1
 echo "rc=$?" >> $O/r02_sanitizer_racecheck_decode.log
 echo done

@@ -1,7 +1,7 @@
 """Small workload for compute-sanitizer (memcheck / racecheck / synccheck): one
 block of every tcgen05 specialisation (one CTA per SM, two CTAs per SM, CTA pairs wide / narrow, paired tiles), the
 tcgen05 attention, and a few frames of both decode loops with a window move.
-   compute-sanitizer --tool memcheck python tools/sanitize_run.py [what ...]      what: blocks attention decode graph"""
+   compute-sanitizer --tool memcheck python tools/sanitize_run.py [what ...]      what: blocks attention decode graph train"""
 import os
 import sys
 
@@ -46,3 +46,11 @@ if "graph" in what:
     Y, P, _, _ = e.text2mel_generate(L, steps=4)
     torch.cuda.synchronize(); print("graph decode ok", flush=True)
     e.set_option("decode_mode", 1)
+if "train" in what:
+    # the tcgen05 training GEMMs (kernels_gemm_tc.cu): one Text2Mel step at B = 2 (forward, data gradient, weight gradient)
+    t = Engine(0)
+    t.load_params(init_params(0))
+    t.train_init(2)
+    mels = rng.uniform(0, 1, (2, hp.max_T, hp.n_mels)).astype(np.float32)
+    out = t.train_step(synthetic_text(2, 60, seed=1), mels, global_step=7, seed=1)
+    torch.cuda.synchronize(); print("train step ok", out, flush=True)
