@@ -97,7 +97,7 @@ struct dctts_handle_s {
     int F = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // device->host copies of finished spectrogram chunks (dctts_synthesize_host)
-    cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunk_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     std::string err;
 
     std::map<std::string, HostParam> staged;
@@ -172,6 +172,7 @@ struct dctts_handle_s {
         int fused_ln = 0;         // graph decode: split-K GEMM and LN epilogue in one launch
         int decode_prof = 0;      // persistent decode: record SM-clock lap timers of cluster 0 / rank 0 (dctts_decode_profile)
         int decode_mode = 1;      // 1 = persistent cluster kernel (kernels_decode.cu), 0 = one CUDA graph per frame (round-1 path)
+        int train_probe = 0;      // measurement only (tools/bench_train.py --probe): the training GEMMs fetch their operands but issue no MMA
         int train_tc = 7;         // training GEMMs on tcgen05, bit mask: 1 forward conv, 2 data gradient, 4 weight gradient; 0 = fp32 CUDA-core kernels
     } opt;
 
@@ -1432,7 +1433,7 @@ void train_forward_backward(H* h, const int* L, const float* mels, int B, uint32
     Launch lc{h, s};
     CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
-    gemm_tc_begin_step(tr.tc, s);
+    gemm_tc_begin_step(tr.tc, s); tr.tc.probe = h->opt.train_probe;
     tr.layers[tr.first[1]].in = mels;
     launch_embed(L, h->embed_table, tr.emb.as<float>(), B * N, hp.e, s); lc.count();
     train_fwd(h, lc, tr.first[0], tr.last[0], B, seed);
@@ -1471,7 +1472,7 @@ void train_forward_backward_ssrn(H* h, const float* mels, const float* mags, int
     Launch lc{h, s};
     CUDA_CHECK(cudaMemsetAsync(tr.grads.p, 0, tr.n_grad * sizeof(float), s));
     CUDA_CHECK(cudaMemsetAsync(tr.sums.p, 0, 4 * sizeof(double), s));
-    gemm_tc_begin_step(tr.tc, s);
+    gemm_tc_begin_step(tr.tc, s); tr.tc.probe = h->opt.train_probe;
     tr.layers[0].in = mels;
     const int last = (int)tr.layers.size() - 1;
     train_fwd(h, lc, 0, last, B, seed);
@@ -1720,11 +1721,18 @@ int dctts_synthesize_host(dctts_handle h, const int32_t* L_host, int32_t B, floa
             CUDA_CHECK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
             for (auto& e : h->chunk_done) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
-        const int nchunk = B >= 16 ? 4 : (B >= 4 ? 2 : 1);
+        // chunk ends: quarters of the batch (B >= 16) with the LAST quarter split again -- only the last chunk's copy is exposed,
+        // and a chunk costs the SSRN a partly filled wave (measured ~0.55 ms per extra chunk at B = 32), so more, smaller chunks
+        // at the front would cost more than they hide
+        int ends[8], nchunk = 0;
+        if (B >= 16) { for (int c = 1; c <= 3; ++c) ends[nchunk++] = (int)((long long)B * c / 4); ends[nchunk++] = (int)((long long)B * 7 / 8); ends[nchunk++] = B; }
+        else if (B >= 4) { ends[nchunk++] = B / 2; ends[nchunk++] = B; }
+        else ends[nchunk++] = B;
         const size_t zrow = (size_t)T * hp.r * h->F;
         Launch lc{h, s};
+        int b0 = 0;
         for (int c = 0; c < nchunk; ++c) {
-            const int b0 = (int)((long long)B * c / nchunk), b1 = (int)((long long)B * (c + 1) / nchunk);
+            const int b1 = ends[c];
             if (b1 <= b0) continue;
             float* zc = h->zbuf.as<float>() + (size_t)b0 * zrow;
             run_chain_full(lc, h->ssrn, h->ybuf.as<float>() + (size_t)b0 * T * hp.n_mels, hp.n_mels, b1 - b0, T, nullptr, zc);
@@ -1732,6 +1740,7 @@ int dctts_synthesize_host(dctts_handle h, const int32_t* L_host, int32_t B, floa
             CUDA_CHECK(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
             CUDA_CHECK(cudaMemcpyAsync(Z_host + (size_t)b0 * zrow, zc, (size_t)(b1 - b0) * zrow * sizeof(float),
                                        cudaMemcpyDeviceToHost, h->copy_stream));
+            b0 = b1;
         }
         CUDA_CHECK(cudaStreamSynchronize(h->copy_stream));
         CUDA_CHECK(cudaStreamSynchronize(s));
@@ -2030,6 +2039,7 @@ static int* option_slot(dctts_handle h, const char* name) {
     if (n == "decode_mode") return &h->opt.decode_mode;
     if (n == "decode_prof") return &h->opt.decode_prof;
     if (n == "train_tc") return &h->opt.train_tc;
+    if (n == "train_probe") return &h->opt.train_probe;
     return nullptr;
 }
 

@@ -166,6 +166,7 @@ struct GemmTcWs {
     __half* a_hi = nullptr; __half* a_lo = nullptr; size_t a_elems = 0;   // operand A planes (activations / gradients, plain or transposed)
     __half* b_hi = nullptr; __half* b_lo = nullptr; size_t b_elems = 0;   // operand B planes (weights / transposed gradients)
     unsigned* slots = nullptr; int n_slots = 0; int cursor = 0;           // per-tensor abs-max slots, cleared once per step
+    int probe = 0;                                                        // measurement only: fetch the operands, issue no MMA, store nothing
 };
 void gemm_tc_begin_step(GemmTcWs& ws, cudaStream_t s);
 bool conv_gemm_tc_ok(const ConvArgs& c, const GemmTcWs& ws);

@@ -58,7 +58,12 @@ struct GemmTcArgs {
     int tblocks, nb_per_split, B, ksplit, K;
     float* dW; int ldw; long long tap_stride;
     const unsigned* slot_a; const unsigned* slot_b;
+    int probe;                // measurement only: 1 = the operands are fetched but no MMA is issued and nothing is stored
 };
+
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
 
 __global__ void __launch_bounds__(G_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
@@ -130,7 +135,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
             const int s = kb % stages;
             mbar_wait(&full_bar[s], ((uint32_t)(kb / stages)) & 1u);
             tc_fence_after();
-            if (lane == 0) {
+            if (lane == 0 && a.probe) {                             // ingest probe: release the stage at once
+                mbar_arrive_local(&empty_bar[s]);
+                if (kb == nkb - 1) mbar_arrive_local(tmem_full_bar);
+            } else if (lane == 0) {
                 const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint64_t dA_hi = umma_desc_kmajor<G_SW>(st), dA_lo = umma_desc_kmajor<G_SW>(st + G_APLANE);
                 const uint64_t dB_hi = umma_desc_kmajor<G_SW>(st + 2 * G_APLANE), dB_lo = umma_desc_kmajor<G_SW>(st + 2 * G_APLANE + b_plane);
@@ -155,7 +163,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constan
         const float inv = 1.0f / (slot_scale(a.slot_a) * slot_scale(a.slot_b));      // both powers of two: exact
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        if (a.mode == 0) {
+        if (a.probe) {
+        } else if (a.mode == 0) {
             const int t = t0 + r;
             const bool ok = t < a.L;
             float* yrow = a.Y + ((size_t)b0 * a.Lout + (ok ? t : 0)) * a.ldy;
@@ -439,7 +448,7 @@ int launch_conv_gemm_tc(const ConvArgs& c, GemmTcWs& ws, cudaStream_t s, GemmTcS
     a.kb_per_tap = Kp2 / G_BK; a.Kp2 = Kp2; a.N = c.N;
     for (int j = 0; j < c.ntaps; ++j) a.shifts[j] = c.taps[j].shift;
     a.Y = c.Y; a.ldy = c.ldy; a.bias = c.bias; a.accumulate = c.accumulate;
-    a.slot_a = sa; a.slot_b = sb;
+    a.slot_a = sa; a.slot_b = sb; a.probe = ws.probe;
     launch_gemm(m, a, dim3((unsigned)n_tiles, (unsigned)(a.tiles_t * B), 1), s);
     if (io) { io->x = sa; io->w = sb; }
     return launches;
@@ -478,7 +487,7 @@ int launch_conv_wgrad_tc(const WgradArgs& w, int B, GemmTcWs& ws, cudaStream_t s
     a.nb_per_split = (B + ksplit - 1) / ksplit;
     a.ksplit = (B + a.nb_per_split - 1) / a.nb_per_split;          // no empty split
     a.dW = w.dW; a.ldw = w.ldw; a.tap_stride = (long long)w.K * w.ldw;
-    a.slot_a = sa; a.slot_b = sb;
+    a.slot_a = sa; a.slot_b = sb; a.probe = ws.probe;
     launch_gemm(m, a, dim3((unsigned)n_tiles, (unsigned)k_tiles, (unsigned)(w.ntaps * a.ksplit)), s);
     if (io) { io->x = sa; io->w = sb; }
     return launches;

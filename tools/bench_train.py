@@ -20,6 +20,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--probe", type=int, default=0, help="measurement only: 1 = the tcgen05 GEMMs fetch their operands but issue no MMA (results are garbage)")
 ap.add_argument("--net", type=int, default=1, choices=[1, 2], help="1 = Text2Mel trainer (BASELINE config 5), 2 = SSRN trainer (train.py num=2) at T = 210")
 ap.add_argument("--train-tc", type=int, default=7, help="bit mask: 1 forward conv, 2 data gradient, 4 weight gradient on tcgen05 (default 7 = all), 0 = fp32 CUDA-core kernels")
 a = ap.parse_args()
@@ -31,6 +32,7 @@ eng = Engine(local)
 eng.load_params(init_params(0))
 B = a.batch
 eng.set_option("train_tc", a.train_tc)
+eng.set_option("train_probe", a.probe)
 if a.net == 1:
     eng.train_init(B)
 else:
