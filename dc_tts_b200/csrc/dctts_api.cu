@@ -1349,8 +1349,8 @@ void train_fwd(H* h, Launch& lc, int first, int last, int B, uint32_t seed) {
             if ((h->opt.train_tc & 1) && conv_gemm_tc_ok(c, tr.tc)) lc.count(launch_conv_gemm_tc(c, tr.tc, s, &t.tc_slots));
             else { launch_conv_gemm(c, s, 0, false); lc.count(); }
         }
+        if (tr.rate > 0.f) n.drop = drop_args(tr.rate, t.li, seed);      // the forward mask is applied by the LayerNorm epilogue
         launch_ln_rows(n, s); lc.count();
-        if (tr.rate > 0.f) { launch_train_dropout(t.out, t.rows, l.cout, t.ld_out, drop_args(tr.rate, t.li, seed), s); lc.count(); }
     }
 }
 

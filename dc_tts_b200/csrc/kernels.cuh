@@ -62,6 +62,22 @@ struct ConvArgs {
     int accumulate = 0;            // tiled kernels only: Y += result (data gradient on top of the highway path)
 };
 
+// Dropout of the training step (modules.py:139 at training=True): a stateless hash of (dense element index, block index, seed) --
+// TF's random stream cannot be reproduced, so the oracle (oracle/ref_train.py: mix32) and the kernels share this one.
+struct DropArgs { uint32_t thresh = 0, layer = 0, seed = 0; float scale = 1.f; };   // keep iff mix32(i, layer, seed) >= thresh
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t mix32(uint32_t idx, uint32_t layer, uint32_t seed) {
+    uint32_t x = idx * 0x9E3779B1u;
+    x ^= layer * 0x85EBCA77u + seed;
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ float keep_mul(uint32_t idx, const DropArgs& d) {
+    if (d.thresh == 0u) return 1.0f;
+    return mix32(idx, d.layer, d.seed) >= d.thresh ? d.scale : 0.0f;
+}
+#endif
+
 // Row-wise epilogue on the pre-LN scratch.
 //  mode 0 (conv1d):  o = act(LN(y[0:C]) * g1 + b1);            out = o; out2 = sigmoid(o) if out2
 //  mode 1 (hc):      H1 = sigmoid(LN(y[0:C])*g1+b1); H2 = LN(y[C:2C])*g2+b2;
@@ -77,6 +93,7 @@ struct LnArgs {
     int nparts = 1;                // split-K partials to sum (skinny GEMM), else 1
     int compact = 0;               // 1: scratch rows are indexed by b*R + r instead of the output row
     size_t part_stride = 0;        // floats between consecutive partials
+    DropArgs drop;                 // training forward: dropout of the block output fused into this epilogue (thresh 0 = none)
 };
 
 struct GemmOut { int nparts; int compact; size_t part_stride; };
@@ -122,7 +139,6 @@ void feat_run(const float* y, int len, float preemph, float* mag, float* mel, co
 
 
 // ---- training step (kernels_train.cu; reference train.py mode "train") ----
-struct DropArgs { uint32_t thresh = 0, layer = 0, seed = 0; float scale = 1.f; };   // keep iff mix32(i, layer, seed) >= thresh
 struct BlockBwdArgs {
     const float* pre; int ldy;         // pre-LN conv output (rows, nconv)
     const float* gout; int ldg;        // gradient w.r.t. the block output (rows, C), leading dimension ldg (also of gin)

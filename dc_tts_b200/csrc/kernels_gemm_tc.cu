@@ -313,22 +313,24 @@ void launch_to_planes(const float* x, int ld, long long rows, int C, __half* hi,
 struct Shifts { int n; int s[3]; };
 __global__ void to_planes_t_kernel(const float* __restrict__ x, int ld, int B, int L, int C, __half* __restrict__ hi,
                                    __half* __restrict__ lo, int ldt, Shifts sh, const unsigned* slot) {
-    __shared__ float tile[32][33];
-    const int j = blockIdx.z / B, b = blockIdx.z - j * B, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    __shared__ float tile[64][33];                     // 64 time rows x 32 channels; stores are two time rows (4 bytes) per thread
+    const int j = blockIdx.z / B, b = blockIdx.z - j * B, t0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
     const int shift = sh.s[j];
     const float s = slot_scale(slot);
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    for (int i = threadIdx.y; i < 64; i += blockDim.y) {
         const int t = t0 + i, ts = t + shift, c = c0 + threadIdx.x;
         tile[i][threadIdx.x] = (t < L && ts >= 0 && ts < L && c < C) ? x[((size_t)b * L + ts) * ld + c] * s : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, t = t0 + threadIdx.x;
-        if (c < C && t < ldt) {
-            __half h, l;
-            split_half(tile[threadIdx.x][i], h, l);
+        const int c = c0 + i, t = t0 + 2 * threadIdx.x;
+        if (c < C && t < ldt) {                        // ldt is a multiple of 8 and t even: the pair stays inside the row
+            __half h0, l0, h1, l1;
+            split_half(tile[2 * threadIdx.x][i], h0, l0);
+            split_half(tile[2 * threadIdx.x + 1][i], h1, l1);
             const size_t o = (((size_t)j * B + b) * C + c) * ldt + t;
-            hi[o] = h; lo[o] = l;
+            *reinterpret_cast<__half2*>(hi + o) = __halves2half2(h0, h1);
+            *reinterpret_cast<__half2*>(lo + o) = __halves2half2(l0, l1);
         }
     }
 }
@@ -470,10 +472,10 @@ int launch_conv_wgrad_tc(const WgradArgs& w, int B, GemmTcWs& ws, cudaStream_t s
     if (!sa) { sa = take_slot(ws); launch_absmax(w.X, w.ldx, w.rows, w.K, sa, s); ++launches; }
     Shifts sh{}; sh.n = w.ntaps;
     for (int j = 0; j < w.ntaps; ++j) sh.s[j] = w.shifts[j];
-    to_planes_t_kernel<<<dim3((ldt + 31) / 32, (w.K + 31) / 32, B * w.ntaps), dim3(32, 8), 0, s>>>(w.X, w.ldx, B, L, w.K, ws.a_hi, ws.a_lo, ldt, sh, sa);
+    to_planes_t_kernel<<<dim3((ldt + 63) / 64, (w.K + 31) / 32, B * w.ntaps), dim3(32, 8), 0, s>>>(w.X, w.ldx, B, L, w.K, ws.a_hi, ws.a_lo, ldt, sh, sa);
     if (!sb) { sb = take_slot(ws); launch_absmax(w.dy, w.ldy, w.rows, w.N, sb, s); ++launches; }
     Shifts none{}; none.n = 1;
-    to_planes_t_kernel<<<dim3((ldt + 31) / 32, (w.N + 31) / 32, B), dim3(32, 8), 0, s>>>(w.dy, w.ldy, B, L, w.N, ws.b_hi, ws.b_lo, ldt, none, sb);
+    to_planes_t_kernel<<<dim3((ldt + 63) / 64, (w.N + 31) / 32, B), dim3(32, 8), 0, s>>>(w.dy, w.ldy, B, L, w.N, ws.b_hi, ws.b_lo, ldt, none, sb);
     const int bn = pick_bn(w.N), n_tiles = (w.N + bn - 1) / bn, k_tiles = (w.K + G_BM - 1) / G_BM;
     CUtensorMap m[4];
     tc_make_map3(&m[0], ws.a_hi, L, w.K, (uint64_t)w.ntaps * B, (uint64_t)ldt * 2, (uint64_t)w.K * ldt * 2, G_BK, G_BM);

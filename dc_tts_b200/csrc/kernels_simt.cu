@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
             if (c < C) {
                 float z = (v1[i] - mean1) * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c);
                 if (a.act == 1) z = fmaxf(z, 0.f);
-                o[c] = z;
+                o[c] = z * keep_mul((uint32_t)(row * C + c), a.drop);
                 if (o2) o2[c] = sigmoidf_acc(z);
             }
         }
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(256) ln_rows_kernel(const LnArgs a) {
             if (c < C) {
                 float h1 = sigmoidf_acc((v1[i] - mean1) * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c));
                 float h2 = (v2[i] - mean2) * inv2 * __ldg(a.g2 + c) + __ldg(a.b2 + c);
-                o[c] = h1 * h2 + (1.0f - h1) * x[c];
+                o[c] = (h1 * h2 + (1.0f - h1) * x[c]) * keep_mul((uint32_t)(row * C + c), a.drop);
             }
         }
     }
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(128) ln_row_cta_kernel(const LnArgs a) {
             if (c < C) {
                 float z = (u ? d1 : d0) * inv1 * __ldg(a.g1 + c) + __ldg(a.b1 + c);
                 if (a.act == 1) z = fmaxf(z, 0.f);
-                o[c] = z;
+                o[c] = z * keep_mul((uint32_t)(row * C + c), a.drop);
                 if (o2) o2[c] = sigmoidf_acc(z);
             }
         }
@@ -593,7 +593,7 @@ __device__ void ln_row_256(const LnArgs& a, int rix, float* sm) {
 void launch_ln_rows(const LnArgs& a, cudaStream_t s) {
     const int rows = a.win.B * a.win.R;
     if (rows <= 0) return;
-    if (a.C <= 256 && rows <= 1024) {                    // the decode step's blocks
+    if (a.C <= 256 && rows <= 1024 && a.drop.thresh == 0u) {   // the decode step's blocks (no dropout there: only ln_rows_kernel applies the training mask)
         launch_kernel(ln_row_cta_kernel, dim3(rows), dim3(128), 0, s, a);
         return;
     }

@@ -19,16 +19,7 @@
 namespace dctts {
 
 // ------------------------------------------------------------------------------------ dropout
-__device__ __forceinline__ uint32_t mix32(uint32_t idx, uint32_t layer, uint32_t seed) {
-    uint32_t x = idx * 0x9E3779B1u;
-    x ^= layer * 0x85EBCA77u + seed;
-    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
-    return x;
-}
-__device__ __forceinline__ float keep_mul(uint32_t idx, const DropArgs& d) {
-    if (d.thresh == 0u) return 1.0f;
-    return mix32(idx, d.layer, d.seed) >= d.thresh ? d.scale : 0.0f;
-}
+// mix32 / keep_mul: kernels.cuh (shared with the LayerNorm epilogue, which applies the forward mask)
 
 // x: (rows, C) with leading dimension ld; the mask index is the DENSE element index row * C + c
 __global__ void train_dropout_kernel(float* __restrict__ x, long long n, int C, int ld, DropArgs d) {
