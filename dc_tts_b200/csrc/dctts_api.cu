@@ -463,7 +463,7 @@ void pack_decode(H* h) {
         for (int c = L.ch0; c < L.ch0 + L.nch; ++c) { P.C[c].off16 = off; off += L.krows * L.ns; }
     }
     P.stream_len = off;
-    // streams: chunk = 8 warp regions, region w = rows [w*kr8, (w+1)*kr8) as [k/4][column][4]
+    // streams: chunk = 8 warp regions, region w = rows [w*kr8, (w+1)*kr8) as [k/4][column][4] (32-column slices: pair-split, below)
     std::vector<float> st((size_t)DEC_NC * off, 0.f);
     for (int li = 0; li < P.nl; ++li) {                              // power-of-two scale per receptive-field block (as pack_tc)
         const LayerDev& l = *nets[li]; const DecLayer& L = P.L[li];
@@ -495,7 +495,11 @@ void pack_decode(H* h) {
                     for (int n = 0; n < L.ns; ++n) {
                         const int col = column(n);
                         if (col < 0) continue;
-                        dst[(size_t)w * kr8 * L.ns + ((size_t)(kk / 4) * L.ns + n) * 4 + (kk % 4)] = wrow[col];
+                        // 32-column slices: pair-split layout per 8-k block [column parity][k-group][column pair][4 k]
+                        // (gemv_warp32); narrower slices: [k/4][column][4]
+                        const size_t idx = L.ns == 32 ? (size_t)(kk / 8) * 256 + ((size_t)((n & 1) * 2 + (kk / 4) % 2) * 16 + (n >> 1)) * 4 + (kk % 4)
+                                                      : ((size_t)(kk / 4) * L.ns + n) * 4 + (kk % 4);
+                        dst[(size_t)w * kr8 * L.ns + idx] = wrow[col];
                     }
                 }
                 if (L.prow <= 1) continue;

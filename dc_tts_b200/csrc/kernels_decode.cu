@@ -226,6 +226,38 @@ __device__ __forceinline__ void gemv_warp(const float* __restrict__ wreg, const 
 }
 
 
+// ---- the same for the 32-column slices (all hc blocks: 16 of the 24) in the PAIR-SPLIT layout ------------------------------
+// The loop above is bound by shared-memory wavefronts: per 8 k a warp reads 8 wavefronts of weights and 2 x GT broadcast
+// loads of the activations (every lane wants the same 8 k of x).  Here a lane owns TWO columns (2cp, 2cp+1) and HALF of the k
+// (kh = lane >> 4 takes k-group 2j + kh), so a step needs ONE activation load per utterance (two addresses per warp, one
+// wavefront) for the same number of FMAs: 8 + GT wavefronts instead of 8 + 2 GT.  Weight layout per 8-k block (1 KB, pack_decode):
+// [column parity][k-group kh][column pair cp][4 k], so both weight loads of a warp are 512 contiguous bytes.  Partial sums of
+// the two k-halves are added with one shuffle per accumulator after the last chunk.
+template <int GT>
+__device__ __forceinline__ void gemv_warp32(const float* __restrict__ wreg, const float* __restrict__ x, int kr8, float2 (&pe)[GT],
+                                            float2 (&po)[GT]) {
+    const int lane = threadIdx.x & 31, cp = lane & 15, kh = lane >> 4;
+    const float* w = wreg + (kh * 16 + cp) * 4;
+    const float* xs = x + kh * 4;
+#pragma unroll 2
+    for (int k = 0; k < kr8; k += 8) {
+        const float4 wa = *reinterpret_cast<const float4*>(w);
+        const float4 wb = *reinterpret_cast<const float4*>(w + 128);
+        w += 256;
+#pragma unroll
+        for (int g = 0; g < GT; ++g) {
+            const float4 xv = *reinterpret_cast<const float4*>(xs + g * XLD + k);
+            float2 a = pe[g], c = po[g];
+            a = __ffma2_rn(make_float2(xv.x, xv.y), make_float2(wa.x, wa.y), a);
+            c = __ffma2_rn(make_float2(xv.x, xv.y), make_float2(wb.x, wb.y), c);
+            a = __ffma2_rn(make_float2(xv.z, xv.w), make_float2(wa.z, wa.w), a);
+            c = __ffma2_rn(make_float2(xv.z, xv.w), make_float2(wb.z, wb.w), c);
+            pe[g] = a; po[g] = c;
+        }
+    }
+}
+
+
 // ---- one block on ONE row per utterance -------------------------------------------------------------------
 // in: S.xin[cb][g] = [taps | current row] of the block's input, S.prm[li&1] = its parameters (both prefetched).
 // out: S.xin[cb^1][g][next_off ..] = the block's output row; this CTA's channel slice appended to the output history.
@@ -251,22 +283,46 @@ __device__ __forceinline__ int layer_row(const DecParams& P, Smem& S, Stream& st
     cp_async_commit();
     LAP(LP_START);
 
-    float acc[GT];
+    if (l.ns == 32) {
+        float2 pe[GT], po[GT];
 #pragma unroll
-    for (int g = 0; g < GT; ++g) acc[g] = 0.f;
-    for (int c = 0; c < l.nch; ++c) {
-        const DecChunk& ch = P.C[l.ch0 + c];
-        const int slot = (int)(st.pos % DEC_NSLOT);
-        mbar_wait(bar64(&S.fullw[slot][warp]), (st.pos / DEC_NSLOT) & 1u);
-        LAP(LP_WAIT);
-        const int kr8 = ch.krows >> 3;
-        gemv_warp<GT>(&S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], kr8, l.ns, acc);
-        LAP(LP_GEMV);
-        warp_release(P, S, st, warp, lane);
-        LAP(LP_RELEASE);
+        for (int g = 0; g < GT; ++g) { pe[g] = make_float2(0.f, 0.f); po[g] = make_float2(0.f, 0.f); }
+        for (int c = 0; c < l.nch; ++c) {
+            const DecChunk& ch = P.C[l.ch0 + c];
+            const int slot = (int)(st.pos % DEC_NSLOT);
+            mbar_wait(bar64(&S.fullw[slot][warp]), (st.pos / DEC_NSLOT) & 1u);
+            LAP(LP_WAIT);
+            const int kr8 = ch.krows >> 3;
+            gemv_warp32<GT>(&S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], kr8, pe, po);
+            LAP(LP_GEMV);
+            warp_release(P, S, st, warp, lane);
+            LAP(LP_RELEASE);
+        }
+#pragma unroll
+        for (int g = 0; g < GT; ++g) {                              // the two k-halves of the warp (lanes l and l ^ 16)
+            float e = pe[g].x + pe[g].y, o = po[g].x + po[g].y;
+            e += __shfl_xor_sync(0xffffffffu, e, 16);
+            o += __shfl_xor_sync(0xffffffffu, o, 16);
+            if (lane < 16) *reinterpret_cast<float2*>(&S.red[g][warp * 32 + 2 * lane]) = make_float2(e, o);
+        }
+    } else {
+        float acc[GT];
+#pragma unroll
+        for (int g = 0; g < GT; ++g) acc[g] = 0.f;
+        for (int c = 0; c < l.nch; ++c) {
+            const DecChunk& ch = P.C[l.ch0 + c];
+            const int slot = (int)(st.pos % DEC_NSLOT);
+            mbar_wait(bar64(&S.fullw[slot][warp]), (st.pos / DEC_NSLOT) & 1u);
+            LAP(LP_WAIT);
+            const int kr8 = ch.krows >> 3;
+            gemv_warp<GT>(&S.ring[slot][warp][0], &S.xin[cb][0][ch.k0 + warp * kr8], kr8, l.ns, acc);
+            LAP(LP_GEMV);
+            warp_release(P, S, st, warp, lane);
+            LAP(LP_RELEASE);
+        }
+#pragma unroll
+        for (int g = 0; g < GT; ++g) S.red[g][tid] = acc[g];
     }
-#pragma unroll
-    for (int g = 0; g < GT; ++g) S.red[g][tid] = acc[g];
     __syncthreads();
     // final sums of the slice (one thread per value) -> staging -> one bulk copy per peer (all-gather through distributed
     // shared memory).  With one utterance the values fit one warp, which then issues the copies without a second block barrier.
