@@ -4,7 +4,7 @@
 // Why: a decode step is 24 dependent conv blocks on one row per utterance; as 46 graph nodes it was
 // bound by kernel boundaries and by split-K round trips through L2 (round 1: ~300 us per step, 1.5 %
 // of any roofline).  Utterances never interact (networks.py:140-153 is batched per row), so a group
-// of G <= 4 utterances is decoded by one thread-block CLUSTER with no grid-level synchronisation:
+// of G <= 5 utterances is decoded by one thread-block CLUSTER with no grid-level synchronisation:
 //
 //   * 16 CTAs per cluster; CTA r owns 1/16 of every block's output channels (for `hc` the same 16
 //     channels of the gate and of the info half, so the highway mix is local).
@@ -16,16 +16,16 @@
 //   * per block: GEMV of the slice on fp32 FMA (exact fp32 arithmetic, as the reference), one block
 //     barrier for the cross-warp reduction, the pre-LN slice goes to every peer with ONE bulk copy
 //     per peer through distributed shared memory, completing on the peer's mbarrier (no hardware
-//     cluster barrier on this path); every CTA then normalises the whole rows redundantly (one warp
-//     per utterance: both LayerNorms, gate, highway mix in registers), so the next block's input is in
-//     local shared memory.  Dilated taps come from the per-layer history in HBM/L2, prefetched one
+//     cluster barrier on this path); every CTA then normalises the whole rows redundantly (LayerNorm
+//     statistics one warp per (utterance, half), gate / highway mix one thread per channel), so the next
+//     block's input is in local shared memory.  Dilated taps come from the per-layer history in HBM/L2, prefetched one
 //     block ahead with cp.async; each CTA appends its channel slice of the new row.
 //   * Quirk Q1: the reference recomputes R under the CURRENT window every step.  While
 //     the window of an utterance does not move, the cached rows are exactly what a recompute would
 //     give.  When it moves, a PRE-PASS refreshes the rows t < j of its AudioDec receptive field
 //     (84/82/76/58/4/2 rows of C_1, HC_2..HC_6) under the new window -- attention one warp per row, a
-//     register-tiled fp32 GEMM per utterance (3 rows x 4 columns per thread, the input rows staged ONCE
-//     per 16-channel slab for all three taps through a 3-stage cp.async pipeline), pre-LN rows through
+//     tcgen05 GEMM per utterance (split-fp16 planes staged per 16-channel slab in the no-swizzle K-major
+//     layout, the three taps being the same slab read through shifted descriptors), pre-LN rows through
 //     an L2 scratch, LayerNorm one warp per row over the whole cluster -- and the ordinary one-row pass
 //     then runs for every utterance.  The pre-pass consumes the same weight chunks a second time: the
 //     stream is "virtual" (frame, segment, chunk) and both the consumer and the refill cursor walk it.

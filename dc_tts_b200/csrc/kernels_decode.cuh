@@ -1,5 +1,5 @@
 // kernels_decode.cuh -- the autoregressive Text2Mel decode loop (reference synthesize.py:45-54) as ONE
-// persistent launch: a 16-CTA thread-block cluster per group of <= 4 utterances walks AudioEnc ->
+// persistent launch: a 16-CTA thread-block cluster per group of <= 5 utterances walks AudioEnc ->
 // Attention -> AudioDec for all mel frames, streaming its slice of the 27 MB of decode weights
 // from L2 through a TMA-bulk ring.  See kernels_decode.cu for the design.
 #pragma once
