@@ -63,7 +63,7 @@ struct ConvArgs {
 };
 
 // Dropout of the training step (modules.py:139 at training=True): a stateless hash of (dense element index, block index, seed) --
-// TF's random stream cannot be reproduced, so the oracle (oracle/ref_train.py: mix32) and the kernels share this one.
+// TF's random stream cannot be reproduced, so the CPU checker and the kernels share this one (mix32).
 struct DropArgs { uint32_t thresh = 0, layer = 0, seed = 0; float scale = 1.f; };   // keep iff mix32(i, layer, seed) >= thresh
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t mix32(uint32_t idx, uint32_t layer, uint32_t seed) {
