@@ -101,12 +101,12 @@ def test_data_parallel_gradient_average_two_ranks_gloo():
 
 
 # ---- overlapped chunked gather: same result as the plain gather, ragged shards included ----
-def _og_worker(rank, world, port, total, q):
+def _og_worker(rank, world, port, total, q, chunks=4):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from dc_tts_b200.parallel import OverlappedGather
-        og = OverlappedGather(total, (3, 5), torch.float32, "cpu", chunks=4)
+        og = OverlappedGather(total, (3, 5), torch.float32, "cpu", chunks=chunks)
         lo, hi = shard_bounds(total, rank, world)
         for step in range(2):                                   # the receive buffer is reused across steps
             og.begin()
@@ -128,12 +128,12 @@ def _og_worker(rank, world, port, total, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("total", [16, 7, 2])
-def test_overlapped_gather_two_ranks_gloo(total):
+@pytest.mark.parametrize("total,chunks", [(16, 4), (7, 4), (2, 4), (16, 1)])      # one chunk = bench.py's choice up to 4 GPUs
+def test_overlapped_gather_two_ranks_gloo(total, chunks):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29300 + os.getpid() % 300 + total
-    procs = [ctx.Process(target=_og_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    port = 29300 + os.getpid() % 300 + total + 40 * chunks
+    procs = [ctx.Process(target=_og_worker, args=(r, 2, port, total, q, chunks)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
