@@ -131,6 +131,29 @@ def _tie_free(P):
     return P
 
 
+def _t2m_relu_margin(P, B, rate, seed):
+    """Smallest |pre-activation| over every ReLU block of the oracle's Text2Mel training forward."""
+    L, mels = _batch(B)
+    T = {n: torch.tensor(np.asarray(P[n], np.float32)) for n in rtr.text2mel_names()}
+    seen, orig = [], torch.relu
+    torch.relu = lambda z: (seen.append(float(z.detach().abs().min())), orig(z))[1]
+    try:
+        with torch.no_grad():
+            rtr.forward(T, L, mels, seed, rate)
+    finally:
+        torch.relu = orig
+    assert len(seen) == 6                                   # TextEnc C_2, AudioEnc C_1 C_2, AudioDec C_8 C_9 C_10
+    return min(seen)
+
+
+def test_tie_free_set_has_no_relu_near_zero():
+    """The premise of the tensor-core gradient-parity cases: on the plain set some ReLU pre-activation sits within the forward
+    noise of zero (so a correct fp32-grade forward may flip its mask), on the tie-free set none comes closer than 1."""
+    P = init_params(0, "perturbed")
+    assert _t2m_relu_margin(P, 2, 0.05, 11) < 1e-4
+    assert _t2m_relu_margin(_tie_free(P), 2, 0.05, 11) > 1.0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,rate,seed,tc", [(2, 0.0, 0, 7), (2, 0.05, 11, 7), (3, 0.05, 4, 7), (2, 0.0, 0, 0), (2, 0.05, 11, 0), (3, 0.05, 4, 0),
                                             (32, 0.05, 5, 7)])
